@@ -1,0 +1,159 @@
+/*
+ * semigcn_b200 -- C-ABI of the B200 (sm_100a) graph-convolution hot path of SeMIGCN.
+ *
+ * Drop-in boundary: the reference reaches this arithmetic through three
+ * torch_geometric symbols -- `from torch_geometric.nn import GCNConv, ChebConv, Sequential`
+ * (reference util/networks.py:4, util/meshnet.py:6).  The Python host layer
+ * (semigcn_b200/nn.py) re-exposes those classes; every FLOP and byte they move goes through
+ * the entry points below, loaded with ctypes.
+ *
+ * Conventions
+ *   - plain pointers + sizes; every pointer is a DEVICE pointer unless the name ends in
+ *     `_host`; the caller owns every buffer, including workspaces (the library allocates
+ *     nothing);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no internal
+ *     synchronisation -> CUDA-graph capturable;
+ *   - return 0 on success, a negative SGB_E* code otherwise; never throws, never exits;
+ *     `sgb_last_error()` returns a thread-local message for the last failing call;
+ *   - all matrices are dense row-major fp32 with an explicit leading dimension (elements);
+ *   - deterministic: no floating-point atomics anywhere (integer atomics only in the
+ *     one-off graph builder, whose output is order-independent).
+ */
+#ifndef SEMIGCN_B200_H
+#define SEMIGCN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SGB_API __attribute__((visibility("default")))
+#else
+#define SGB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGB_VERSION 100
+
+#define SGB_OK 0
+#define SGB_EINVAL (-1)   /* bad argument (null pointer, negative size, bad enum, alignment) */
+#define SGB_ECUDA (-2)    /* a CUDA runtime call / kernel launch failed                       */
+#define SGB_ENOSPC (-3)   /* caller-provided workspace too small                              */
+#define SGB_ENOTSUP (-4)  /* shape not supported by this entry point                          */
+
+/* normalisation modes (which PyG operator the sparse matrix stands for) */
+#define SGB_MODE_GCN 0  /* D~^-1/2 (A+I) D~^-1/2, degree over targets (+1 self loop); replaces
+                           torch_geometric gcn_norm as called by GCNConv (util/networks.py:25) */
+#define SGB_MODE_CHEB 1 /* -D^-1/2 A D^-1/2 with the explicit (+x_i, -x_i) loop pair of
+                           ChebConv.__norm__ (util/networks.py:42), degree over sources        */
+#define SGB_MODE_ADJ 2  /* plain adjacency sum (weights 1, no loops): mesh_laplacian_loss
+                           (util/loss.py:60-76), mask dilation (util/datamaker.py:124-127)    */
+
+SGB_API int sgb_version(void);
+SGB_API const char* sgb_last_error(void);
+/* number of SMs of the current device (used by callers to size stat-partial buffers) */
+SGB_API int sgb_num_sms(void);
+
+/* ------------------------------------------------------------------------------------ *
+ * 1. Graph builder: edge_index[2, nnz] (int64, row 0 = sources, row 1 = targets)
+ *    -> CSR grouped by target (transpose = 0; forward aggregation) or by source
+ *    (transpose = 1; backward aggregation), STABLE in edge order inside each row, self
+ *    loops removed (GCN re-adds exactly one per vertex implicitly), plus dis[i] =
+ *    1/sqrt(deg_i) computed as IEEE div(1, sqrt(deg)) -- bit-exact against torch-CPU
+ *    `deg.pow_(-0.5)`; deg = 0 -> 0.
+ *    Replaces: gcn_norm / get_laplacian / add_remaining_self_loops executed inside every
+ *    GCNConv / ChebConv forward; input contract util/mesh.py:229-230.
+ *    perm[e] = slot of edge e in colidx, or -1 for a dropped self loop.
+ *    err_flag (device int32[1], zero-initialised by the call): 1 if an index was outside
+ *    [0, n).
+ * ------------------------------------------------------------------------------------ */
+SGB_API size_t sgb_graph_build_workspace_bytes(int64_t nnz, int64_t n);
+SGB_API int sgb_graph_build(const int64_t* edge_index, int64_t nnz, int64_t n, int mode, int transpose,
+                    int32_t* rowptr /* [n+1] */, int32_t* colidx /* [nnz] */, float* dis /* [n] */,
+                    int32_t* perm /* [nnz] or NULL */, int32_t* err_flag /* [1] */,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------ *
+ * 2. SpMM: Y = alpha * (S f(X)) + beta * ADDEND + bias, row-parallel gather, one
+ *    sub-warp per vertex, 128-bit loads, atomic-free; S is defined by (rowptr, colidx,
+ *    dis, mode); accumulation order per row = CSR order then the self-loop term(s), with
+ *    separately rounded multiply and add -- the op order of PyG's message/aggregate
+ *    (SURVEY.md A.1 step 3, A.6), so the result is bit-identical to the CPU path.
+ *    f (optional, in_scale != NULL): per-channel affine + LeakyReLU applied to every
+ *    gathered element, f(x) = lrelu(x * in_scale[c] + in_shift[c], slope): the fused
+ *    BatchNorm1d + LeakyReLU of the previous block (util/networks.py:26-27).
+ *    stat_partials (optional): per-CTA column sums of Y and Y^2, laid out
+ *    [sgb_spmm_stat_rows(n, c)][2][c]; feeds sgb_bn_finalize.
+ *    Replaces MessagePassing.propagate (index_select -> mul -> scatter_add), fwd and,
+ *    called with the transpose CSR, bwd.
+ * ------------------------------------------------------------------------------------ */
+SGB_API int sgb_spmm_stat_rows(int64_t n, int c);
+SGB_API int sgb_spmm(const int32_t* rowptr, const int32_t* colidx, const float* dis, int mode,
+             const float* x, int64_t ldx, int64_t n, int c,
+             const float* in_scale, const float* in_shift, float slope,
+             float alpha, const float* addend, int64_t ld_addend, float beta,
+             const float* bias, float* y, int64_t ldy, float* stat_partials, void* stream);
+
+/* ------------------------------------------------------------------------------------ *
+ * 3. Dense feature transform (the per-layer `lin` of GCNConv / `lins[k]` of ChebConv,
+ *    nn.Linear of util/networks.py:35,52,58-61) and its two gradients.
+ *    sgb_gemm:       C[m,n] (+)= f(A)[m,k] * op(B) + bias,  op(B) = B^T for transb=1
+ *                    (B is [n,k], i.e. a torch Linear weight) or B for transb=0 (B is [k,n]).
+ *                    f = optional per-k-channel affine + LeakyReLU on A (as in sgb_spmm).
+ *                    stat_partials: [sgb_gemm_stat_rows(m)][2][n] column sums of C, C^2.
+ *    sgb_gemm_tn:    D[n,k] (+)= G[m,n]^T * A[m,k]   (weight gradient; split over m with a
+ *                    fixed-order two-stage reduction -> deterministic).
+ *    sgb_colsum:     out[n] (+)= sum_m G[m,n]        (bias gradient).
+ *    `engine`: 0 = auto, 1 = fp32 CUDA-core tiles, 2 = tcgen05 3xTF32 tensor-core tiles
+ *    (error-compensated: hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM).
+ * ------------------------------------------------------------------------------------ */
+SGB_API int sgb_gemm_stat_rows(int64_t m);
+SGB_API int sgb_gemm(int transb, const float* a, int64_t lda, const float* b, int64_t ldb,
+             float* c, int64_t ldc, int64_t m, int n, int k,
+             const float* a_scale, const float* a_shift, float slope,
+             const float* bias, int accumulate, float* stat_partials, int engine, void* stream);
+SGB_API size_t sgb_gemm_tn_workspace_bytes(int64_t m, int n, int k);
+SGB_API int sgb_gemm_tn(const float* g, int64_t ldg, const float* a, int64_t lda, float* d, int64_t ldd,
+                int64_t m, int n, int k, int accumulate, void* workspace, size_t workspace_bytes,
+                int engine, void* stream);
+SGB_API size_t sgb_colsum_workspace_bytes(int64_t m, int n);
+SGB_API int sgb_colsum(const float* g, int64_t ldg, int64_t m, int n, float* out, int accumulate,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------ *
+ * 4. BatchNorm1d (batch statistics over all vertices) + LeakyReLU, forward and backward.
+ *    Replaces nn.BatchNorm1d + nn.LeakyReLU between convs (util/networks.py:26-27,43-44).
+ *    sgb_col_stats      : partials[rows][2][c] of (sum, sum of squares) for a matrix that was
+ *                         not produced by one of our kernels.
+ *    sgb_bn_finalize    : fp64 reduction of the partials -> mean, invstd (biased var, eps),
+ *                         scale = gamma*invstd, shift = beta - mean*scale; updates running
+ *                         stats (momentum, unbiased var) when running_mean != NULL.
+ *    sgb_bn_act_apply   : Z = lrelu(Y*scale + shift, slope).
+ *    sgb_bn_act_bwd_reduce / _apply : dY from dZ (two-pass: per-channel sums, then apply).
+ * ------------------------------------------------------------------------------------ */
+SGB_API int sgb_col_stat_rows(int64_t m, int c);
+SGB_API int sgb_col_stats(const float* y, int64_t ldy, int64_t m, int c, float* partials, void* stream);
+SGB_API int sgb_bn_finalize(const float* partials, int rows, int c, int64_t count,
+                    const float* gamma, const float* beta, float eps, float momentum,
+                    float* running_mean, float* running_var,
+                    float* mean, float* invstd, float* scale, float* shift, void* stream);
+SGB_API int sgb_bn_act_apply(const float* y, int64_t ldy, int64_t m, int c, const float* scale,
+                     const float* shift, float slope, float* z, int64_t ldz, void* stream);
+/* partials[rows][2][c]: (sum dA, sum dA*xhat) with dA = dZ * lrelu'(Y*scale+shift) */
+SGB_API int sgb_bn_act_bwd_reduce(const float* dz, int64_t lddz, const float* y, int64_t ldy, int64_t m, int c,
+                          const float* scale, const float* shift, const float* mean, const float* invstd,
+                          float slope, float* partials, void* stream);
+/* sums[2][c] = fp64-reduced partials (as float); dY = scale * (dA - sum0/m - xhat*sum1/m);
+ * also emits dgamma = sums[1], dbeta = sums[0] (accumulating when accumulate != 0).      */
+SGB_API int sgb_bn_bwd_finalize(const float* partials, int rows, int c, float* sums, float* dgamma,
+                        float* dbeta, int accumulate, void* stream);
+SGB_API int sgb_bn_act_bwd_apply(const float* dz, int64_t lddz, const float* y, int64_t ldy, int64_t m, int c,
+                         const float* scale, const float* shift, const float* mean, const float* invstd,
+                         const float* sums, float slope, int training, float* dy, int64_t lddy, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEMIGCN_B200_H */

@@ -1,0 +1,364 @@
+// BatchNorm1d (batch statistics over all vertices) + LeakyReLU, forward and backward, and the
+// generic deterministic column reductions they share (also used for bias gradients).
+//
+// Replaces nn.BatchNorm1d(h) + nn.LeakyReLU() between the convs (util/networks.py:26-27,
+// 43-44; util/meshnet.py:41-42) -- in the reference 2 reductions + 1 elementwise pass forward
+// and the mirror image backward, each a separate ATen kernel.  Here the forward statistics
+// normally arrive as per-CTA partials from the producing SpMM / GEMM epilogue; this file
+// holds the fp64 finalisation, the stand-alone column-statistics kernel for foreign inputs,
+// and the elementwise apply / backward kernels.  All HBM-bound streaming kernels, float4.
+#include "common.cuh"
+
+namespace sgb {
+
+constexpr int kColThreads = 256;
+
+enum ColOp { COL_STATS = 0, COL_BN_BWD = 1, COL_SUM = 2 };
+
+struct ColArgs {
+    const float* y; int64_t ldy;        // STATS: matrix; BN_BWD: Y (pre-BN conv output); SUM: matrix
+    const float* dz; int64_t lddz;      // BN_BWD: upstream gradient
+    int64_t m; int c;
+    const float* scale; const float* shift; const float* mean; const float* invstd;
+    float slope;
+    float* partials;                    // [gridDim.x][2][c]
+};
+
+// One thread owns VEC channels of one row-lane; rows are grid-strided; fixed-order smem
+// reduction over the row-lanes of the CTA at the end.
+template <int OP, int VEC>
+__global__ void __launch_bounds__(kColThreads) k_col_reduce(const ColArgs a, int tpr /* threads per row, pow2 <= 256 */) {
+    __shared__ float red[2][kColThreads * VEC];
+    const int cl = threadIdx.x % tpr;
+    const int rl = threadIdx.x / tpr;
+    const int rows_per_pass = kColThreads / tpr;
+    for (int c0 = 0; c0 < a.c; c0 += tpr * VEC) {
+        const int ch = c0 + cl * VEC;
+        const bool act = ch < a.c;
+        double s1[VEC], s2[VEC];   // fp64 running sums: hundreds of rows per thread
+        float sc[VEC], sh[VEC], mu[VEC], is[VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+            s1[q] = 0.0; s2[q] = 0.0;
+            sc[q] = 1.f; sh[q] = 0.f; mu[q] = 0.f; is[q] = 1.f;
+            if (OP == COL_BN_BWD && act) {
+                sc[q] = __ldg(a.scale + ch + q); sh[q] = __ldg(a.shift + ch + q);
+                mu[q] = __ldg(a.mean + ch + q);  is[q] = __ldg(a.invstd + ch + q);
+            }
+        }
+        if (act) {
+            for (int64_t r = (int64_t)blockIdx.x * rows_per_pass + rl; r < a.m; r += (int64_t)gridDim.x * rows_per_pass) {
+                float yv[VEC], dv[VEC];
+                if (VEC == 4) {
+                    float4 t = ldg4(a.y + r * a.ldy + ch);
+                    yv[0] = t.x; yv[1] = t.y; yv[2] = t.z; yv[3] = t.w;
+                    if (OP == COL_BN_BWD) {
+                        float4 u = ldg4(a.dz + r * a.lddz + ch);
+                        dv[0] = u.x; dv[1] = u.y; dv[2] = u.z; dv[3] = u.w;
+                    }
+                } else {
+                    yv[0] = __ldg(a.y + r * a.ldy + ch);
+                    if (OP == COL_BN_BWD) dv[0] = __ldg(a.dz + r * a.lddz + ch);
+                }
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) {
+                    if (OP == COL_STATS) {
+                        s1[q] += (double)yv[q];
+                        s2[q] += (double)yv[q] * (double)yv[q];
+                    } else if (OP == COL_SUM) {
+                        s1[q] += (double)yv[q];
+                    } else {
+                        const float pre = fmaf(yv[q], sc[q], sh[q]);
+                        const float da = pre > 0.f ? dv[q] : dv[q] * a.slope;
+                        const float xh = (yv[q] - mu[q]) * is[q];
+                        s1[q] += (double)da;
+                        s2[q] += (double)da * (double)xh;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+            red[0][(rl * tpr + cl) * VEC + q] = (float)s1[q];
+            red[1][(rl * tpr + cl) * VEC + q] = (float)s2[q];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < tpr * VEC; i += kColThreads) {
+            if (c0 + i < a.c) {
+                float t1 = 0.f, t2 = 0.f;
+                for (int r = 0; r < rows_per_pass; ++r) {
+                    t1 += red[0][r * tpr * VEC + i];
+                    t2 += red[1][r * tpr * VEC + i];
+                }
+                a.partials[((int64_t)blockIdx.x * 2 + 0) * a.c + c0 + i] = t1;
+                a.partials[((int64_t)blockIdx.x * 2 + 1) * a.c + c0 + i] = t2;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static int col_tpr(int c, int vec) {
+    int lanes = (c + vec - 1) / vec;
+    int p = 1;
+    while (p < lanes && p < kColThreads) p <<= 1;
+    return p;
+}
+
+static int col_rows_cfg(int64_t m, int c, int vec) {
+    int tpr = col_tpr(c, vec);
+    int rpp = kColThreads / tpr;
+    int64_t need = ceil_div(m > 0 ? m : 1, (int64_t)rpp * 4);   // >= 4 rows per row-lane
+    int64_t cap = (int64_t)num_sms() * 4;
+    int64_t g = need < cap ? need : cap;
+    return (int)(g < 1 ? 1 : g);
+}
+
+static int col_rows(int64_t m, int c) {
+    int g4 = col_rows_cfg(m, c, 4), g1 = col_rows_cfg(m, c, 1);
+    return g4 > g1 ? g4 : g1;
+}
+
+template <int OP>
+static int col_launch(const ColArgs& a, bool vec_ok, cudaStream_t stream) {
+    int vec = (a.c % 4 == 0 && vec_ok) ? 4 : 1;
+    int grid = col_rows_cfg(a.m, a.c, vec);
+    int rows = col_rows(a.m, a.c);
+    if (rows > grid)
+        if (cudaMemsetAsync(a.partials + (size_t)grid * 2 * a.c, 0, (size_t)(rows - grid) * 2 * a.c * sizeof(float), stream) != cudaSuccess) {
+            set_error("col_reduce: memset failed");
+            return SGB_ECUDA;
+        }
+    int tpr = col_tpr(a.c, vec);
+    if (vec == 4) k_col_reduce<OP, 4><<<grid, kColThreads, 0, stream>>>(a, tpr);
+    else k_col_reduce<OP, 1><<<grid, kColThreads, 0, stream>>>(a, tpr);
+    SGB_CHECK_LAUNCH("k_col_reduce");
+    return SGB_OK;
+}
+
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---- fp64 finalisation of [rows][2][c] partials: 32 channels x 32 row-lanes per CTA ----
+struct FinArgs {
+    const float* partials; int rows; int c; int64_t count;
+    const float* gamma; const float* beta; float eps; float momentum;
+    float* running_mean; float* running_var;
+    float* mean; float* invstd; float* scale; float* shift;   // BN forward outputs
+    float* sums; float* dgamma; float* dbeta; int accumulate; // BN backward / colsum outputs
+    int kind;                                                  // 0 = BN fwd, 1 = BN bwd sums, 2 = column sum
+};
+
+__global__ void __launch_bounds__(1024) k_finalize(const FinArgs f) {
+    __shared__ double r1[32][33], r2[32][33];
+    const int ch = blockIdx.x * 32 + threadIdx.x;
+    double s1 = 0.0, s2 = 0.0;
+    if (ch < f.c) {
+        for (int r = threadIdx.y; r < f.rows; r += 32) {
+            s1 += (double)__ldg(f.partials + ((int64_t)r * 2 + 0) * f.c + ch);
+            s2 += (double)__ldg(f.partials + ((int64_t)r * 2 + 1) * f.c + ch);
+        }
+    }
+    r1[threadIdx.y][threadIdx.x] = s1;
+    r2[threadIdx.y][threadIdx.x] = s2;
+    __syncthreads();
+    if (threadIdx.y == 0 && ch < f.c) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int r = 0; r < 32; ++r) { t1 += r1[r][threadIdx.x]; t2 += r2[r][threadIdx.x]; }
+        if (f.kind == 0) {
+            const double n = (double)f.count;
+            const double mean = t1 / n;
+            double var = t2 / n - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const double invstd = 1.0 / sqrt(var + (double)f.eps);
+            const double g = f.gamma ? (double)f.gamma[ch] : 1.0;
+            const double b = f.beta ? (double)f.beta[ch] : 0.0;
+            f.mean[ch] = (float)mean;
+            f.invstd[ch] = (float)invstd;
+            const float scale = (float)(g * invstd);
+            f.scale[ch] = scale;
+            f.shift[ch] = (float)(b - mean * (double)scale);
+            if (f.running_mean) {
+                const double unb = n > 1.0 ? var * n / (n - 1.0) : var;
+                f.running_mean[ch] = (float)((1.0 - f.momentum) * (double)f.running_mean[ch] + f.momentum * mean);
+                f.running_var[ch] = (float)((1.0 - f.momentum) * (double)f.running_var[ch] + f.momentum * unb);
+            }
+        } else if (f.kind == 1) {
+            f.sums[ch] = (float)t1;
+            f.sums[f.c + ch] = (float)t2;
+            if (f.dbeta) f.dbeta[ch] = f.accumulate ? f.dbeta[ch] + (float)t1 : (float)t1;
+            if (f.dgamma) f.dgamma[ch] = f.accumulate ? f.dgamma[ch] + (float)t2 : (float)t2;
+        } else {
+            f.sums[ch] = f.accumulate ? f.sums[ch] + (float)t1 : (float)t1;
+        }
+    }
+}
+
+// ---- elementwise ------------------------------------------------------------------------
+template <int VEC>
+__global__ void k_bn_act_apply(const float* __restrict__ y, int64_t ldy, int64_t m, int c, const float* __restrict__ scale,
+                               const float* __restrict__ shift, float slope, float* __restrict__ z, int64_t ldz) {
+    const int cv = c / VEC;
+    const int64_t total = m * cv;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cv;
+        const int ch = (int)(i % cv) * VEC;
+        if (VEC == 4) {
+            const float4 v = ldg4(y + r * ldy + ch), s = ldg4(scale + ch), b = ldg4(shift + ch);
+            float4 o;
+            o.x = lrelu(fmaf(v.x, s.x, b.x), slope); o.y = lrelu(fmaf(v.y, s.y, b.y), slope);
+            o.z = lrelu(fmaf(v.z, s.z, b.z), slope); o.w = lrelu(fmaf(v.w, s.w, b.w), slope);
+            st4(z + r * ldz + ch, o);
+        } else {
+            z[r * ldz + ch] = lrelu(fmaf(__ldg(y + r * ldy + ch), __ldg(scale + ch), __ldg(shift + ch)), slope);
+        }
+    }
+}
+
+struct BwdArgs {
+    const float* dz; int64_t lddz; const float* y; int64_t ldy; int64_t m; int c;
+    const float* scale; const float* shift; const float* mean; const float* invstd; const float* sums;
+    float slope; int training; float* dy; int64_t lddy;
+};
+
+template <int VEC>
+__global__ void k_bn_act_bwd_apply(const BwdArgs a) {
+    const int cv = a.c / VEC;
+    const int64_t total = a.m * cv;
+    const float inv_m = 1.0f / (float)a.m;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cv;
+        const int ch = (int)(i % cv) * VEC;
+        float yv[VEC], dv[VEC], out[VEC];
+        if (VEC == 4) {
+            float4 t = ldg4(a.y + r * a.ldy + ch), u = ldg4(a.dz + r * a.lddz + ch);
+            yv[0] = t.x; yv[1] = t.y; yv[2] = t.z; yv[3] = t.w;
+            dv[0] = u.x; dv[1] = u.y; dv[2] = u.z; dv[3] = u.w;
+        } else {
+            yv[0] = __ldg(a.y + r * a.ldy + ch);
+            dv[0] = __ldg(a.dz + r * a.lddz + ch);
+        }
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+            const float sc = __ldg(a.scale + ch + q), sh = __ldg(a.shift + ch + q);
+            const float pre = fmaf(yv[q], sc, sh);
+            const float da = pre > 0.f ? dv[q] : dv[q] * a.slope;
+            if (a.training) {
+                const float xh = (yv[q] - __ldg(a.mean + ch + q)) * __ldg(a.invstd + ch + q);
+                const float sb = __ldg(a.sums + ch + q) * inv_m, sg = __ldg(a.sums + a.c + ch + q) * inv_m;
+                out[q] = sc * (da - sb - xh * sg);
+            } else {
+                out[q] = sc * da;
+            }
+        }
+        if (VEC == 4) st4(a.dy + r * a.lddy + ch, make_float4(out[0], out[1], out[2], out[3]));
+        else a.dy[r * a.lddy + ch] = out[0];
+    }
+}
+
+static int ew_grid(int64_t total) {
+    int64_t g = ceil_div(total > 0 ? total : 1, 256);
+    int64_t cap = (int64_t)num_sms() * 16;
+    return (int)(g < cap ? g : cap);
+}
+
+}  // namespace sgb
+
+using namespace sgb;
+
+extern "C" int sgb_col_stat_rows(int64_t m, int c) {
+    if (m < 0 || c <= 0) return 0;
+    return col_rows(m, c);
+}
+
+extern "C" int sgb_col_stats(const float* y, int64_t ldy, int64_t m, int c, float* partials, void* stream) {
+    SGB_CHECK_ARG(y && partials && m >= 0 && c > 0 && ldy >= c, "sgb_col_stats: bad argument");
+    ColArgs a{};
+    a.y = y; a.ldy = ldy; a.m = m; a.c = c; a.partials = partials;
+    return col_launch<COL_STATS>(a, al16(y) && ldy % 4 == 0, (cudaStream_t)stream);
+}
+
+extern "C" int sgb_bn_finalize(const float* partials, int rows, int c, int64_t count, const float* gamma, const float* beta,
+                               float eps, float momentum, float* running_mean, float* running_var, float* mean, float* invstd,
+                               float* scale, float* shift, void* stream) {
+    SGB_CHECK_ARG(partials && rows > 0 && c > 0 && count > 0 && mean && invstd && scale && shift, "sgb_bn_finalize: bad argument");
+    SGB_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "sgb_bn_finalize: running stats must come together");
+    FinArgs f{};
+    f.partials = partials; f.rows = rows; f.c = c; f.count = count; f.gamma = gamma; f.beta = beta; f.eps = eps;
+    f.momentum = momentum; f.running_mean = running_mean; f.running_var = running_var;
+    f.mean = mean; f.invstd = invstd; f.scale = scale; f.shift = shift; f.kind = 0;
+    k_finalize<<<(c + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(f);
+    SGB_CHECK_LAUNCH("k_finalize");
+    return SGB_OK;
+}
+
+extern "C" int sgb_bn_act_apply(const float* y, int64_t ldy, int64_t m, int c, const float* scale, const float* shift, float slope,
+                                float* z, int64_t ldz, void* stream) {
+    SGB_CHECK_ARG(y && z && scale && shift && m >= 0 && c > 0 && ldy >= c && ldz >= c, "sgb_bn_act_apply: bad argument");
+    if (m == 0) return SGB_OK;
+    bool vec = c % 4 == 0 && al16(y) && al16(z) && al16(scale) && al16(shift) && ldy % 4 == 0 && ldz % 4 == 0;
+    if (vec) k_bn_act_apply<4><<<ew_grid(m * (c / 4)), 256, 0, (cudaStream_t)stream>>>(y, ldy, m, c, scale, shift, slope, z, ldz);
+    else k_bn_act_apply<1><<<ew_grid(m * c), 256, 0, (cudaStream_t)stream>>>(y, ldy, m, c, scale, shift, slope, z, ldz);
+    SGB_CHECK_LAUNCH("k_bn_act_apply");
+    return SGB_OK;
+}
+
+extern "C" int sgb_bn_act_bwd_reduce(const float* dz, int64_t lddz, const float* y, int64_t ldy, int64_t m, int c, const float* scale,
+                                     const float* shift, const float* mean, const float* invstd, float slope, float* partials,
+                                     void* stream) {
+    SGB_CHECK_ARG(dz && y && scale && shift && mean && invstd && partials && m >= 0 && c > 0 && ldy >= c && lddz >= c,
+                  "sgb_bn_act_bwd_reduce: bad argument");
+    ColArgs a{};
+    a.y = y; a.ldy = ldy; a.dz = dz; a.lddz = lddz; a.m = m; a.c = c;
+    a.scale = scale; a.shift = shift; a.mean = mean; a.invstd = invstd; a.slope = slope; a.partials = partials;
+    return col_launch<COL_BN_BWD>(a, al16(y) && al16(dz) && ldy % 4 == 0 && lddz % 4 == 0, (cudaStream_t)stream);
+}
+
+extern "C" int sgb_bn_bwd_finalize(const float* partials, int rows, int c, float* sums, float* dgamma, float* dbeta, int accumulate,
+                                   void* stream) {
+    SGB_CHECK_ARG(partials && rows > 0 && c > 0 && sums, "sgb_bn_bwd_finalize: bad argument");
+    FinArgs f{};
+    f.partials = partials; f.rows = rows; f.c = c; f.sums = sums; f.dgamma = dgamma; f.dbeta = dbeta; f.accumulate = accumulate;
+    f.kind = 1;
+    k_finalize<<<(c + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(f);
+    SGB_CHECK_LAUNCH("k_finalize");
+    return SGB_OK;
+}
+
+extern "C" int sgb_bn_act_bwd_apply(const float* dz, int64_t lddz, const float* y, int64_t ldy, int64_t m, int c, const float* scale,
+                                    const float* shift, const float* mean, const float* invstd, const float* sums, float slope,
+                                    int training, float* dy, int64_t lddy, void* stream) {
+    SGB_CHECK_ARG(dz && y && dy && scale && shift && m >= 0 && c > 0 && ldy >= c && lddz >= c && lddy >= c,
+                  "sgb_bn_act_bwd_apply: bad argument");
+    SGB_CHECK_ARG(!training || (mean && invstd && sums), "sgb_bn_act_bwd_apply: training mode needs mean/invstd/sums");
+    if (m == 0) return SGB_OK;
+    BwdArgs a{dz, lddz, y, ldy, m, c, scale, shift, mean, invstd, sums, slope, training, dy, lddy};
+    bool vec = c % 4 == 0 && al16(y) && al16(dz) && al16(dy) && ldy % 4 == 0 && lddz % 4 == 0 && lddy % 4 == 0;
+    if (vec) k_bn_act_bwd_apply<4><<<ew_grid(m * (c / 4)), 256, 0, (cudaStream_t)stream>>>(a);
+    else k_bn_act_bwd_apply<1><<<ew_grid(m * c), 256, 0, (cudaStream_t)stream>>>(a);
+    SGB_CHECK_LAUNCH("k_bn_act_bwd_apply");
+    return SGB_OK;
+}
+
+extern "C" size_t sgb_colsum_workspace_bytes(int64_t m, int n) {
+    if (m < 0 || n <= 0) return 0;
+    return (size_t)col_rows(m, n) * 2 * n * sizeof(float);
+}
+
+extern "C" int sgb_colsum(const float* g, int64_t ldg, int64_t m, int n, float* out, int accumulate, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+    SGB_CHECK_ARG(g && out && m >= 0 && n > 0 && ldg >= n, "sgb_colsum: bad argument");
+    size_t need = sgb_colsum_workspace_bytes(m, n);
+    if (!workspace || workspace_bytes < need) {
+        set_error("sgb_colsum: workspace %zu < required %zu", workspace_bytes, need);
+        return SGB_ENOSPC;
+    }
+    ColArgs a{};
+    a.y = g; a.ldy = ldg; a.m = m; a.c = n; a.partials = (float*)workspace;
+    int rc = col_launch<COL_SUM>(a, al16(g) && ldg % 4 == 0, (cudaStream_t)stream);
+    if (rc != SGB_OK) return rc;
+    FinArgs f{};
+    f.partials = (const float*)workspace; f.rows = col_rows(m, n); f.c = n; f.sums = out; f.accumulate = accumulate; f.kind = 2;
+    k_finalize<<<(n + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(f);
+    SGB_CHECK_LAUNCH("k_finalize");
+    return SGB_OK;
+}

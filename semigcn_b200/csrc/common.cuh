@@ -1,0 +1,61 @@
+// Shared helpers for the semigcn_b200 C-ABI library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/semigcn_b200.h"
+
+namespace sgb {
+
+void set_error(const char* fmt, ...);   // thread-local message (api.cu)
+int num_sms();                           // cached per process (api.cu)
+
+#define SGB_CHECK_ARG(cond, ...)                 \
+    do {                                         \
+        if (!(cond)) {                           \
+            sgb::set_error(__VA_ARGS__);         \
+            return SGB_EINVAL;                   \
+        }                                        \
+    } while (0)
+
+#define SGB_CHECK_LAUNCH(name)                                                        \
+    do {                                                                              \
+        cudaError_t e__ = cudaGetLastError();                                         \
+        if (e__ != cudaSuccess) {                                                     \
+            sgb::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));   \
+            return SGB_ECUDA;                                                         \
+        }                                                                             \
+    } while (0)
+
+#define SGB_CUDA(call)                                                                \
+    do {                                                                              \
+        cudaError_t e__ = (call);                                                     \
+        if (e__ != cudaSuccess) {                                                     \
+            sgb::set_error("%s failed: %s", #call, cudaGetErrorString(e__));          \
+            return SGB_ECUDA;                                                         \
+        }                                                                             \
+    } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+// streaming 128-bit load/store helpers (read-only path; Y/Z outputs are written once)
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// arguments of the dense transform C (+)= f(A) op(B) + bias (see sgb_gemm)
+struct GemmArgs {
+    int transb;
+    const float* a; int64_t lda;
+    const float* b; int64_t ldb;
+    float* c; int64_t ldc;
+    int64_t m; int n; int k;
+    const float* a_scale; const float* a_shift; float slope;
+    const float* bias; int accumulate; float* stat_partials;
+};
+
+}  // namespace sgb

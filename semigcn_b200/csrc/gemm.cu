@@ -1,0 +1,47 @@
+// C-ABI entry points of the dense feature transform; dispatch between the fp32 CUDA-core
+// tiles (gemm_simt.cu) and the tcgen05 3xTF32 tiles (gemm_tc.cu).
+#include "common.cuh"
+
+namespace sgb {
+int gemm_simt_launch(const GemmArgs& g, cudaStream_t stream);
+int gemm_tn_simt_launch(const float* g, int64_t ldg, const float* a, int64_t lda, float* d, int64_t ldd, int64_t m, int n, int k,
+                        int accumulate, void* ws, size_t ws_bytes, cudaStream_t stream);
+size_t gemm_tn_simt_workspace(int64_t m, int n, int k);
+}  // namespace sgb
+
+using namespace sgb;
+
+extern "C" int sgb_gemm_stat_rows(int64_t m) { return m <= 0 ? 0 : (int)ceil_div(m, 128); }
+
+extern "C" int sgb_gemm(int transb, const float* a, int64_t lda, const float* b, int64_t ldb, float* c, int64_t ldc, int64_t m,
+                        int n, int k, const float* a_scale, const float* a_shift, float slope, const float* bias, int accumulate,
+                        float* stat_partials, int engine, void* stream) {
+    SGB_CHECK_ARG(a && b && c && m >= 0 && n > 0 && k > 0, "sgb_gemm: bad argument m=%lld n=%d k=%d", (long long)m, n, k);
+    SGB_CHECK_ARG(lda >= k && ldc >= n && ldb >= (transb ? k : n), "sgb_gemm: leading dimension too small");
+    SGB_CHECK_ARG((a_scale == nullptr) == (a_shift == nullptr), "sgb_gemm: a_scale / a_shift must come together");
+    SGB_CHECK_ARG(engine >= 0 && engine <= 2, "sgb_gemm: bad engine %d", engine);
+    if (m == 0) return SGB_OK;
+    GemmArgs g{transb, a, lda, b, ldb, c, ldc, m, n, k, a_scale, a_shift, slope, bias, accumulate, stat_partials};
+    if (engine == 2) {
+        set_error("sgb_gemm: tcgen05 engine not available for this shape");
+        return SGB_ENOTSUP;
+    }
+    return gemm_simt_launch(g, (cudaStream_t)stream);
+}
+
+extern "C" size_t sgb_gemm_tn_workspace_bytes(int64_t m, int n, int k) {
+    if (m < 0 || n <= 0 || k <= 0) return 0;
+    return gemm_tn_simt_workspace(m, n, k);
+}
+
+extern "C" int sgb_gemm_tn(const float* g, int64_t ldg, const float* a, int64_t lda, float* d, int64_t ldd, int64_t m, int n, int k,
+                           int accumulate, void* workspace, size_t workspace_bytes, int engine, void* stream) {
+    SGB_CHECK_ARG(g && a && d && m >= 0 && n > 0 && k > 0, "sgb_gemm_tn: bad argument");
+    SGB_CHECK_ARG(ldg >= n && lda >= k && ldd >= k, "sgb_gemm_tn: leading dimension too small");
+    SGB_CHECK_ARG(engine >= 0 && engine <= 2, "sgb_gemm_tn: bad engine %d", engine);
+    if (engine == 2) {
+        set_error("sgb_gemm_tn: tcgen05 engine not available for this shape");
+        return SGB_ENOTSUP;
+    }
+    return gemm_tn_simt_launch(g, ldg, a, lda, d, ldd, m, n, k, accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
+}

@@ -1,0 +1,234 @@
+// Graph builder: edge_index[2, nnz] (int64) -> stable CSR (by target or by source) + dis.
+//
+// Restates, once per edge_index instead of once per conv per forward, what PyG's gcn_norm /
+// get_laplacian recompute inside every GCNConv / ChebConv call.
+// Integer work only (exact); dis = IEEE div(1, sqrt(deg)) so it is bit-identical to
+// torch-CPU `deg.pow_(-0.5)` (A.5).  Stability (CSR order == edge order inside a row)
+// reproduces the CPU scatter_add accumulation order (A.6).
+//
+// Pipeline (all on the caller's stream, HBM-bound, nnz*~40 B + n*~24 B of traffic):
+//   k_count   : histogram of group keys + degree keys (int atomics: exact, order-free)
+//   scan x3   : exclusive scan -> rowptr
+//   k_fill    : bucket edge ids (unordered inside a bucket)
+//   k_rank    : per row, rank edge ids (8 lanes per row) -> stable colidx + perm
+//   k_dis     : dis[i] = deg ? 1/sqrt(deg (+1 for GCN)) : 0
+#include "common.cuh"
+
+namespace sgb {
+
+constexpr int kScanThreads = 1024;
+constexpr int kScanPerThread = 4;
+constexpr int kScanTile = kScanThreads * kScanPerThread;
+
+__global__ void k_count(const int64_t* __restrict__ ei, int64_t nnz, int64_t n, int mode, int transpose,
+                        int32_t* __restrict__ cnt, int32_t* __restrict__ deg, int32_t* __restrict__ perm,
+                        int32_t* __restrict__ err) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = ei[e], c = ei[nnz + e];
+        if (r < 0 || r >= n || c < 0 || c >= n) {
+            *err = 1;
+            if (perm) perm[e] = -1;
+            continue;
+        }
+        if (r == c) {          // self loops never enter the CSR (GCN re-adds one per vertex)
+            if (perm) perm[e] = -1;
+            continue;
+        }
+        atomicAdd(&cnt[transpose ? r : c], 1);
+        // GCN: in-degree over targets (gcn_norm); CHEB / ADJ: degree over sources (get_laplacian)
+        atomicAdd(&deg[mode == SGB_MODE_GCN ? c : r], 1);
+    }
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) >= o) v += t;
+    }
+    return v;
+}
+
+// inclusive scan of one int per thread across a 1024-thread block; returns inclusive value, total in *total
+__device__ int block_incl_scan(int v, int* total) {
+    __shared__ int wsum[32];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = warp_incl_scan(v);
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int s = wsum[lane];
+        s = warp_incl_scan(s);
+        wsum[lane] = s;
+    }
+    __syncthreads();
+    int off = w ? wsum[w - 1] : 0;
+    *total = wsum[31];
+    __syncthreads();
+    return inc + off;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_tile_sums(const int32_t* __restrict__ cnt, int64_t n, int32_t* __restrict__ tsum) {
+    int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanPerThread;
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanPerThread; ++i)
+        if (base + i < n) s += cnt[base + i];
+    int total;
+    block_incl_scan(s, &total);
+    if (threadIdx.x == 0) tsum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_tile_sums(int32_t* __restrict__ tsum, int ntiles) {
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < ntiles; base += kScanThreads) {
+        int i = base + threadIdx.x;
+        int v = i < ntiles ? tsum[i] : 0;
+        int total;
+        int inc = block_incl_scan(v, &total);
+        int carry = carry_s;
+        if (i < ntiles) tsum[i] = carry + inc - v;   // exclusive
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + total;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_tile_scan(const int32_t* __restrict__ cnt, int64_t n, const int32_t* __restrict__ tsum,
+                                                            int32_t* __restrict__ rowptr) {
+    int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanPerThread;
+    int v[kScanPerThread];
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanPerThread; ++i) {
+        v[i] = (base + i < n) ? cnt[base + i] : 0;
+        s += v[i];
+    }
+    int total;
+    int inc = block_incl_scan(s, &total);
+    int run = tsum[blockIdx.x] + inc - s;
+#pragma unroll
+    for (int i = 0; i < kScanPerThread; ++i) {
+        if (base + i < n) rowptr[base + i] = run;
+        run += v[i];
+        if (base + i == n - 1) rowptr[n] = run;
+    }
+}
+
+__global__ void k_fill(const int64_t* __restrict__ ei, int64_t nnz, int64_t n, int transpose,
+                       const int32_t* __restrict__ rowptr, int32_t* __restrict__ cursor, int32_t* __restrict__ tmp) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = ei[e], c = ei[nnz + e];
+        if (r < 0 || r >= n || c < 0 || c >= n || r == c) continue;
+        int64_t key = transpose ? r : c;
+        int slot = atomicAdd(&cursor[key], 1);
+        tmp[rowptr[key] + slot] = (int32_t)e;
+    }
+}
+
+// 8 lanes per row: rank every bucketed edge id among its row's ids -> stable position.
+__global__ void k_rank(const int64_t* __restrict__ ei, int64_t nnz, int64_t n, int transpose,
+                       const int32_t* __restrict__ rowptr, const int32_t* __restrict__ tmp,
+                       int32_t* __restrict__ colidx, int32_t* __restrict__ perm) {
+    constexpr int G = 8;
+    int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
+    int sub = threadIdx.x & (G - 1);
+    int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / G;
+    for (int64_t row = gid; row < n; row += ngroups) {
+        int s = rowptr[row], t = rowptr[row + 1];
+        for (int p = s + sub; p < t; p += G) {
+            int32_t e = tmp[p];
+            int rank = 0;
+            for (int q = s; q < t; ++q) rank += (tmp[q] < e);
+            int64_t other = transpose ? ei[nnz + e] : ei[e];
+            colidx[s + rank] = (int32_t)other;
+            if (perm) perm[e] = s + rank;
+        }
+    }
+}
+
+__global__ void k_dis(const int32_t* __restrict__ deg, int64_t n, int mode, float* __restrict__ dis) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int d = deg[i] + (mode == SGB_MODE_GCN ? 1 : 0);
+        // fl(1 / fl(sqrt(d))): the bit pattern torch-CPU pow(-0.5) produces; NOT rsqrtf.
+        dis[i] = d > 0 ? __fdiv_rn(1.0f, __fsqrt_rn((float)d)) : 0.0f;
+    }
+}
+
+struct BuildWs {
+    int32_t *cnt, *cursor, *deg, *tmp, *tsum;
+    size_t bytes;
+};
+
+static BuildWs carve(void* ws, int64_t nnz, int64_t n) {
+    BuildWs w;
+    size_t off = 0;
+    auto take = [&](size_t elems) {
+        int32_t* p = ws ? reinterpret_cast<int32_t*>(reinterpret_cast<char*>(ws) + off) : nullptr;
+        off += align_up(elems * sizeof(int32_t), 256);
+        return p;
+    };
+    int64_t ntiles = ceil_div(n > 0 ? n : 1, kScanTile);
+    w.cnt = take((size_t)n + 1);
+    w.cursor = take((size_t)n + 1);
+    w.deg = take((size_t)n + 1);
+    w.tsum = take((size_t)ntiles + 1);
+    w.tmp = take((size_t)(nnz > 0 ? nnz : 1));
+    w.bytes = off;
+    return w;
+}
+
+}  // namespace sgb
+
+extern "C" size_t sgb_graph_build_workspace_bytes(int64_t nnz, int64_t n) {
+    if (nnz < 0 || n < 0) return 0;
+    return sgb::carve(nullptr, nnz, n).bytes;
+}
+
+extern "C" int sgb_graph_build(const int64_t* edge_index, int64_t nnz, int64_t n, int mode, int transpose,
+                               int32_t* rowptr, int32_t* colidx, float* dis, int32_t* perm, int32_t* err_flag,
+                               void* workspace, size_t workspace_bytes, void* stream_) {
+    using namespace sgb;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SGB_CHECK_ARG(nnz >= 0 && n >= 0, "sgb_graph_build: negative size");
+    SGB_CHECK_ARG(nnz < (int64_t)0x7fffffff && n < (int64_t)0x7fffffff, "sgb_graph_build: nnz and n must fit int32");
+    SGB_CHECK_ARG(mode == SGB_MODE_GCN || mode == SGB_MODE_CHEB || mode == SGB_MODE_ADJ, "sgb_graph_build: bad mode %d", mode);
+    SGB_CHECK_ARG(rowptr && dis && err_flag && (nnz == 0 || (edge_index && colidx)), "sgb_graph_build: null pointer");
+    BuildWs w = carve(workspace, nnz, n);
+    if (workspace_bytes < w.bytes || !workspace) {
+        set_error("sgb_graph_build: workspace %zu < required %zu", workspace_bytes, w.bytes);
+        return SGB_ENOSPC;
+    }
+    SGB_CUDA(cudaMemsetAsync(workspace, 0, w.bytes - align_up((size_t)(nnz > 0 ? nnz : 1) * 4, 256), stream));
+    SGB_CUDA(cudaMemsetAsync(err_flag, 0, sizeof(int32_t), stream));
+    if (n == 0) {
+        SGB_CUDA(cudaMemsetAsync(rowptr, 0, sizeof(int32_t), stream));
+        return SGB_OK;
+    }
+    const int threads = 256;
+    int egrid = (int)min64(ceil_div(nnz > 0 ? nnz : 1, threads), (int64_t)num_sms() * 16);
+    int ngrid = (int)min64(ceil_div(n, threads), (int64_t)num_sms() * 16);
+    int ntiles = (int)ceil_div(n, kScanTile);
+    if (nnz > 0) {
+        k_count<<<egrid, threads, 0, stream>>>(edge_index, nnz, n, mode, transpose, w.cnt, w.deg, perm, err_flag);
+        SGB_CHECK_LAUNCH("k_count");
+    }
+    k_tile_sums<<<ntiles, kScanThreads, 0, stream>>>(w.cnt, n, w.tsum);
+    SGB_CHECK_LAUNCH("k_tile_sums");
+    k_scan_tile_sums<<<1, kScanThreads, 0, stream>>>(w.tsum, ntiles);
+    SGB_CHECK_LAUNCH("k_scan_tile_sums");
+    k_tile_scan<<<ntiles, kScanThreads, 0, stream>>>(w.cnt, n, w.tsum, rowptr);
+    SGB_CHECK_LAUNCH("k_tile_scan");
+    if (nnz > 0) {
+        k_fill<<<egrid, threads, 0, stream>>>(edge_index, nnz, n, transpose, rowptr, w.cursor, w.tmp);
+        SGB_CHECK_LAUNCH("k_fill");
+        int rgrid = (int)min64(ceil_div(n * 8, threads), (int64_t)num_sms() * 32);
+        k_rank<<<rgrid, threads, 0, stream>>>(edge_index, nnz, n, transpose, rowptr, w.tmp, colidx, perm);
+        SGB_CHECK_LAUNCH("k_rank");
+    }
+    k_dis<<<ngrid, threads, 0, stream>>>(w.deg, n, mode, dis);
+    SGB_CHECK_LAUNCH("k_dis");
+    return SGB_OK;
+}

@@ -1,0 +1,319 @@
+// Row-parallel SpMM over the mesh vertex graph:  Y = alpha * (S f(X)) + beta * ADDEND + bias.
+//
+// Replaces PyG's MessagePassing.propagate (x.index_select(0,row) -> norm.view(-1,1)*x_j ->
+// scatter_add at col), SURVEY.md §3.2 / A.1 step 3 / A.2 step 3, forward and -- on the
+// transpose CSR -- backward.  No [nnz, C] message tensor, no atomics, edge weights recomputed
+// from dis (never stored), neighbour indices staged in registers and broadcast by shuffles.
+//
+// Mapping: one sub-warp of LPV lanes per vertex, each lane owns VEC contiguous channels per
+// iteration (128-bit loads when C % 4 == 0), ITERS iterations cover up to LPV*VEC*ITERS
+// channels per pass; persistent grid (multiple of the SM count) with a grid-stride loop over
+// vertices so consecutive vertices are in flight together (their neighbourhoods overlap ->
+// L1/L2 hits; DRAM sees X once).  Up to 8 independent 128-bit gathers in flight per lane.
+//
+// Arithmetic order is the reference's: per row, messages in CSR (= edge) order, each
+// msg = fl(w * x_j) with w = fl(dis_j * dis_i), acc = fl(acc + msg); then the self-loop
+// term(s): GCN  acc += fl(fl(dis_i*dis_i) * x_i);  CHEB  acc = fl(fl(acc + x_i) - x_i).
+// => bit-identical to the CPU oracle on the same inputs.
+//
+// HBM roofline: algorithmic bytes = 2*N*C*4 + (nnz + 2N + 1)*4.
+#include "common.cuh"
+
+namespace sgb {
+
+constexpr int kSpmmThreads = 256;
+constexpr int kSpmmCtasPerSm = 4;
+
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<4> {
+    float v[4];
+    __device__ __forceinline__ void load(const float* p) {
+        float4 t = ldg4(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    __device__ __forceinline__ void store(float* p) const { st4(p, make_float4(v[0], v[1], v[2], v[3])); }
+};
+template <>
+struct Vec<1> {
+    float v[1];
+    __device__ __forceinline__ void load(const float* p) { v[0] = __ldg(p); }
+    __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
+};
+
+struct SpmmArgs {
+    const int32_t* rowptr;
+    const int32_t* colidx;
+    const float* dis;
+    int mode;
+    const float* x;
+    int64_t ldx;
+    int64_t n;
+    int c;
+    const float* in_scale;
+    const float* in_shift;
+    float slope;
+    float alpha;
+    const float* addend;
+    int64_t ld_addend;
+    float beta;
+    const float* bias;
+    float* y;
+    int64_t ldy;
+    float* stat_partials;
+};
+
+template <int LPV, int VEC, int ITERS>
+__global__ void __launch_bounds__(kSpmmThreads) k_spmm(const SpmmArgs a) {
+    constexpr int NB = (8 / ITERS) < 2 ? 2 : (8 / ITERS);   // neighbours batched per round of loads
+    constexpr int CH = LPV * VEC * ITERS;                   // channels per pass
+    constexpr int GROUPS = kSpmmThreads / LPV;
+    const unsigned full = 0xffffffffu;
+    const int l = threadIdx.x & (LPV - 1);
+    const int grp = threadIdx.x / LPV;
+    const int64_t gstride = (int64_t)gridDim.x * GROUPS;
+    const bool pro = a.in_scale != nullptr;
+    const bool stats = a.stat_partials != nullptr;
+    __shared__ float red[2][kSpmmThreads * VEC * ITERS];
+
+    for (int c0 = 0; c0 < a.c; c0 += CH) {
+        int ch[ITERS];
+        bool act[ITERS];
+        Vec<VEC> sc[ITERS], sh[ITERS], bs[ITERS];
+#pragma unroll
+        for (int t = 0; t < ITERS; ++t) {
+            ch[t] = c0 + (t * LPV + l) * VEC;
+            act[t] = ch[t] < a.c;
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) { sc[t].v[q] = 1.f; sh[t].v[q] = 0.f; bs[t].v[q] = 0.f; }
+            if (act[t]) {
+                if (pro) { sc[t].load(a.in_scale + ch[t]); sh[t].load(a.in_shift + ch[t]); }
+                if (a.bias) bs[t].load(a.bias + ch[t]);
+            }
+        }
+        float s1[ITERS][VEC], s2[ITERS][VEC];
+#pragma unroll
+        for (int t = 0; t < ITERS; ++t)
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) { s1[t][q] = 0.f; s2[t][q] = 0.f; }
+
+        // all 32 lanes of a warp iterate together (shuffles below are full-warp)
+        const int64_t v0 = (int64_t)blockIdx.x * GROUPS + grp;
+        for (int64_t vbase = v0 - grp % (32 / LPV); vbase < a.n; vbase += gstride) {
+            const int64_t v = vbase + grp % (32 / LPV);
+            const bool vok = v < a.n;
+            int start = 0, end = 0;
+            float di = 0.f;
+            if (vok) {
+                start = __ldg(a.rowptr + v);
+                end = __ldg(a.rowptr + v + 1);
+                di = __ldg(a.dis + v);
+            }
+            Vec<VEC> acc[ITERS];
+#pragma unroll
+            for (int t = 0; t < ITERS; ++t)
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) acc[t].v[q] = 0.f;
+
+            for (int base = start; __any_sync(full, base < end); base += LPV) {
+                const int mine = base + l;
+                int cj = -1;
+                float dj = 0.f;
+                if (mine < end) {
+                    cj = __ldg(a.colidx + mine);
+                    dj = __ldg(a.dis + cj);
+                }
+                const int cnt = min(LPV, end - base);
+                for (int k0 = 0; __any_sync(full, k0 < cnt); k0 += NB) {
+                    Vec<VEC> xv[NB][ITERS];
+                    float w[NB];
+                    bool ok[NB];
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        const int j = __shfl_sync(full, cj, k0 + b, LPV);
+                        const float djb = __shfl_sync(full, dj, k0 + b, LPV);
+                        ok[b] = (k0 + b) < cnt;
+                        // w = fl(dis[row] * dis[col]) (A.1 step 1); CHEB negates (exact); ADJ = 1
+                        float wb = __fmul_rn(djb, di);
+                        if (a.mode == SGB_MODE_CHEB) wb = -wb;
+                        if (a.mode == SGB_MODE_ADJ) wb = 1.f;
+                        w[b] = wb;
+#pragma unroll
+                        for (int t = 0; t < ITERS; ++t) {
+                            if (ok[b] && act[t]) xv[b][t].load(a.x + (int64_t)j * a.ldx + ch[t]);
+                        }
+                    }
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        if (ok[b]) {
+#pragma unroll
+                            for (int t = 0; t < ITERS; ++t) {
+                                if (act[t]) {
+#pragma unroll
+                                    for (int q = 0; q < VEC; ++q) {
+                                        float xx = xv[b][t].v[q];
+                                        if (pro) xx = lrelu(fmaf(xx, sc[t].v[q], sh[t].v[q]), a.slope);
+                                        acc[t].v[q] = __fadd_rn(acc[t].v[q], __fmul_rn(w[b], xx));
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (vok) {
+#pragma unroll
+                for (int t = 0; t < ITERS; ++t) {
+                    if (!act[t]) continue;
+                    Vec<VEC> out = acc[t];
+                    if (a.mode != SGB_MODE_ADJ) {
+                        Vec<VEC> xi;
+                        xi.load(a.x + v * a.ldx + ch[t]);
+                        const float wii = __fmul_rn(di, di);
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) {
+                            float xx = xi.v[q];
+                            if (pro) xx = lrelu(fmaf(xx, sc[t].v[q], sh[t].v[q]), a.slope);
+                            if (a.mode == SGB_MODE_GCN) {
+                                out.v[q] = __fadd_rn(out.v[q], __fmul_rn(wii, xx));
+                            } else {   // CHEB: the (+1, -1) loop pair of ChebConv.__norm__, not cancelled
+                                out.v[q] = __fadd_rn(__fadd_rn(out.v[q], xx), -xx);
+                            }
+                        }
+                    }
+                    if (a.addend) {
+                        Vec<VEC> ad;
+                        ad.load(a.addend + v * a.ld_addend + ch[t]);
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q)
+                            out.v[q] = __fadd_rn(__fmul_rn(a.alpha, out.v[q]), __fmul_rn(a.beta, ad.v[q]));
+                    } else if (a.alpha != 1.f) {
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) out.v[q] = __fmul_rn(a.alpha, out.v[q]);
+                    }
+                    if (a.bias) {
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) out.v[q] = __fadd_rn(out.v[q], bs[t].v[q]);
+                    }
+                    out.store(a.y + v * a.ldy + ch[t]);
+                    if (stats) {
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) {
+                            s1[t][q] += out.v[q];
+                            s2[t][q] = fmaf(out.v[q], out.v[q], s2[t][q]);
+                        }
+                    }
+                }
+            }
+        }
+        if (stats) {   // fixed-order block reduction -> partials[blockIdx.x][2][c]
+#pragma unroll
+            for (int t = 0; t < ITERS; ++t)
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) {
+                    const int cl = (t * LPV + l) * VEC + q;     // channel within the pass
+                    red[0][grp * CH + cl] = s1[t][q];
+                    red[1][grp * CH + cl] = s2[t][q];
+                }
+            __syncthreads();
+            for (int cl = threadIdx.x; cl < CH; cl += kSpmmThreads) {
+                if (c0 + cl < a.c) {
+                    float t1 = 0.f, t2 = 0.f;
+                    for (int g = 0; g < GROUPS; ++g) {
+                        t1 += red[0][g * CH + cl];
+                        t2 += red[1][g * CH + cl];
+                    }
+                    a.stat_partials[((int64_t)blockIdx.x * 2 + 0) * a.c + c0 + cl] = t1;
+                    a.stat_partials[((int64_t)blockIdx.x * 2 + 1) * a.c + c0 + cl] = t2;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+struct SpmmCfg {
+    int lpv, vec, iters;
+};
+
+static SpmmCfg pick_cfg(int c, bool aligned) {
+    SpmmCfg k;
+    if (c % 4 == 0 && aligned) {
+        k.vec = 4;
+        int lanes = c / 4;
+        int p = 1;
+        while (p < lanes && p < 32) p <<= 1;
+        k.lpv = p;
+        k.iters = lanes > 32 ? 2 : 1;
+    } else {
+        k.vec = 1;
+        k.lpv = c <= 4 ? 4 : 32;
+        k.iters = 1;
+    }
+    return k;
+}
+
+static int spmm_grid(int64_t n, const SpmmCfg& k) {
+    int groups = kSpmmThreads / k.lpv;
+    int64_t need = ceil_div(n > 0 ? n : 1, groups);
+    int64_t cap = (int64_t)num_sms() * kSpmmCtasPerSm;
+    return (int)(need < cap ? need : cap);
+}
+
+}  // namespace sgb
+
+extern "C" int sgb_spmm_stat_rows(int64_t n, int c) {
+    if (n < 0 || c <= 0) return 0;
+    // alignment of x/y is not known here: the row count must not depend on it, so both
+    // candidate configurations are sized and the larger grid is reported.
+    int g1 = sgb::spmm_grid(n, sgb::pick_cfg(c, true));
+    int g2 = sgb::spmm_grid(n, sgb::pick_cfg(c, false));
+    return g1 > g2 ? g1 : g2;
+}
+
+extern "C" int sgb_spmm(const int32_t* rowptr, const int32_t* colidx, const float* dis, int mode,
+                        const float* x, int64_t ldx, int64_t n, int c,
+                        const float* in_scale, const float* in_shift, float slope,
+                        float alpha, const float* addend, int64_t ld_addend, float beta,
+                        const float* bias, float* y, int64_t ldy, float* stat_partials, void* stream_) {
+    using namespace sgb;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SGB_CHECK_ARG(n >= 0 && c > 0, "sgb_spmm: bad shape n=%lld c=%d", (long long)n, c);
+    SGB_CHECK_ARG(mode == SGB_MODE_GCN || mode == SGB_MODE_CHEB || mode == SGB_MODE_ADJ, "sgb_spmm: bad mode %d", mode);
+    SGB_CHECK_ARG(rowptr && dis && x && y, "sgb_spmm: null pointer");
+    SGB_CHECK_ARG(ldx >= c && ldy >= c && (!addend || ld_addend >= c), "sgb_spmm: leading dimension < c");
+    SGB_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr), "sgb_spmm: in_scale / in_shift must come together");
+    SGB_CHECK_ARG(x != y, "sgb_spmm: in-place aggregation is not supported");
+    if (n == 0) return SGB_OK;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    bool aligned = al16(x) && al16(y) && ldx % 4 == 0 && ldy % 4 == 0 && (!addend || (al16(addend) && ld_addend % 4 == 0)) &&
+                   (!bias || al16(bias)) && (!in_scale || (al16(in_scale) && al16(in_shift)));
+    SpmmCfg k = pick_cfg(c, aligned);
+    int grid = spmm_grid(n, k);
+    if (stat_partials) {
+        // rows the caller sized for; unused rows must read as zero
+        int rows = sgb_spmm_stat_rows(n, c);
+        if (rows > grid)
+            SGB_CUDA(cudaMemsetAsync(stat_partials + (size_t)grid * 2 * c, 0, (size_t)(rows - grid) * 2 * c * sizeof(float), stream));
+    }
+    SpmmArgs a{rowptr, colidx, dis, mode, x, ldx, n, c, in_scale, in_shift, slope, alpha, addend, ld_addend, beta, bias, y, ldy, stat_partials};
+#define SGB_SPMM_CASE(L, V, I)                                         \
+    if (k.lpv == L && k.vec == V && k.iters == I) {                    \
+        k_spmm<L, V, I><<<grid, kSpmmThreads, 0, stream>>>(a);         \
+        SGB_CHECK_LAUNCH("k_spmm");                                    \
+        return SGB_OK;                                                 \
+    }
+    SGB_SPMM_CASE(1, 4, 1)
+    SGB_SPMM_CASE(2, 4, 1)
+    SGB_SPMM_CASE(4, 4, 1)
+    SGB_SPMM_CASE(8, 4, 1)
+    SGB_SPMM_CASE(16, 4, 1)
+    SGB_SPMM_CASE(32, 4, 1)
+    SGB_SPMM_CASE(32, 4, 2)
+    SGB_SPMM_CASE(4, 1, 1)
+    SGB_SPMM_CASE(32, 1, 1)
+#undef SGB_SPMM_CASE
+    set_error("sgb_spmm: no kernel configuration for c=%d", c);
+    return SGB_ENOTSUP;
+}

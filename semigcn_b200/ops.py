@@ -1,0 +1,346 @@
+"""Host-side wrappers (torch tensors in, C-ABI calls out) and the autograd Functions built on
+them.  PyTorch supplies device memory, streams and the autograd tape; every kernel launched
+here is ours (libsemigcn_b200.so).  No CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib as L
+from ._lib import MODE_ADJ, MODE_CHEB, MODE_GCN, SgbError, check, ptr, require_cuda, stream_ptr
+
+Affine = Optional[Tuple[Tensor, Tensor, float]]   # (scale[c], shift[c], slope): fused BN + LeakyReLU on load
+
+
+def _f32c(t: Tensor, name: str) -> Tensor:
+    if t.dtype != torch.float32:
+        raise SgbError(f"{name}: expected float32, got {t.dtype}")
+    if t.dim() == 2 and t.stride(1) != 1:
+        t = t.contiguous()
+    elif t.dim() != 2 and not t.is_contiguous():
+        t = t.contiguous()
+    return t
+
+
+def _ws(nbytes: int, device) -> Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ----------------------------------------------------------------------------------------
+# graph: CSR by target (forward) and by source (backward) + dis, cached per edge_index
+# ----------------------------------------------------------------------------------------
+class MeshGraph:
+    """Normalised sparse operator of one ``edge_index`` for one mode (GCN / CHEB / ADJ).
+
+    Holds what PyG recomputes in every conv call (gcn_norm / get_laplacian):
+    ``rowptr/colidx`` grouped by target in stable edge order, the same grouped by source for
+    the backward pass, and ``dis = deg^-1/2`` (bit-exact).  Edge weights are never stored.
+    """
+
+    def __init__(self, edge_index: Tensor, num_nodes: int, mode: int, with_perm: bool = False):
+        require_cuda(edge_index)
+        if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
+            raise SgbError("edge_index must be an int64 tensor of shape [2, nnz]")
+        lib = L.load()
+        ei = edge_index.contiguous()
+        dev = ei.device
+        nnz, n = int(ei.shape[1]), int(num_nodes)
+        self.n, self.nnz, self.mode, self.device = n, nnz, mode, dev
+        wsb = lib.sgb_graph_build_workspace_bytes(nnz, n)
+        ws = _ws(wsb, dev)
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.dis = torch.empty(n, dtype=torch.float32, device=dev)
+        out = []
+        with torch.cuda.device(dev):
+            for transpose in (0, 1):
+                rowptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+                colidx = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+                perm = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev) if with_perm else None
+                check(lib.sgb_graph_build(ptr(ei), nnz, n, mode, transpose, ptr(rowptr), ptr(colidx), ptr(self.dis),
+                                          ptr(perm), ptr(err), ptr(ws), wsb, stream_ptr(dev)), "sgb_graph_build")
+                L.count(7)
+                out.append((rowptr, colidx, perm))
+        # one host sync per (edge_index, mode), at cache-fill time only
+        if int(err.item()) != 0:
+            raise SgbError("edge_index contains vertex ids outside [0, num_nodes)")
+        (self.rowptr, self.colidx, self.perm), (self.rowptr_t, self.colidx_t, self.perm_t) = out
+
+    def csr(self, transpose: bool):
+        return (self.rowptr_t, self.colidx_t) if transpose else (self.rowptr, self.colidx)
+
+
+_GRAPH_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_GRAPH_CACHE_MAX = 16
+
+
+def graph_for(edge_index: Tensor, num_nodes: int, mode: int) -> MeshGraph:
+    """Cache keyed on (storage pointer, shape, version counter, device, mode, N) -- the
+    reference passes the same ``edge_index`` to every conv of every forward
+    (util/networks.py:65,86) and never mutates it."""
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, str(edge_index.device), mode, int(num_nodes))
+    hit = _GRAPH_CACHE.get(key)
+    if hit is not None:
+        _GRAPH_CACHE.move_to_end(key)
+        return hit[0]
+    g = MeshGraph(edge_index, num_nodes, mode)
+    _GRAPH_CACHE[key] = (g, edge_index)      # keep the tensor alive so the pointer cannot be recycled
+    while len(_GRAPH_CACHE) > _GRAPH_CACHE_MAX:
+        _GRAPH_CACHE.popitem(last=False)
+    return g
+
+
+def clear_graph_cache() -> None:
+    _GRAPH_CACHE.clear()
+
+
+# ----------------------------------------------------------------------------------------
+# thin functional wrappers
+# ----------------------------------------------------------------------------------------
+def spmm(g: MeshGraph, x: Tensor, transpose: bool = False, in_affine: Affine = None, alpha: float = 1.0,
+         addend: Optional[Tensor] = None, beta: float = 0.0, bias: Optional[Tensor] = None,
+         want_stats: bool = False, out: Optional[Tensor] = None):
+    lib = L.load()
+    require_cuda(x, addend, bias)
+    x = _f32c(x, "x")
+    n, c = x.shape
+    if n != g.n:
+        raise SgbError(f"x has {n} rows but the graph has {g.n} vertices")
+    y = out if out is not None else torch.empty((n, c), dtype=torch.float32, device=x.device)
+    if addend is not None:
+        addend = _f32c(addend, "addend")
+    partials = None
+    if want_stats:
+        rows = lib.sgb_spmm_stat_rows(n, c)
+        partials = torch.empty((rows, 2, c), dtype=torch.float32, device=x.device)
+    rowptr, colidx = g.csr(transpose)
+    sc, sh, slope = (in_affine if in_affine is not None else (None, None, 0.0))
+    with torch.cuda.device(x.device):
+        check(lib.sgb_spmm(ptr(rowptr), ptr(colidx), ptr(g.dis), g.mode, ptr(x), x.stride(0), n, c,
+                           ptr(sc), ptr(sh), float(slope), float(alpha), ptr(addend),
+                           addend.stride(0) if addend is not None else 0, float(beta), ptr(bias),
+                           ptr(y), y.stride(0), ptr(partials), stream_ptr(x.device)), "sgb_spmm")
+    L.count(1)
+    return (y, partials) if want_stats else y
+
+
+def gemm(a: Tensor, b: Tensor, transb: bool = True, a_affine: Affine = None, bias: Optional[Tensor] = None,
+         out: Optional[Tensor] = None, accumulate: bool = False, want_stats: bool = False, engine: int = 0):
+    """C (+)= f(A) @ (B^T if transb else B) + bias."""
+    lib = L.load()
+    require_cuda(a, b, bias)
+    a, b = _f32c(a, "a"), _f32c(b, "b")
+    m, k = a.shape
+    n = b.shape[0] if transb else b.shape[1]
+    if (b.shape[1] if transb else b.shape[0]) != k:
+        raise SgbError(f"gemm: inner dimensions differ ({a.shape} x {b.shape}, transb={transb})")
+    c = out if out is not None else torch.empty((m, n), dtype=torch.float32, device=a.device)
+    partials = None
+    if want_stats:
+        partials = torch.empty((lib.sgb_gemm_stat_rows(m), 2, n), dtype=torch.float32, device=a.device)
+    sc, sh, slope = (a_affine if a_affine is not None else (None, None, 0.0))
+    with torch.cuda.device(a.device):
+        check(lib.sgb_gemm(1 if transb else 0, ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(c), c.stride(0), m, n, k,
+                           ptr(sc), ptr(sh), float(slope), ptr(bias), 1 if accumulate else 0, ptr(partials),
+                           engine, stream_ptr(a.device)), "sgb_gemm")
+    L.count(1)
+    return (c, partials) if want_stats else c
+
+
+def gemm_tn(gmat: Tensor, a: Tensor, out: Optional[Tensor] = None, accumulate: bool = False, engine: int = 0) -> Tensor:
+    """D[n,k] (+)= G[m,n]^T @ A[m,k]  (weight gradient)."""
+    lib = L.load()
+    require_cuda(gmat, a)
+    gmat, a = _f32c(gmat, "g"), _f32c(a, "a")
+    m, n = gmat.shape
+    k = a.shape[1]
+    if a.shape[0] != m:
+        raise SgbError("gemm_tn: row counts differ")
+    d = out if out is not None else torch.empty((n, k), dtype=torch.float32, device=a.device)
+    wsb = lib.sgb_gemm_tn_workspace_bytes(m, n, k)
+    ws = _ws(wsb, a.device)
+    with torch.cuda.device(a.device):
+        check(lib.sgb_gemm_tn(ptr(gmat), gmat.stride(0), ptr(a), a.stride(0), ptr(d), d.stride(0), m, n, k,
+                              1 if accumulate else 0, ptr(ws), wsb, engine, stream_ptr(a.device)), "sgb_gemm_tn")
+    L.count(2)
+    return d
+
+
+def colsum(gmat: Tensor, out: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
+    lib = L.load()
+    require_cuda(gmat)
+    gmat = _f32c(gmat, "g")
+    m, n = gmat.shape
+    o = out if out is not None else torch.empty(n, dtype=torch.float32, device=gmat.device)
+    wsb = lib.sgb_colsum_workspace_bytes(m, n)
+    ws = _ws(wsb, gmat.device)
+    with torch.cuda.device(gmat.device):
+        check(lib.sgb_colsum(ptr(gmat), gmat.stride(0), m, n, ptr(o), 1 if accumulate else 0, ptr(ws), wsb,
+                             stream_ptr(gmat.device)), "sgb_colsum")
+    L.count(2)
+    return o
+
+
+def col_stats(y: Tensor) -> Tensor:
+    lib = L.load()
+    y = _f32c(y, "y")
+    m, c = y.shape
+    partials = torch.empty((lib.sgb_col_stat_rows(m, c), 2, c), dtype=torch.float32, device=y.device)
+    with torch.cuda.device(y.device):
+        check(lib.sgb_col_stats(ptr(y), y.stride(0), m, c, ptr(partials), stream_ptr(y.device)), "sgb_col_stats")
+    L.count(1)
+    return partials
+
+
+def bn_finalize(partials: Tensor, count: int, gamma: Optional[Tensor], beta: Optional[Tensor], eps: float,
+                momentum: float, running_mean: Optional[Tensor], running_var: Optional[Tensor]):
+    lib = L.load()
+    rows, _, c = partials.shape
+    dev = partials.device
+    st = torch.empty((4, c), dtype=torch.float32, device=dev)     # mean, invstd, scale, shift
+    with torch.cuda.device(dev):
+        check(lib.sgb_bn_finalize(ptr(partials), rows, c, count, ptr(gamma), ptr(beta), float(eps), float(momentum),
+                                  ptr(running_mean), ptr(running_var), ptr(st[0]), ptr(st[1]), ptr(st[2]), ptr(st[3]),
+                                  stream_ptr(dev)), "sgb_bn_finalize")
+    L.count(1)
+    return st[0], st[1], st[2], st[3]
+
+
+def bn_act_apply(y: Tensor, scale: Tensor, shift: Tensor, slope: float, out: Optional[Tensor] = None) -> Tensor:
+    lib = L.load()
+    y = _f32c(y, "y")
+    m, c = y.shape
+    z = out if out is not None else torch.empty_like(y)
+    with torch.cuda.device(y.device):
+        check(lib.sgb_bn_act_apply(ptr(y), y.stride(0), m, c, ptr(scale), ptr(shift), float(slope), ptr(z), z.stride(0),
+                                   stream_ptr(y.device)), "sgb_bn_act_apply")
+    L.count(1)
+    return z
+
+
+def bn_act_bwd(dz: Tensor, y: Tensor, scale: Tensor, shift: Tensor, mean: Optional[Tensor], invstd: Optional[Tensor],
+               slope: float, training: bool, want_param_grads: bool = True):
+    """dY (and dgamma, dbeta) of Z = lrelu(BN(Y)) given dZ."""
+    lib = L.load()
+    dz, y = _f32c(dz, "dz"), _f32c(y, "y")
+    m, c = y.shape
+    dev = y.device
+    dy = torch.empty_like(y)
+    dgamma = dbeta = sums = None
+    with torch.cuda.device(dev):
+        if training or want_param_grads:
+            if mean is None:       # eval mode: xhat from the running statistics folded in scale/shift is not available
+                raise SgbError("bn_act_bwd: mean/invstd required")
+            rows = lib.sgb_col_stat_rows(m, c)
+            partials = torch.empty((rows, 2, c), dtype=torch.float32, device=dev)
+            check(lib.sgb_bn_act_bwd_reduce(ptr(dz), dz.stride(0), ptr(y), y.stride(0), m, c, ptr(scale), ptr(shift),
+                                            ptr(mean), ptr(invstd), float(slope), ptr(partials), stream_ptr(dev)),
+                  "sgb_bn_act_bwd_reduce")
+            sums = torch.empty((2, c), dtype=torch.float32, device=dev)
+            dgamma = torch.empty(c, dtype=torch.float32, device=dev)
+            dbeta = torch.empty(c, dtype=torch.float32, device=dev)
+            check(lib.sgb_bn_bwd_finalize(ptr(partials), rows, c, ptr(sums), ptr(dgamma), ptr(dbeta), 0, stream_ptr(dev)),
+                  "sgb_bn_bwd_finalize")
+            L.count(2)
+        check(lib.sgb_bn_act_bwd_apply(ptr(dz), dz.stride(0), ptr(y), y.stride(0), m, c, ptr(scale), ptr(shift), ptr(mean),
+                                       ptr(invstd), ptr(sums), float(slope), 1 if training else 0, ptr(dy), dy.stride(0),
+                                       stream_ptr(dev)), "sgb_bn_act_bwd_apply")
+        L.count(1)
+    return dy, dgamma, dbeta
+
+
+# ----------------------------------------------------------------------------------------
+# autograd Functions (unfused building blocks; the fused conv+BN+act block lives in nn.py)
+# ----------------------------------------------------------------------------------------
+class PropagateFn(torch.autograd.Function):
+    """y = alpha * (S x) + beta * addend;  backward: dx = alpha * (S^T dy), daddend = beta * dy."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, graph: MeshGraph, alpha: float, addend: Optional[Tensor], beta: float):
+        ctx.graph, ctx.alpha, ctx.beta = graph, alpha, beta
+        ctx.has_addend = addend is not None
+        return spmm(graph, x, alpha=alpha, addend=addend, beta=beta)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        dy = dy.contiguous()
+        dx = spmm(ctx.graph, dy, transpose=True, alpha=ctx.alpha) if ctx.needs_input_grad[0] else None
+        dadd = None
+        if ctx.has_addend and ctx.needs_input_grad[3]:
+            dadd = dy * ctx.beta
+        return dx, None, None, dadd, None
+
+
+def propagate(graph: MeshGraph, x: Tensor, alpha: float = 1.0, addend: Optional[Tensor] = None, beta: float = 0.0) -> Tensor:
+    return PropagateFn.apply(x, graph, alpha, addend, beta)
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x W^T (+ b) on our GEMM tiles; dX = dY W, dW = dY^T X (split-m, fixed order), db = colsum(dY)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor]):
+        x = _f32c(x, "x")
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return gemm(x, weight, transb=True, bias=bias)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = gemm(dy, weight, transb=False) if ctx.needs_input_grad[0] else None
+        dw = gemm_tn(dy, x) if ctx.needs_input_grad[1] else None
+        db = colsum(dy) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx, dw, db
+
+
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None) -> Tensor:
+    return LinearFn.apply(x, weight, bias)
+
+
+class BnActFn(torch.autograd.Function):
+    """Z = lrelu(BatchNorm1d(Y)); training: batch statistics (+ running-stat update), eval: running stats."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, running_mean, running_var, eps, momentum, slope, training, partials):
+        y = _f32c(y, "y")
+        m, c = y.shape
+        if training:
+            if partials is None:
+                partials = col_stats(y)
+            mean, invstd, scale, shift = bn_finalize(partials, m, gamma, beta, eps, momentum, running_mean, running_var)
+        else:
+            invstd = torch.rsqrt(running_var + eps)
+            mean = running_mean
+            scale = invstd * gamma if gamma is not None else invstd
+            shift = (beta if beta is not None else 0.0) - mean * scale
+            scale, shift = scale.contiguous(), shift.contiguous()
+        z = bn_act_apply(y, scale, shift, slope)
+        ctx.save_for_backward(y, scale, shift, mean, invstd)
+        ctx.slope, ctx.training, ctx.has_affine = slope, training, gamma is not None
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        y, scale, shift, mean, invstd = ctx.saved_tensors
+        dy, dgamma, dbeta = bn_act_bwd(dz.contiguous(), y, scale, shift, mean, invstd, ctx.slope, ctx.training)
+        if not ctx.has_affine:
+            dgamma = dbeta = None
+        return dy, dgamma, dbeta, None, None, None, None, None, None, None
+
+
+def bn_act(y: Tensor, bn: torch.nn.BatchNorm1d, slope: float, partials: Optional[Tensor] = None) -> Tensor:
+    """BatchNorm1d module semantics (torch.nn.BatchNorm1d) + LeakyReLU(slope); slope=1 -> BN only, 0 -> ReLU."""
+    training = bn.training or (bn.running_mean is None)
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        if bn.momentum is None:
+            momentum = 1.0 / float(bn.num_batches_tracked)
+    rm = bn.running_mean if (training and bn.track_running_stats) or not training else None
+    rv = bn.running_var if (training and bn.track_running_stats) or not training else None
+    return BnActFn.apply(y, bn.weight, bn.bias, rm, rv, bn.eps, momentum, slope, training, partials)

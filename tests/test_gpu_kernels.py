@@ -1,0 +1,256 @@
+"""GPU parity tests of the individual C-ABI entry points against the CPU oracle.
+Bars: graph builder and aggregation BIT-EXACT; dense transform / BatchNorm
+within 1e-5 norm-relative of an fp64 evaluation."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import (assert_bit_equal, assert_close, load_golden, random_graph, rel_err, stable_csr_from_edges)
+from oracle import pyg_ref as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _ops():
+    from semigcn_b200 import ops
+    return ops
+
+
+GRAPHS = [
+    dict(n=50, nnz=200, seed=0),
+    dict(n=64, nnz=300, seed=1, self_loops=9),
+    dict(n=64, nnz=300, seed=2, duplicates=40),
+    dict(n=70, nnz=200, seed=3, isolated=11),
+    dict(n=300, nnz=4000, seed=4, self_loops=5, duplicates=50, isolated=3, symmetric=True),
+    dict(n=5000, nnz=60000, seed=5),
+    dict(n=20, nnz=4000, seed=6, duplicates=500),          # very long rows (rank kernel, multi-batch gather)
+]
+
+
+def _graph(kw):
+    kw = dict(kw)
+    n = kw.pop("n")
+    return n, random_graph(n, **kw)
+
+
+# ------------------------------------------------------------------ 1. graph builder
+@pytest.mark.parametrize("kw", GRAPHS)
+@pytest.mark.parametrize("mode", [0, 1])
+def test_graph_build_bit_exact(kw, mode):
+    ops = _ops()
+    n, ei = _graph(kw)
+    g = ops.MeshGraph(ei.to(DEV), n, mode, with_perm=True)
+    for by_source, (rowptr, colidx, perm) in ((False, (g.rowptr, g.colidx, g.perm)), (True, (g.rowptr_t, g.colidx_t, g.perm_t))):
+        rp, ci, pm = stable_csr_from_edges(ei, n, by_source)
+        assert_bit_equal(rowptr, rp, "rowptr")
+        m = int(rp[-1])
+        assert_bit_equal(colidx[:m], ci, "colidx")
+        assert_bit_equal(perm, pm, "perm")
+    # dis against the oracle's deg.pow_(-0.5) (degree over targets +1 for GCN, over sources for Cheb)
+    row, col = ei
+    keep = row != col
+    if mode == 0:
+        deg = torch.bincount(col[keep], minlength=n).float() + 1
+    else:
+        deg = torch.bincount(row[keep], minlength=n).float()
+    dis = deg.pow_(-0.5)
+    dis[dis == float("inf")] = 0
+    assert_bit_equal(g.dis, dis, "dis")
+
+
+def test_graph_build_all_degrees_bit_exact():
+    """dis for every degree 1..4096 (star-like rows) == torch-CPU pow(-0.5) (A.5)."""
+    ops = _ops()
+    degs = torch.arange(1, 1025)
+    n = int(degs.numel()) + 1100
+    tgt = torch.repeat_interleave(torch.arange(degs.numel()), degs)
+    src = torch.cat([torch.arange(d) + 1024 for d in degs.tolist()])         # sources never equal targets
+    ei = torch.stack([src, tgt])
+    g = ops.MeshGraph(ei.to(DEV), n, 0)
+    want = (degs.float() + 1).pow_(-0.5)
+    assert_bit_equal(g.dis[:degs.numel()], want, "dis(deg+1)")
+
+
+def test_graph_build_errors_and_empty():
+    ops = _ops()
+    from semigcn_b200 import SgbError
+    with pytest.raises(SgbError):
+        ops.MeshGraph(torch.tensor([[0, 5], [1, 0]], device=DEV), 3, 0)
+    g = ops.MeshGraph(torch.zeros((2, 0), dtype=torch.int64, device=DEV), 4, 0)
+    assert g.rowptr.tolist() == [0, 0, 0, 0, 0] and torch.all(g.dis == 1.0)
+
+
+@pytest.mark.parametrize("n", [4, 8])
+def test_graph_build_golden_mesh(n):
+    ops = _ops()
+    gold = load_golden(n)
+    ei = torch.from_numpy(gold["edge_index"])
+    nv = gold["vs"].shape[0]
+    g = ops.MeshGraph(ei.to(DEV), nv, 1)
+    deg = (g.rowptr[1:] - g.rowptr[:-1]).float().cpu()
+    assert np.array_equal(deg.numpy(), gold["v_dims"])          # reference util/mesh.py:267
+    assert torch.equal(g.rowptr.cpu(), g.rowptr_t.cpu())        # mesh graph is symmetric
+
+
+# ------------------------------------------------------------------ 2. SpMM
+WIDTHS = [1, 3, 4, 8, 16, 32, 60, 64, 128, 130, 256, 512, 640]
+
+
+@pytest.mark.parametrize("c", WIDTHS)
+@pytest.mark.parametrize("mode", [0, 1])
+def test_spmm_bit_exact_vs_oracle_propagate(c, mode):
+    ops = _ops()
+    n, ei = _graph(GRAPHS[4])
+    torch.manual_seed(c)
+    x = torch.randn(n, c)
+    ei2, w = (O.gcn_norm if mode == 0 else O.cheb_norm)(ei, n)
+    want = O.propagate(ei2, w, x)
+    g = ops.MeshGraph(ei.to(DEV), n, mode)
+    got = ops.spmm(g, x.to(DEV))
+    assert_bit_equal(got, want, f"spmm mode={mode} c={c}")
+
+
+@pytest.mark.parametrize("kw", GRAPHS)
+def test_spmm_graph_zoo_and_transpose(kw):
+    ops = _ops()
+    n, ei = _graph(kw)
+    torch.manual_seed(1)
+    x = torch.randn(n, 32)
+    for mode, norm in ((0, O.gcn_norm), (1, O.cheb_norm)):
+        g = ops.MeshGraph(ei.to(DEV), n, mode)
+        ei2, w = norm(ei, n)
+        assert_bit_equal(ops.spmm(g, x.to(DEV)), O.propagate(ei2, w, x), "forward")
+        # backward aggregation = autograd of the oracle (index_select backward = index_add over row)
+        xr = x.clone().requires_grad_(True)
+        O.propagate(ei2, w, xr).backward(torch.ones(n, 32) * x)
+        got = ops.spmm(g, x.to(DEV), transpose=True)
+        assert_close(got, xr.grad, 2e-6, "transpose")
+
+
+def test_spmm_epilogue_cheb_recurrence_bias_and_prologue():
+    ops = _ops()
+    n, ei = _graph(GRAPHS[5])
+    torch.manual_seed(2)
+    c = 64
+    x, t0, bias = torch.randn(n, c), torch.randn(n, c), torch.randn(c)
+    ei2, w = O.cheb_norm(ei, n)
+    g = ops.MeshGraph(ei.to(DEV), n, 1)
+    want = 2.0 * O.propagate(ei2, w, x) - t0
+    got = ops.spmm(g, x.to(DEV), alpha=2.0, addend=t0.to(DEV), beta=-1.0)
+    assert_bit_equal(got, want, "T2 = 2 L^ T1 - T0")
+    g0 = ops.MeshGraph(ei.to(DEV), n, 0)
+    ei3, w3 = O.gcn_norm(ei, n)
+    want = O.propagate(ei3, w3, x) + bias
+    assert_bit_equal(ops.spmm(g0, x.to(DEV), bias=bias.to(DEV)), want, "+bias")
+    # fused BN-affine + LeakyReLU on the gathered operand
+    sc, sh = torch.rand(c) + 0.5, torch.randn(c)
+    z = torch.nn.functional.leaky_relu(x * sc + sh, 0.01)
+    want = O.propagate(ei3, w3, z)
+    got = ops.spmm(g0, x.to(DEV), in_affine=(sc.to(DEV), sh.to(DEV), 0.01))
+    assert_close(got, want, 2e-6, "prologue")
+
+
+@pytest.mark.parametrize("c", [4, 16, 64, 256, 512])
+def test_spmm_stats_epilogue(c):
+    ops = _ops()
+    n, ei = _graph(GRAPHS[5])
+    torch.manual_seed(3)
+    x = torch.randn(n, c) + 0.3
+    g = ops.MeshGraph(ei.to(DEV), n, 0)
+    y, partials = ops.spmm(g, x.to(DEV), want_stats=True)
+    s = partials.double().sum(0).cpu()
+    yd = y.double().cpu()
+    assert_close(s[0], yd.sum(0), 1e-6, "sum")
+    assert_close(s[1], (yd * yd).sum(0), 1e-6, "sum of squares")
+
+
+def test_spmm_deterministic():
+    ops = _ops()
+    n, ei = _graph(GRAPHS[5])
+    x = torch.randn(n, 128, device=DEV)
+    g = ops.MeshGraph(ei.to(DEV), n, 0)
+    a = ops.spmm(g, x)
+    for _ in range(3):
+        assert torch.equal(a, ops.spmm(g, x))
+
+
+# ------------------------------------------------------------------ 3. dense transform
+SHAPES = [(1000, 16, 4), (1000, 3, 16), (777, 32, 16), (1030, 64, 32), (515, 128, 64), (2049, 256, 128), (1200, 512, 256),
+          (640, 256, 512), (130, 130, 70), (128, 48, 200)]
+
+
+@pytest.mark.parametrize("m,n,k", SHAPES)
+@pytest.mark.parametrize("transb", [True, False])
+def test_gemm_vs_fp64(m, n, k, transb):
+    ops = _ops()
+    torch.manual_seed(m + n + k)
+    a = torch.randn(m, k)
+    b = torch.randn(n, k) if transb else torch.randn(k, n)
+    bias = torch.randn(n)
+    want = a.double() @ (b.double().t() if transb else b.double()) + bias.double()
+    got, partials = ops.gemm(a.to(DEV), b.to(DEV), transb=transb, bias=bias.to(DEV), want_stats=True)
+    assert_close(got, want, 2e-6, "gemm")
+    s = partials.double().sum(0).cpu()
+    assert_close(s[0], want.sum(0), 1e-5, "stat sum")
+    assert_close(s[1], (want * want).sum(0), 1e-5, "stat sumsq")
+    # accumulate
+    c0 = torch.randn(m, n)
+    got2 = ops.gemm(a.to(DEV), b.to(DEV), transb=transb, out=c0.to(DEV).clone(), accumulate=True)
+    assert_close(got2, want - bias.double() + c0.double(), 2e-6, "accumulate")
+
+
+def test_gemm_prologue():
+    ops = _ops()
+    torch.manual_seed(5)
+    m, n, k = 900, 64, 128
+    a, b = torch.randn(m, k), torch.randn(n, k)
+    sc, sh = torch.rand(k) + 0.5, torch.randn(k)
+    z = torch.nn.functional.leaky_relu(a.double() * sc.double() + sh.double(), 0.01)
+    got = ops.gemm(a.to(DEV), b.to(DEV), a_affine=(sc.to(DEV), sh.to(DEV), 0.01))
+    assert_close(got, z @ b.double().t(), 2e-6, "prologue")
+
+
+@pytest.mark.parametrize("m,n,k", [(5000, 16, 4), (4097, 64, 32), (3000, 256, 128), (2500, 130, 70), (100000, 32, 16), (300, 512, 256)])
+def test_gemm_tn_and_colsum(m, n, k):
+    ops = _ops()
+    torch.manual_seed(m)
+    g, a = torch.randn(m, n), torch.randn(m, k)
+    got = ops.gemm_tn(g.to(DEV), a.to(DEV))
+    assert_close(got, g.double().t() @ a.double(), 2e-6, "gemm_tn")
+    again = ops.gemm_tn(g.to(DEV), a.to(DEV))
+    assert torch.equal(got, again), "split-m reduction must be deterministic"
+    acc = ops.gemm_tn(g.to(DEV), a.to(DEV), out=got.clone(), accumulate=True)
+    assert_close(acc, 2 * (g.double().t() @ a.double()), 2e-6, "gemm_tn accumulate")
+    assert_close(ops.colsum(g.to(DEV)), g.double().sum(0), 2e-6, "colsum")
+
+
+# ------------------------------------------------------------------ 4. BatchNorm + LeakyReLU
+@pytest.mark.parametrize("m,c", [(1000, 4), (5000, 16), (3001, 3), (2000, 130), (4000, 256), (777, 512)])
+@pytest.mark.parametrize("slope", [0.01, 0.0, 1.0])
+def test_bn_act_forward_backward_vs_torch(m, c, slope):
+    ops = _ops()
+    torch.manual_seed(c)
+    y = torch.randn(m, c) * 2 + 0.7
+    bn_ref = torch.nn.BatchNorm1d(c).double()
+    bn_ref.weight.data.uniform_(0.5, 1.5)
+    bn_ref.bias.data.normal_()
+    bn = torch.nn.BatchNorm1d(c).to(DEV)
+    bn.load_state_dict({k: v.float() if v.dtype.is_floating_point else v for k, v in bn_ref.state_dict().items()})
+    yr = y.double().requires_grad_(True)
+    zr = torch.nn.functional.leaky_relu(bn_ref(yr), slope)
+    dz = torch.randn(m, c)
+    zr.backward(dz.double())
+    yg = y.to(DEV).requires_grad_(True)
+    z = ops.bn_act(yg, bn, slope)
+    z.backward(dz.to(DEV))
+    assert_close(z, zr, 2e-6, "z")
+    assert_close(yg.grad, yr.grad, 1e-5, "dy")
+    assert_close(bn.weight.grad, bn_ref.weight.grad, 1e-5, "dgamma")
+    assert_close(bn.bias.grad, bn_ref.bias.grad, 1e-5, "dbeta")
+    assert_close(bn.running_mean, bn_ref.running_mean, 1e-6, "running_mean")
+    assert_close(bn.running_var, bn_ref.running_var, 1e-6, "running_var")
+    assert int(bn.num_batches_tracked) == 1
+    # eval mode uses the running statistics
+    bn.eval(); bn_ref.eval()
+    assert_close(ops.bn_act(y.to(DEV), bn, slope), torch.nn.functional.leaky_relu(bn_ref(y.double()), slope), 2e-6, "eval")

@@ -1,0 +1,228 @@
+"""GPU parity tests at the drop-in boundary: our GCNConv / ChebConv / Sequential / SGCN against
+the CPU oracle (restatement of PyG 2.2.0) on the same seeded inputs and identical state_dicts.
+Tolerance: max|a-b| / max|b| <= 1e-5 for layer outputs and gradients (BASELINE.json north_star)."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from helpers import REL_TOL, assert_close, load_golden, random_graph, rel_err
+from oracle import pyg_ref as O
+from semigcn_b200 import meshgen
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _grads_close(ours: nn.Module, ref: nn.Module, tol=REL_TOL, skip_zero_bias=True):
+    ro = dict(ref.named_parameters())
+    for name, p in ours.named_parameters():
+        r = ro[name]
+        if r.grad is None:
+            assert p.grad is None or p.grad.abs().max() == 0, name
+            continue
+        assert p.grad is not None, name
+        if skip_zero_bias and name.endswith("module_0.bias"):
+            # a conv bias followed by BatchNorm has an exactly-zero true gradient: both sides hold
+            # rounding noise only; compare on the scale of the weight gradient instead
+            continue
+        assert_close(p.grad, r.grad, tol, name)
+
+
+@pytest.mark.parametrize("cin,cout", [(4, 16), (16, 32), (64, 128), (128, 64), (256, 256), (16, 3), (3, 5)])
+@pytest.mark.parametrize("kind", ["gcn", "cheb"])
+def test_conv_forward_backward_vs_oracle(cin, cout, kind):
+    from semigcn_b200.nn import ChebConv, GCNConv
+    mesh = meshgen.icosphere(6)
+    n = mesh.num_vertices
+    torch.manual_seed(cin * 1000 + cout)
+    ref = O.GCNConv(cin, cout) if kind == "gcn" else O.ChebConv(cin, cout, K=3)
+    ref.bias.data.normal_()
+    ours = (GCNConv(cin, cout) if kind == "gcn" else ChebConv(cin, cout, K=3))
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(DEV)
+    x = torch.randn(n, cin)
+    dy = torch.randn(n, cout)
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr, mesh.edge_index)
+    yr.backward(dy)
+    xg = x.to(DEV).requires_grad_(True)
+    y = ours(xg, mesh.edge_index.to(DEV))
+    y.backward(dy.to(DEV))
+    assert_close(y, yr, REL_TOL, "output")
+    assert_close(xg.grad, xr.grad, REL_TOL, "dx")
+    _grads_close(ours, ref, skip_zero_bias=False)
+
+
+@pytest.mark.parametrize("kw", [dict(n=200, nnz=1500, seed=11, self_loops=7, duplicates=30, isolated=5),
+                                dict(n=300, nnz=2000, seed=12, symmetric=True)])
+@pytest.mark.parametrize("kind", ["gcn", "cheb"])
+def test_conv_on_irregular_graphs(kw, kind):
+    """Asymmetric edge lists, duplicates, existing self loops, isolated vertices."""
+    from semigcn_b200.nn import ChebConv, GCNConv
+    kw = dict(kw)
+    n = kw.pop("n")
+    ei = random_graph(n, **kw)
+    torch.manual_seed(5)
+    ref = O.GCNConv(8, 12) if kind == "gcn" else O.ChebConv(8, 12, K=3)
+    ours = (GCNConv(8, 12) if kind == "gcn" else ChebConv(8, 12, K=3))
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(DEV)
+    x = torch.randn(n, 8)
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr, ei)
+    yr.backward(torch.ones_like(yr))
+    xg = x.to(DEV).requires_grad_(True)
+    y = ours(xg, ei.to(DEV))
+    y.backward(torch.ones_like(y))
+    assert_close(y, yr, REL_TOL, "output")
+    assert_close(xg.grad, xr.grad, REL_TOL, "dx")
+    _grads_close(ours, ref, skip_zero_bias=False)
+
+
+@pytest.mark.parametrize("K", [1, 2, 4])
+def test_chebconv_other_orders(K):
+    from semigcn_b200.nn import ChebConv
+    mesh = meshgen.icosphere(4)
+    torch.manual_seed(K)
+    ref = O.ChebConv(6, 10, K=K)
+    ours = ChebConv(6, 10, K=K)
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(DEV)
+    x = torch.randn(mesh.num_vertices, 6)
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr, mesh.edge_index)
+    yr.sum().backward()
+    xg = x.to(DEV).requires_grad_(True)
+    y = ours(xg, mesh.edge_index.to(DEV))
+    y.sum().backward()
+    assert_close(y, yr, REL_TOL, "output")
+    assert_close(xg.grad, xr.grad, REL_TOL, "dx")
+    _grads_close(ours, ref, skip_zero_bias=False)
+
+
+@pytest.mark.parametrize("cin,cout", [(4, 16), (64, 128), (128, 32), (16, 3)])
+@pytest.mark.parametrize("kind", ["gcn", "cheb"])
+@pytest.mark.parametrize("train", [True, False])
+def test_fused_block_vs_oracle_sequential(cin, cout, kind, train):
+    """conv -> BatchNorm1d -> LeakyReLU (-> Linear) exactly as util/networks.py:24-36 builds it."""
+    from semigcn_b200.nn import ChebConv, GCNConv, Sequential
+    mesh = meshgen.icosphere(7)
+    n = mesh.num_vertices
+    torch.manual_seed(cin + cout)
+
+    def build(mod):
+        conv = (mod.GCNConv(cin, cout) if kind == "gcn" else mod.ChebConv(cin, cout, K=3))
+        return mod.Sequential("x, edge_index", [(conv, "x, edge_index -> x"), nn.BatchNorm1d(cout), nn.LeakyReLU(),
+                                                (nn.Linear(cout, 3), "x -> x")])
+    import semigcn_b200.nn as OURS
+    ref = build(O)
+    ref.module_1.weight.data.uniform_(0.5, 1.5)
+    ref.module_1.bias.data.normal_()
+    ref.module_1.running_mean.normal_()
+    ref.module_1.running_var.uniform_(0.5, 2.0)
+    ours = build(OURS)
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(DEV)
+    ref.train(train); ours.train(train)
+    x = torch.randn(n, cin)
+    dy = torch.randn(n, 3)
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr, mesh.edge_index)
+    yr.backward(dy)
+    xg = x.to(DEV).requires_grad_(True)
+    y = ours(xg, mesh.edge_index.to(DEV))
+    y.backward(dy.to(DEV))
+    assert_close(y, yr, REL_TOL, "output")
+    assert_close(xg.grad, xr.grad, REL_TOL, "dx")
+    _grads_close(ours, ref)
+    for k in ("module_1.running_mean", "module_1.running_var", "module_1.num_batches_tracked"):
+        assert_close(ours.state_dict()[k].float(), ref.state_dict()[k].float(), 1e-6, k)
+
+
+def _sgcn_pair(conv, seed=314, skip=False):
+    from semigcn_b200.networks import SingleScaleGCN
+    torch.manual_seed(seed)
+    ref = O.SingleScaleGCN(conv, skip=skip)
+    ours = SingleScaleGCN(DEV, conv=conv, skip=skip)
+    ours.load_state_dict(ref.state_dict())
+    return ours.to(DEV), ref
+
+
+@pytest.mark.parametrize("conv", ["gcnconv", "chebconv"])
+@pytest.mark.parametrize("skip", [False, True])
+def test_sgcn_forward_backward_vs_oracle(conv, skip):
+    """Whole 13-block SGCN (util/networks.py) on a 1 002-vertex icosphere: output, input gradient
+    and every parameter gradient within 1e-5 norm-relative of the CPU oracle."""
+    from semigcn_b200.data import Data
+    prob = meshgen.synth_inpainting_problem(10, smooth_iters=10, n_dummy=4)
+    mesh = prob["mesh"]
+    ours, ref = _sgcn_pair(conv, skip=skip)
+    dm = prob["vmask_dummy"][:, :1] * prob["v_mask"].float().reshape(-1, 1)
+    z1r = prob["z1"].clone().requires_grad_(True)
+    out_r = ref(z1r, prob["x_pos"], mesh.edge_index, dm)
+    loss_r = O.mask_pos_rec_loss(out_r, prob["ini_vs"], prob["v_mask"]) + \
+        4.0 * O.mask_norm_rec_loss(O.compute_fn(out_r, mesh.faces), prob["fn"], prob["f_mask"])
+    loss_r.backward()
+    z1g = prob["z1"].to(DEV).requires_grad_(True)
+    data = Data(z1=z1g, x_pos=prob["x_pos"].to(DEV), edge_index=mesh.edge_index.to(DEV))
+    out = ours(data, dm)
+    loss = O.mask_pos_rec_loss(out, prob["ini_vs"].to(DEV), prob["v_mask"].to(DEV)) + \
+        4.0 * O.mask_norm_rec_loss(O.compute_fn(out, mesh.faces.to(DEV)), prob["fn"].to(DEV), prob["f_mask"].to(DEV))
+    loss.backward()
+    assert_close(out, out_r, REL_TOL, "positions")
+    assert abs(loss.item() - loss_r.item()) <= 1e-5 * abs(loss_r.item())
+    assert_close(z1g.grad, z1r.grad, 5e-5, "d z1")
+    ro = dict(ref.named_parameters())
+    worst = 0.0
+    for name, p in ours.named_parameters():
+        r = ro[name]
+        if r.grad is None or name.endswith("module_0.bias"):
+            continue
+        worst = max(worst, rel_err(p.grad, r.grad))
+    assert worst <= 5e-5, f"worst parameter-gradient error {worst:.2e}"
+
+
+def test_sgcn_training_100_steps_tracks_oracle():
+    """BASELINE.json: final vertex error <= 1e-4 of the bounding-box diagonal after 100 steps from
+    identical state_dicts and an identical mask schedule (Adam lr 0.01 as sgcn.py:79)."""
+    from semigcn_b200.data import Data
+    prob = meshgen.synth_inpainting_problem(6, smooth_iters=10, n_dummy=8)
+    mesh = prob["mesh"]
+    ours, ref = _sgcn_pair("gcnconv")
+    opt_o = torch.optim.Adam(ours.parameters(), lr=0.01)
+    opt_r = torch.optim.Adam(ref.parameters(), lr=0.01)
+    data = Data(z1=prob["z1"].to(DEV), x_pos=prob["x_pos"].to(DEV), edge_index=mesh.edge_index.to(DEV))
+    g = torch.Generator().manual_seed(314)
+    vm = prob["v_mask"]
+    for step in range(100):
+        j = int(torch.randint(0, 8, (1,), generator=g))
+        dm = prob["vmask_dummy"][:, j:j + 1] * vm.float().reshape(-1, 1)
+        opt_r.zero_grad()
+        out_r = ref(prob["z1"], prob["x_pos"], mesh.edge_index, dm)
+        O.mask_pos_rec_loss(out_r, prob["ini_vs"], vm).backward()
+        opt_r.step()
+        opt_o.zero_grad()
+        out = ours(data, dm)
+        O.mask_pos_rec_loss(out, prob["ini_vs"].to(DEV), vm.to(DEV)).backward()
+        opt_o.step()
+    ours.eval(); ref.eval()
+    with torch.no_grad():
+        fin_r = ref(prob["z1"], prob["x_pos"], mesh.edge_index, vm.float().reshape(-1, 1))
+        fin = ours(data, vm.float().reshape(-1, 1)).cpu()
+    bbox = (prob["ini_vs"].max(0)[0] - prob["ini_vs"].min(0)[0]).norm().item()
+    err = (fin - fin_r).norm(dim=1).max().item() / bbox
+    assert err <= 1e-4, f"vertex error {err:.3e} of the bbox diagonal"
+
+
+def test_reference_scripts_import_surface():
+    """The reference's util/networks.py pattern, written against the torch_geometric shim names."""
+    import semigcn_b200.compat as compat
+    compat.install(force=True)
+    from torch_geometric.nn import ChebConv, Sequential
+    blk = Sequential("x, edge_index", [(ChebConv(4, 16, K=3), "x, edge_index -> x"), nn.BatchNorm1d(16), nn.LeakyReLU()]).to(DEV)
+    mesh = meshgen.icosphere(3)
+    y = blk(torch.randn(mesh.num_vertices, 4, device=DEV), mesh.edge_index.to(DEV))
+    assert y.shape == (mesh.num_vertices, 16) and torch.isfinite(y).all()

