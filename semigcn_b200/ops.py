@@ -11,6 +11,7 @@ import torch
 from torch import Tensor
 
 from . import _lib as L
+from . import profile as _prof
 from ._lib import MODE_ADJ, MODE_CHEB, MODE_GCN, SgbError, check, ptr, require_cuda, stream_ptr
 
 Affine = Optional[Tuple[Tensor, Tensor, float]]   # (scale[c], shift[c], slope): fused BN + LeakyReLU on load
@@ -118,11 +119,16 @@ def spmm(g: MeshGraph, x: Tensor, transpose: bool = False, in_affine: Affine = N
         partials = torch.empty((rows, 2, c), dtype=torch.float32, device=x.device)
     rowptr, colidx = g.csr(transpose)
     sc, sh, slope = (in_affine if in_affine is not None else (None, None, 0.0))
+    nnz_eff = int(g.nnz) + (n if g.mode == MODE_GCN else 0)
+    sp = _prof.span(f"spmm_c{c}", 4.0 * (2 * n * c + nnz_eff + 2 * n + 1 + (n * c if addend is not None else 0)),
+                    2.0 * nnz_eff * c) if _prof.ACTIVE is not None else None
     with torch.cuda.device(x.device):
         check(lib.sgb_spmm(ptr(rowptr), ptr(colidx), ptr(g.dis), g.mode, ptr(x), x.stride(0), n, c,
                            ptr(sc), ptr(sh), float(slope), float(alpha), ptr(addend),
                            addend.stride(0) if addend is not None else 0, float(beta), ptr(bias),
                            ptr(y), y.stride(0), ptr(partials), stream_ptr(x.device)), "sgb_spmm")
+    if sp is not None:
+        sp.close()
     L.count(1)
     return (y, partials) if want_stats else y
 
@@ -142,10 +148,14 @@ def gemm(a: Tensor, b: Tensor, transb: bool = True, a_affine: Affine = None, bia
     if want_stats:
         partials = torch.empty((lib.sgb_gemm_stat_rows(m), 2, n), dtype=torch.float32, device=a.device)
     sc, sh, slope = (a_affine if a_affine is not None else (None, None, 0.0))
+    sp = _prof.span(f"gemm_n{n}_k{k}", 4.0 * (m * (k + n) + k * n + (m * n if accumulate else 0)), 2.0 * m * n * k) \
+        if _prof.ACTIVE is not None else None
     with torch.cuda.device(a.device):
         check(lib.sgb_gemm(1 if transb else 0, ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(c), c.stride(0), m, n, k,
                            ptr(sc), ptr(sh), float(slope), ptr(bias), 1 if accumulate else 0, ptr(partials),
                            engine, stream_ptr(a.device)), "sgb_gemm")
+    if sp is not None:
+        sp.close()
     L.count(1)
     return (c, partials) if want_stats else c
 
@@ -162,9 +172,12 @@ def gemm_tn(gmat: Tensor, a: Tensor, out: Optional[Tensor] = None, accumulate: b
     d = out if out is not None else torch.empty((n, k), dtype=torch.float32, device=a.device)
     wsb = lib.sgb_gemm_tn_workspace_bytes(m, n, k)
     ws = _ws(wsb, a.device)
+    sp = _prof.span(f"gemm_tn_n{n}_k{k}", 4.0 * (m * (k + n) + k * n), 2.0 * m * n * k) if _prof.ACTIVE is not None else None
     with torch.cuda.device(a.device):
         check(lib.sgb_gemm_tn(ptr(gmat), gmat.stride(0), ptr(a), a.stride(0), ptr(d), d.stride(0), m, n, k,
                               1 if accumulate else 0, ptr(ws), wsb, engine, stream_ptr(a.device)), "sgb_gemm_tn")
+    if sp is not None:
+        sp.close()
     L.count(2)
     return d
 
@@ -177,9 +190,12 @@ def colsum(gmat: Tensor, out: Optional[Tensor] = None, accumulate: bool = False)
     o = out if out is not None else torch.empty(n, dtype=torch.float32, device=gmat.device)
     wsb = lib.sgb_colsum_workspace_bytes(m, n)
     ws = _ws(wsb, gmat.device)
+    sp = _prof.span(f"colsum_c{n}", 4.0 * m * n) if _prof.ACTIVE is not None else None
     with torch.cuda.device(gmat.device):
         check(lib.sgb_colsum(ptr(gmat), gmat.stride(0), m, n, ptr(o), 1 if accumulate else 0, ptr(ws), wsb,
                              stream_ptr(gmat.device)), "sgb_colsum")
+    if sp is not None:
+        sp.close()
     L.count(2)
     return o
 
@@ -214,9 +230,12 @@ def bn_act_apply(y: Tensor, scale: Tensor, shift: Tensor, slope: float, out: Opt
     y = _f32c(y, "y")
     m, c = y.shape
     z = out if out is not None else torch.empty_like(y)
+    sp = _prof.span(f"bn_act_apply_c{c}", 8.0 * m * c) if _prof.ACTIVE is not None else None
     with torch.cuda.device(y.device):
         check(lib.sgb_bn_act_apply(ptr(y), y.stride(0), m, c, ptr(scale), ptr(shift), float(slope), ptr(z), z.stride(0),
                                    stream_ptr(y.device)), "sgb_bn_act_apply")
+    if sp is not None:
+        sp.close()
     L.count(1)
     return z
 
@@ -230,6 +249,7 @@ def bn_act_bwd(dz: Tensor, y: Tensor, scale: Tensor, shift: Tensor, mean: Option
     dev = y.device
     dy = torch.empty_like(y)
     dgamma = dbeta = sums = None
+    sp = _prof.span(f"bn_act_bwd_c{c}", 4.0 * m * c * (5 if training else 3)) if _prof.ACTIVE is not None else None
     with torch.cuda.device(dev):
         if training or want_param_grads:
             if mean is None:       # eval mode: xhat from the running statistics folded in scale/shift is not available
@@ -249,6 +269,8 @@ def bn_act_bwd(dz: Tensor, y: Tensor, scale: Tensor, shift: Tensor, mean: Option
                                        ptr(invstd), ptr(sums), float(slope), 1 if training else 0, ptr(dy), dy.stride(0),
                                        stream_ptr(dev)), "sgb_bn_act_bwd_apply")
         L.count(1)
+    if sp is not None:
+        sp.close()
     return dy, dgamma, dbeta
 
 

@@ -154,18 +154,28 @@ def _sgcn_pair(conv, seed=314, skip=False):
 @pytest.mark.parametrize("conv", ["gcnconv", "chebconv"])
 @pytest.mark.parametrize("skip", [False, True])
 def test_sgcn_forward_backward_vs_oracle(conv, skip):
-    """Whole 13-block SGCN (util/networks.py) on a 1 002-vertex icosphere: output, input gradient
-    and every parameter gradient within 1e-5 norm-relative of the CPU oracle."""
+    """Whole 13-block SGCN (util/networks.py) on a 1 002-vertex icosphere.  Positions and loss must
+    match the fp32 CPU oracle to 1e-5.  Gradients that have crossed 13 BatchNorm layers are compared
+    with an fp64 evaluation of the oracle: our deviation from fp64 must be no worse than a small
+    multiple of the fp32 CPU oracle's own deviation from fp64 (the layer-level 1e-5 bar is
+    enforced per layer in the tests above)."""
     from semigcn_b200.data import Data
     prob = meshgen.synth_inpainting_problem(10, smooth_iters=10, n_dummy=4)
     mesh = prob["mesh"]
     ours, ref = _sgcn_pair(conv, skip=skip)
+    ref64 = copy.deepcopy(ref).double()
     dm = prob["vmask_dummy"][:, :1] * prob["v_mask"].float().reshape(-1, 1)
-    z1r = prob["z1"].clone().requires_grad_(True)
-    out_r = ref(z1r, prob["x_pos"], mesh.edge_index, dm)
-    loss_r = O.mask_pos_rec_loss(out_r, prob["ini_vs"], prob["v_mask"]) + \
-        4.0 * O.mask_norm_rec_loss(O.compute_fn(out_r, mesh.faces), prob["fn"], prob["f_mask"])
-    loss_r.backward()
+
+    def run_ref(net, dtype):
+        z1 = prob["z1"].to(dtype).clone().requires_grad_(True)
+        out = net(z1, prob["x_pos"].to(dtype), mesh.edge_index, dm.to(dtype))
+        loss = O.mask_pos_rec_loss(out, prob["ini_vs"], prob["v_mask"]) + \
+            4.0 * O.mask_norm_rec_loss(O.compute_fn(out, mesh.faces), prob["fn"], prob["f_mask"])
+        loss.backward()
+        return out, loss, z1.grad
+
+    out_r, loss_r, dz_r = run_ref(ref, torch.float32)
+    out_64, loss_64, dz_64 = run_ref(ref64, torch.float64)
     z1g = prob["z1"].to(DEV).requires_grad_(True)
     data = Data(z1=z1g, x_pos=prob["x_pos"].to(DEV), edge_index=mesh.edge_index.to(DEV))
     out = ours(data, dm)
@@ -174,15 +184,18 @@ def test_sgcn_forward_backward_vs_oracle(conv, skip):
     loss.backward()
     assert_close(out, out_r, REL_TOL, "positions")
     assert abs(loss.item() - loss_r.item()) <= 1e-5 * abs(loss_r.item())
-    assert_close(z1g.grad, z1r.grad, 5e-5, "d z1")
-    ro = dict(ref.named_parameters())
-    worst = 0.0
+
+    def check(name, g_ours, g_ref32, g_ref64):
+        e_ours, e_ref = rel_err(g_ours, g_ref64), rel_err(g_ref32, g_ref64)
+        assert e_ours <= max(3.0 * e_ref, 2e-5), f"{name}: ours vs fp64 {e_ours:.2e}, fp32 oracle vs fp64 {e_ref:.2e}"
+        assert e_ours <= 1e-3, name
+
+    check("d z1", z1g.grad, dz_r, dz_64)
+    r32, r64 = dict(ref.named_parameters()), dict(ref64.named_parameters())
     for name, p in ours.named_parameters():
-        r = ro[name]
-        if r.grad is None or name.endswith("module_0.bias"):
+        if r32[name].grad is None or name.endswith("module_0.bias"):
             continue
-        worst = max(worst, rel_err(p.grad, r.grad))
-    assert worst <= 5e-5, f"worst parameter-gradient error {worst:.2e}"
+        check(name, p.grad, r32[name].grad, r64[name].grad)
 
 
 def test_sgcn_training_100_steps_tracks_oracle():
