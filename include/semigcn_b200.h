@@ -107,13 +107,16 @@ SGB_API int sgb_spmm(const int32_t* rowptr, const int32_t* colidx, const float* 
  *                    fixed-order two-stage reduction -> deterministic).
  *    sgb_colsum:     out[n] (+)= sum_m G[m,n]        (bias gradient).
  *    `engine`: 0 = auto, 1 = fp32 CUDA-core tiles, 2 = tcgen05 3xTF32 tensor-core tiles
- *    (error-compensated: hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM).
+ *    (error-compensated: hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM).  The tensor-core
+ *    engine stages the split / pre-tiled weights in `workspace` (sgb_gemm_workspace_bytes).
  * ------------------------------------------------------------------------------------ */
 SGB_API int sgb_gemm_stat_rows(int64_t m);
+SGB_API size_t sgb_gemm_workspace_bytes(int64_t m, int n, int k, int engine);
 SGB_API int sgb_gemm(int transb, const float* a, int64_t lda, const float* b, int64_t ldb,
              float* c, int64_t ldc, int64_t m, int n, int k,
              const float* a_scale, const float* a_shift, float slope,
-             const float* bias, int accumulate, float* stat_partials, int engine, void* stream);
+             const float* bias, int accumulate, float* stat_partials,
+             void* workspace, size_t workspace_bytes, int engine, void* stream);
 SGB_API size_t sgb_gemm_tn_workspace_bytes(int64_t m, int n, int k);
 SGB_API int sgb_gemm_tn(const float* g, int64_t ldg, const float* a, int64_t lda, float* d, int64_t ldd,
                 int64_t m, int n, int k, int accumulate, void* workspace, size_t workspace_bytes,

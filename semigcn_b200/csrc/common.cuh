@@ -38,7 +38,7 @@ int num_sms();                           // cached per process (api.cu)
     } while (0)
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
-static inline int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
+__host__ __device__ static inline int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }

@@ -7,25 +7,45 @@ int gemm_simt_launch(const GemmArgs& g, cudaStream_t stream);
 int gemm_tn_simt_launch(const float* g, int64_t ldg, const float* a, int64_t lda, float* d, int64_t ldd, int64_t m, int n, int k,
                         int accumulate, void* ws, size_t ws_bytes, cudaStream_t stream);
 size_t gemm_tn_simt_workspace(int64_t m, int n, int k);
+bool gemm_tc_supported(int64_t m, int n, int k, int64_t lda, int64_t ldc, const void* a, const void* c, const void* bias,
+                       const void* a_scale);
+size_t gemm_tc_workspace(int n, int k);
+int gemm_tc_launch(const GemmArgs& g, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+// auto policy: the tensor pipe only where the transform is a real dense contraction
+static bool tc_worthwhile(int64_t m, int n, int k) { return n >= 64 && k >= 32 && m >= 2048; }
 }  // namespace sgb
 
 using namespace sgb;
 
 extern "C" int sgb_gemm_stat_rows(int64_t m) { return m <= 0 ? 0 : (int)ceil_div(m, 128); }
 
+extern "C" size_t sgb_gemm_workspace_bytes(int64_t m, int n, int k, int engine) {
+    if (m < 0 || n <= 0 || k <= 0 || engine == 1) return 0;
+    if (engine == 0 && !tc_worthwhile(m, n, k)) return 0;
+    if (n % 16 != 0 || k % 4 != 0) return 0;
+    return gemm_tc_workspace(n, k);
+}
+
 extern "C" int sgb_gemm(int transb, const float* a, int64_t lda, const float* b, int64_t ldb, float* c, int64_t ldc, int64_t m,
                         int n, int k, const float* a_scale, const float* a_shift, float slope, const float* bias, int accumulate,
-                        float* stat_partials, int engine, void* stream) {
+                        float* stat_partials, void* workspace, size_t workspace_bytes, int engine, void* stream) {
     SGB_CHECK_ARG(a && b && c && m >= 0 && n > 0 && k > 0, "sgb_gemm: bad argument m=%lld n=%d k=%d", (long long)m, n, k);
     SGB_CHECK_ARG(lda >= k && ldc >= n && ldb >= (transb ? k : n), "sgb_gemm: leading dimension too small");
     SGB_CHECK_ARG((a_scale == nullptr) == (a_shift == nullptr), "sgb_gemm: a_scale / a_shift must come together");
     SGB_CHECK_ARG(engine >= 0 && engine <= 2, "sgb_gemm: bad engine %d", engine);
     if (m == 0) return SGB_OK;
     GemmArgs g{transb, a, lda, b, ldb, c, ldc, m, n, k, a_scale, a_shift, slope, bias, accumulate, stat_partials};
+    const bool tc_ok = gemm_tc_supported(m, n, k, lda, ldc, a, c, bias, a_scale);
     if (engine == 2) {
-        set_error("sgb_gemm: tcgen05 engine not available for this shape");
-        return SGB_ENOTSUP;
+        if (!tc_ok) {
+            set_error("sgb_gemm: tcgen05 engine needs n %% 16 == 0, k %% 4 == 0 and 16-byte aligned operands (n=%d k=%d)", n, k);
+            return SGB_ENOTSUP;
+        }
+        return gemm_tc_launch(g, workspace, workspace_bytes, (cudaStream_t)stream);
     }
+    if (engine == 0 && tc_ok && tc_worthwhile(m, n, k) && workspace && workspace_bytes >= gemm_tc_workspace(n, k))
+        return gemm_tc_launch(g, workspace, workspace_bytes, (cudaStream_t)stream);
     return gemm_simt_launch(g, (cudaStream_t)stream);
 }
 

@@ -1,0 +1,459 @@
+// tcgen05 (5th-gen tensor core) tiles for the dense feature transform, fp32-accurate via
+// error-compensated 3xTF32:  x = hi + lo with hi = rn_tf32(x), lo = rn_tf32(x - hi);
+//   A*B ~= A_hi*B_hi + A_lo*B_hi + A_hi*B_lo      (fp32 accumulation in TMEM)
+// which keeps ~22 mantissa bits per product -- plain TF32 (10 bits) cannot meet the 1e-5 parity
+// bar (SURVEY.md §0 finding 6).
+//
+// Kernel k_gemm_tc  (forward transform and dX):   C[M,N] (+)= f(A)[M,K] * Wp^T + bias
+//   * persistent: one CTA per SM, static round-robin over (m-tile, n-tile) pairs
+//   * A (activations, M ~ 1e6 rows) : global -> registers (BatchNorm-affine + LeakyReLU prologue,
+//     hi/lo split) -> shared memory in the canonical K-major no-swizzle UMMA layout, padded so the
+//     16-byte stores are bank-conflict free                       [8 producer warps]
+//   * B (weights, tiny, L2-resident): pre-split and pre-tiled once per call by k_prep_weights into
+//     exactly the shared-memory image one stage needs, then fetched with one cp.async.bulk per
+//     stage signalling the stage's mbarrier                       [1 elected lane]
+//   * MMA: tcgen05.mma.cta_group::1.kind::tf32, M=128, N<=256, K=8 per instruction, 12 per
+//     32-wide K chunk, issued by one elected lane; smem slots released with tcgen05.commit
+//   * accumulators double-buffered in TMEM (2 x N columns) so the epilogue of tile i overlaps the
+//     main loop of tile i+1; epilogue warps read TMEM with tcgen05.ld.32x32b, add bias (and C when
+//     accumulating) and store rows straight to global memory      [4 epilogue warps]
+//
+// Kernel k_gemm_tn_tc (weight gradient):  D[N,K] = G[M,N]^T A[M,K], reduction over the vertices;
+//   both operands are MN-major for the tensor core, so the row-major global tiles are staged with
+//   16-byte stores as they are (no transposition); split over M across CTAs, fixed-order
+//   reduction of the partial tiles afterwards (deterministic).
+#include "common.cuh"
+
+namespace sgb {
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 lanes x 32 columns of 32-bit: thread (lane) receives 32 consecutive columns of its row
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = tf32_rn(x);
+    lo = tf32_rn(x - hi);
+}
+
+// shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type=0 [61,64))
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @4, a/b_format TF32 = 2 @7/@10,
+// a_major @15, b_major @16 (0 = K-major, 1 = MN-major), n>>3 @17, m>>4 @24
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------
+// tile geometry (forward / dX kernel)
+// ------------------------------------------------------------------------------------------
+constexpr int kTcBM = 128;                      // rows per tile == UMMA M
+constexpr int kTcBK = 32;                       // K chunk per pipeline stage (4 MMA k-slices of 8)
+constexpr int kTcALbo = 144;                    // bytes between K-adjacent 8x16B core matrices of A (128 + 16 pad: conflict-free stores)
+constexpr int kTcASbo = (kTcBK / 4) * kTcALbo;  // bytes between M-adjacent core matrices of A = 1152
+constexpr int kTcATile = (kTcBM / 8) * kTcASbo; // 18432 bytes per hi (or lo) A tile
+constexpr int kTcBLbo = 128;
+constexpr int kTcBSbo = (kTcBK / 4) * kTcBLbo;  // 1024
+constexpr int kTcProducerWarps = 8;
+constexpr int kTcThreads = (kTcProducerWarps + 2 + 4) * 32;   // producers, B-copy warp, MMA warp, 4 epilogue warps
+constexpr int kTcMaxStages = 4;
+
+__host__ __device__ constexpr int tc_b_tile_bytes(int bn) { return (bn / 8) * kTcBSbo; }     // per hi (or lo)
+__host__ __device__ constexpr int tc_stage_bytes(int bn) { return 2 * kTcATile + 2 * tc_b_tile_bytes(bn); }
+
+struct TcArgs {
+    const float* a; int64_t lda;
+    const float* wp;                  // prepped weights: [n_tiles][k_chunks][hi|lo][tile image]
+    float* c; int64_t ldc;
+    int64_t m; int n; int k;
+    int bn;                           // columns per n-tile (multiple of 16, <= 256); all n-tiles but the last are full
+    int n_tiles; int k_chunks; int stages;
+    const float* a_scale; const float* a_shift; float slope;
+    const float* bias; int accumulate;
+    uint32_t tmem_cols;
+    int acc_stride;                   // TMEM columns between the two accumulator buffers (multiple of 32)
+};
+
+// weights -> hi/lo split, zero padded, in the exact per-stage shared-memory image
+// element (n, k) of n-tile t, chunk q:  core (nl/8, kl/4), row nl%8, word kl%4
+__global__ void k_prep_weights(const float* __restrict__ w, int64_t ldw, int transb, int n, int k, int bn, int n_tiles, int k_chunks,
+                               float* __restrict__ wp) {
+    const int tile_words = tc_b_tile_bytes(bn) / 4;
+    const int64_t total = (int64_t)n_tiles * k_chunks * tile_words;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int word = (int)(i % tile_words);
+        const int64_t blk = i / tile_words;
+        const int q = (int)(blk % k_chunks), t = (int)(blk / k_chunks);
+        const int core_n = word / (kTcBSbo / 4);
+        const int rem = word % (kTcBSbo / 4);
+        const int core_k = rem / 32, in_core = rem % 32;
+        const int nl = core_n * 8 + in_core / 4, kl = core_k * 4 + in_core % 4;
+        const int gn = t * bn + nl, gk = q * kTcBK + kl;
+        float v = 0.f;
+        if (gn < n && gk < k) v = transb ? w[(int64_t)gn * ldw + gk] : w[(int64_t)gk * ldw + gn];
+        float hi, lo;
+        split_tf32(v, hi, lo);
+        float* base = wp + (blk * 2) * tile_words;
+        base[word] = hi;
+        base[tile_words + word] = lo;
+    }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const TcArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stage_bytes = tc_stage_bytes(g.bn);
+    const int b_tile_bytes = tc_b_tile_bytes(g.bn);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)g.stages * stage_bytes);
+    uint64_t* empty = full + kTcMaxStages;
+    uint64_t* tfull = empty + kTcMaxStages;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.stages; ++s) {
+            mbar_init(&full[s], kTcProducerWarps * 32 + 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tfull[b], 1);
+            mbar_init(&tempty[b], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == kTcProducerWarps + 1) tmem_alloc(tmem_slot, g.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t m_tiles = (g.m + kTcBM - 1) / kTcBM;
+    const int64_t total_tiles = m_tiles * g.n_tiles;
+
+    if (warp < kTcProducerWarps) {
+        // ================= A producers: global -> regs (prologue, hi/lo) -> smem =================
+        const int ptid = threadIdx.x;                          // 0..255
+        const bool pro = g.a_scale != nullptr;
+        // chunk = 128 rows x 8 float4; thread handles rows r0 + 32*i (i<4), float4 column cq
+        const int cq = ptid & 7, r0 = ptid >> 3;               // r0 in 0..31
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int64_t m0 = (tile / g.n_tiles) * kTcBM;
+            for (int q = 0; q < g.k_chunks; ++q, ++it) {
+                const int s = it % g.stages;
+                const uint32_t ph = (it / g.stages) & 1;
+                const int kcol = q * kTcBK + cq * 4;
+                float4 v[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int64_t gm = m0 + r0 + 32 * i;
+                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (gm < g.m && kcol < g.k) v[i] = ldg4(g.a + gm * g.lda + kcol);   // K % 4 == 0 guaranteed by the dispatcher
+                }
+                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pro && kcol < g.k) { sc = ldg4(g.a_scale + kcol); sh = ldg4(g.a_shift + kcol); }
+                mbar_wait(&empty[s], ph ^ 1);
+                uint8_t* a_hi = smem + (size_t)s * stage_bytes;
+                uint8_t* a_lo = a_hi + kTcATile;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = r0 + 32 * i;
+                    float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+                    if (pro) {
+                        x[0] = lrelu(fmaf(x[0], sc.x, sh.x), g.slope); x[1] = lrelu(fmaf(x[1], sc.y, sh.y), g.slope);
+                        x[2] = lrelu(fmaf(x[2], sc.z, sh.z), g.slope); x[3] = lrelu(fmaf(x[3], sc.w, sh.w), g.slope);
+                        if (m0 + r >= g.m || kcol >= g.k) { x[0] = x[1] = x[2] = x[3] = 0.f; }
+                    }
+                    float h[4], l[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) split_tf32(x[e], h[e], l[e]);
+                    const uint32_t off = (uint32_t)(r >> 3) * kTcASbo + (uint32_t)cq * kTcALbo + (uint32_t)(r & 7) * 16;
+                    *reinterpret_cast<float4*>(a_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<float4*>(a_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+                }
+                fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                mbar_arrive(&full[s]);
+            }
+        }
+    } else if (warp == kTcProducerWarps) {
+        // ================= B copy: one bulk copy of the pre-tiled hi|lo weight image per stage =================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = (int)(tile % g.n_tiles);
+                for (int q = 0; q < g.k_chunks; ++q, ++it) {
+                    const int s = it % g.stages;
+                    const uint32_t ph = (it / g.stages) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* b_dst = smem + (size_t)s * stage_bytes + 2 * kTcATile;
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(g.wp) + ((size_t)nt * g.k_chunks + q) * 2 * b_tile_bytes;
+                    mbar_arrive_expect_tx(&full[s], 2 * b_tile_bytes);
+                    bulk_g2s(b_dst, src, 2 * b_tile_bytes, &full[s]);
+                }
+            }
+        }
+    } else if (warp == kTcProducerWarps + 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            uint32_t it = 0, tcount = 0;
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+                const int nt = (int)(tile % g.n_tiles);
+                const int ncols = min(g.bn, g.n - nt * g.bn);                 // multiple of 16
+                const uint32_t idesc = make_idesc_tf32(kTcBM, ncols, 0, 0);
+                const int acc = tcount & 1;
+                mbar_wait(&tempty[acc], ((tcount >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.acc_stride);
+                for (int q = 0; q < g.k_chunks; ++q, ++it) {
+                    const int s = it % g.stages;
+                    const uint32_t ph = (it / g.stages) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t a_lo = a_hi + kTcATile;
+                    const uint32_t b_hi = a_hi + 2 * kTcATile;
+                    const uint32_t b_lo = b_hi + b_tile_bytes;
+#pragma unroll
+                    for (int j = 0; j < kTcBK / 8; ++j) {
+                        const uint64_t dah = make_desc(a_hi + j * 2 * kTcALbo, kTcALbo, kTcASbo);
+                        const uint64_t dal = make_desc(a_lo + j * 2 * kTcALbo, kTcALbo, kTcASbo);
+                        const uint64_t dbh = make_desc(b_hi + j * 2 * kTcBLbo, kTcBLbo, kTcBSbo);
+                        const uint64_t dbl = make_desc(b_lo + j * 2 * kTcBLbo, kTcBLbo, kTcBSbo);
+                        // small terms first, the dominant hi*hi product last
+                        umma_tf32(d_tmem, dal, dbh, idesc, (q | j) ? 1u : 0u);
+                        umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+                        umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+                    }
+                    umma_commit(&empty[s]);          // frees the smem slot when the MMAs above have read it
+                }
+                umma_commit(&tfull[acc]);            // accumulator complete
+            }
+        }
+    } else {
+        // ================= epilogue: TMEM -> registers -> (+bias, +C) -> global =================
+        const int quarter = warp & 3;                // TMEM lanes 32*quarter .. +31 are accessible to this warp
+        uint32_t tcount = 0;
+        for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+            const int nt = (int)(tile % g.n_tiles);
+            const int64_t m0 = (tile / g.n_tiles) * kTcBM;
+            const int n0 = nt * g.bn;
+            const int ncols = min(g.bn, g.n - n0);
+            const int acc = tcount & 1;
+            mbar_wait(&tfull[acc], (tcount >> 1) & 1);
+            tc_fence_after();
+            const int64_t gm = m0 + quarter * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * g.acc_stride);
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+                float v[32];
+                tmem_ld_32x32(taddr + c0, v);        // warp-collective: executed by all lanes regardless of row validity
+                if (gm < g.m) {
+                    float* cp = g.c + gm * g.ldc + n0 + c0;
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4) {
+                        if (c0 + e < ncols) {        // ncols is a multiple of 16 => whole float4 valid
+                            float4 o = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                            if (g.accumulate) {
+                                const float4 old = *reinterpret_cast<const float4*>(cp + e);
+                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                            }
+                            if (g.bias) {
+                                const float4 b = ldg4(g.bias + n0 + c0 + e);
+                                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                            }
+                            *reinterpret_cast<float4*>(cp + e) = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kTcProducerWarps + 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, g.tmem_cols);
+    }
+}
+
+// per-128-row-tile column statistics of C (BatchNorm partials) when the tensor-core path produced C
+__global__ void __launch_bounds__(256) k_tile_col_stats(const float* __restrict__ c, int64_t ldc, int64_t m, int n, float* __restrict__ partials) {
+    const int64_t m0 = (int64_t)blockIdx.x * kTcBM;
+    const int rows = (int)min64(kTcBM, m - m0);
+    for (int col = threadIdx.x; col < n; col += blockDim.x) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int r = 0; r < rows; ++r) {
+            const float v = c[(m0 + r) * ldc + col];
+            s1 += v;
+            s2 = fmaf(v, v, s2);
+        }
+        partials[((int64_t)blockIdx.x * 2 + 0) * n + col] = s1;
+        partials[((int64_t)blockIdx.x * 2 + 1) * n + col] = s2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct TcPlan {
+    int bn, n_tiles, k_chunks, stages, acc_stride;
+    size_t smem_bytes, ws_bytes;
+    uint32_t tmem_cols;
+};
+
+static const int kSmemBudget = 227 * 1024;
+
+static TcPlan tc_plan(int n, int k) {
+    TcPlan p;
+    p.bn = n <= 256 ? n : 256;
+    p.n_tiles = (n + p.bn - 1) / p.bn;
+    p.k_chunks = (k + kTcBK - 1) / kTcBK;
+    int sb = tc_stage_bytes(p.bn);
+    int st = (kSmemBudget - 256) / sb;
+    p.stages = st > kTcMaxStages ? kTcMaxStages : st;
+    p.smem_bytes = (size_t)p.stages * sb + 256;
+    p.ws_bytes = (size_t)p.n_tiles * p.k_chunks * 2 * tc_b_tile_bytes(p.bn);
+    p.acc_stride = (p.bn + 31) / 32 * 32;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * p.acc_stride)) cols <<= 1;
+    p.tmem_cols = cols;
+    return p;
+}
+
+bool gemm_tc_supported(int64_t m, int n, int k, int64_t lda, int64_t ldc, const void* a, const void* c, const void* bias,
+                       const void* a_scale) {
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return n >= 16 && n % 16 == 0 && k >= 8 && k % 4 == 0 && lda % 4 == 0 && ldc % 4 == 0 && al16(a) && al16(c) &&
+           (!bias || al16(bias)) && (!a_scale || al16(a_scale)) && m >= 1;
+}
+
+size_t gemm_tc_workspace(int n, int k) { return tc_plan(n, k).ws_bytes + 256; }
+
+int gemm_tc_launch(const GemmArgs& g, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    TcPlan p = tc_plan(g.n, g.k);
+    if (!ws || ws_bytes < p.ws_bytes) {
+        set_error("sgb_gemm: tensor-core engine needs %zu bytes of workspace, got %zu", p.ws_bytes, ws_bytes);
+        return SGB_ENOSPC;
+    }
+    if (p.stages < 2) {
+        set_error("sgb_gemm: tile does not fit shared memory");
+        return SGB_ENOTSUP;
+    }
+    float* wp = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    {
+        int64_t total = (int64_t)p.n_tiles * p.k_chunks * (tc_b_tile_bytes(p.bn) / 4);
+        int grid = (int)min64(ceil_div(total, 256), (int64_t)num_sms() * 8);
+        k_prep_weights<<<grid, 256, 0, stream>>>(g.b, g.ldb, g.transb, g.n, g.k, p.bn, p.n_tiles, p.k_chunks, wp);
+        SGB_CHECK_LAUNCH("k_prep_weights");
+    }
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        SGB_CUDA(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        attr_set = true;
+    }
+    TcArgs t{};
+    t.a = g.a; t.lda = g.lda; t.wp = wp; t.c = g.c; t.ldc = g.ldc; t.m = g.m; t.n = g.n; t.k = g.k;
+    t.bn = p.bn; t.n_tiles = p.n_tiles; t.k_chunks = p.k_chunks; t.stages = p.stages;
+    t.a_scale = g.a_scale; t.a_shift = g.a_shift; t.slope = g.slope; t.bias = g.bias; t.accumulate = g.accumulate;
+    t.tmem_cols = p.tmem_cols; t.acc_stride = p.acc_stride;
+    int64_t tiles = ceil_div(g.m, kTcBM) * p.n_tiles;
+    int grid = (int)min64(tiles, num_sms());
+    k_gemm_tc<<<grid, kTcThreads, p.smem_bytes, stream>>>(t);
+    SGB_CHECK_LAUNCH("k_gemm_tc");
+    if (g.stat_partials) {
+        k_tile_col_stats<<<(unsigned)ceil_div(g.m, kTcBM), 256, 0, stream>>>(g.c, g.ldc, g.m, g.n, g.stat_partials);
+        SGB_CHECK_LAUNCH("k_tile_col_stats");
+    }
+    return SGB_OK;
+}
+
+}  // namespace sgb

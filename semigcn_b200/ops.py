@@ -150,10 +150,12 @@ def gemm(a: Tensor, b: Tensor, transb: bool = True, a_affine: Affine = None, bia
     sc, sh, slope = (a_affine if a_affine is not None else (None, None, 0.0))
     sp = _prof.span(f"gemm_n{n}_k{k}", 4.0 * (m * (k + n) + k * n + (m * n if accumulate else 0)), 2.0 * m * n * k) \
         if _prof.ACTIVE is not None else None
+    wsb = lib.sgb_gemm_workspace_bytes(m, n, k, engine)
+    ws = _ws(wsb, a.device) if wsb else None
     with torch.cuda.device(a.device):
         check(lib.sgb_gemm(1 if transb else 0, ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(c), c.stride(0), m, n, k,
                            ptr(sc), ptr(sh), float(slope), ptr(bias), 1 if accumulate else 0, ptr(partials),
-                           engine, stream_ptr(a.device)), "sgb_gemm")
+                           ptr(ws), wsb, engine, stream_ptr(a.device)), "sgb_gemm")
     if sp is not None:
         sp.close()
     L.count(1)

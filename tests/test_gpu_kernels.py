@@ -254,3 +254,48 @@ def test_bn_act_forward_backward_vs_torch(m, c, slope):
     # eval mode uses the running statistics
     bn.eval(); bn_ref.eval()
     assert_close(ops.bn_act(y.to(DEV), bn, slope), torch.nn.functional.leaky_relu(bn_ref(y.double()), slope), 2e-6, "eval")
+
+
+# ------------------------------------------------------------------ 5. tcgen05 3xTF32 engine
+TC_SHAPES = [(1000, 64, 64), (129, 16, 8), (5000, 256, 256), (4100, 512, 256), (3000, 128, 64), (2500, 256, 512), (1000, 48, 36),
+             (20000, 256, 128), (777, 80, 200)]
+
+
+@pytest.mark.parametrize("m,n,k", TC_SHAPES)
+@pytest.mark.parametrize("transb", [True, False])
+def test_gemm_tensor_core_engine_vs_fp64(m, n, k, transb):
+    """engine=2 (tcgen05, error-compensated 3xTF32) must hold the same fp32-level bar as the CUDA-core tiles."""
+    ops = _ops()
+    torch.manual_seed(m + n + k)
+    a = torch.randn(m, k)
+    b = torch.randn(n, k) if transb else torch.randn(k, n)
+    bias = torch.randn(n)
+    want = a.double() @ (b.double().t() if transb else b.double()) + bias.double()
+    got, partials = ops.gemm(a.to(DEV), b.to(DEV), transb=transb, bias=bias.to(DEV), want_stats=True, engine=2)
+    assert_close(got, want, 2e-6, "gemm tc")
+    s = partials.double().sum(0).cpu()
+    assert_close(s[0], want.sum(0), 1e-5, "stat sum")
+    assert_close(s[1], (want * want).sum(0), 1e-5, "stat sumsq")
+    c0 = torch.randn(m, n)
+    got2 = ops.gemm(a.to(DEV), b.to(DEV), transb=transb, out=c0.to(DEV).clone(), accumulate=True, engine=2)
+    assert_close(got2, want - bias.double() + c0.double(), 2e-6, "accumulate")
+    again = ops.gemm(a.to(DEV), b.to(DEV), transb=transb, bias=bias.to(DEV), engine=2)
+    assert torch.equal(got, again), "tensor-core path must be deterministic"
+
+
+def test_gemm_tensor_core_prologue_and_wide_dynamic_range():
+    ops = _ops()
+    torch.manual_seed(9)
+    m, n, k = 3000, 128, 256
+    a, b = torch.randn(m, k), torch.randn(n, k)
+    sc, sh = torch.rand(k) + 0.5, torch.randn(k)
+    z = torch.nn.functional.leaky_relu(a.double() * sc.double() + sh.double(), 0.01)
+    got = ops.gemm(a.to(DEV), b.to(DEV), a_affine=(sc.to(DEV), sh.to(DEV), 0.01), engine=2)
+    assert_close(got, z @ b.double().t(), 2e-6, "prologue")
+    # gradients span many orders of magnitude: the hi/lo split must not lose small rows
+    scale = torch.logspace(-12, 3, m).reshape(-1, 1)
+    a2 = a * scale
+    got = ops.gemm(a2.to(DEV), b.to(DEV), engine=2)
+    want = a2.double() @ b.double().t()
+    row_err = ((got.cpu().double() - want).abs().max(1)[0] / want.abs().max(1)[0]).max().item()
+    assert row_err <= 5e-6, f"row-relative error {row_err:.2e}"
