@@ -81,18 +81,20 @@ SGB_API int sgb_graph_build(const int64_t* edge_index, int64_t nnz, int64_t n, i
  *    dis, mode); accumulation order per row = CSR order then the self-loop term(s), with
  *    separately rounded multiply and add -- the op order of PyG's message/aggregate
  *    (SURVEY.md A.1 step 3, A.6), so the result is bit-identical to the CPU path.
- *    f (optional, in_scale != NULL): per-channel affine + LeakyReLU applied to every
- *    gathered element, f(x) = lrelu(x * in_scale[c] + in_shift[c], slope): the fused
- *    BatchNorm1d + LeakyReLU of the previous block (util/networks.py:26-27).
- *    stat_partials (optional): per-CTA column sums of Y and Y^2, laid out
- *    [sgb_spmm_stat_rows(n, c)][2][c]; feeds sgb_bn_finalize.
+ *    f (optional, in_scale != NULL): per-channel BatchNorm + LeakyReLU applied to every
+ *    gathered element in CENTRED form, f(x) = lrelu((x - in_mean[c]) * in_scale[c] +
+ *    in_shift[c], slope) with in_scale = gamma*invstd, in_shift = beta: the fused
+ *    BatchNorm1d + LeakyReLU of the previous block (util/networks.py:26-27).  (The uncentred
+ *    x*scale + shift' form cancels catastrophically on near-constant channels.)
+ *    stat_partials (optional): per-CTA column moments of Y as (count, mean, M2) triples,
+ *    laid out [sgb_spmm_stat_rows(n, c)][3][c]; feeds sgb_bn_finalize (Chan merge).
  *    Replaces MessagePassing.propagate (index_select -> mul -> scatter_add), fwd and,
  *    called with the transpose CSR, bwd.
  * ------------------------------------------------------------------------------------ */
 SGB_API int sgb_spmm_stat_rows(int64_t n, int c);
 SGB_API int sgb_spmm(const int32_t* rowptr, const int32_t* colidx, const float* dis, int mode,
              const float* x, int64_t ldx, int64_t n, int c,
-             const float* in_scale, const float* in_shift, float slope,
+             const float* in_mean, const float* in_scale, const float* in_shift, float slope,
              float alpha, const float* addend, int64_t ld_addend, float beta,
              const float* bias, float* y, int64_t ldy, float* stat_partials, void* stream);
 
@@ -101,8 +103,8 @@ SGB_API int sgb_spmm(const int32_t* rowptr, const int32_t* colidx, const float* 
  *    nn.Linear of util/networks.py:35,52,58-61) and its two gradients.
  *    sgb_gemm:       C[m,n] (+)= f(A)[m,k] * op(B) + bias,  op(B) = B^T for transb=1
  *                    (B is [n,k], i.e. a torch Linear weight) or B for transb=0 (B is [k,n]).
- *                    f = optional per-k-channel affine + LeakyReLU on A (as in sgb_spmm).
- *                    stat_partials: [sgb_gemm_stat_rows(m)][2][n] column sums of C, C^2.
+ *                    f = optional per-k-channel centred BatchNorm + LeakyReLU on A (as in sgb_spmm).
+ *                    stat_partials: [sgb_gemm_stat_rows(m)][3][n] column (count, mean, M2) of C.
  *    sgb_gemm_tn:    D[n,k] (+)= G[m,n]^T * A[m,k]   (weight gradient; split over m with a
  *                    fixed-order two-stage reduction -> deterministic).
  *    sgb_colsum:     out[n] (+)= sum_m G[m,n]        (bias gradient).
@@ -114,7 +116,7 @@ SGB_API int sgb_gemm_stat_rows(int64_t m);
 SGB_API size_t sgb_gemm_workspace_bytes(int64_t m, int n, int k, int engine);
 SGB_API int sgb_gemm(int transb, const float* a, int64_t lda, const float* b, int64_t ldb,
              float* c, int64_t ldc, int64_t m, int n, int k,
-             const float* a_scale, const float* a_shift, float slope,
+             const float* a_mean, const float* a_scale, const float* a_shift, float slope,
              const float* bias, int accumulate, float* stat_partials,
              void* workspace, size_t workspace_bytes, int engine, void* stream);
 SGB_API size_t sgb_gemm_tn_workspace_bytes(int64_t m, int n, int k);
@@ -128,12 +130,12 @@ SGB_API int sgb_colsum(const float* g, int64_t ldg, int64_t m, int n, float* out
 /* ------------------------------------------------------------------------------------ *
  * 4. BatchNorm1d (batch statistics over all vertices) + LeakyReLU, forward and backward.
  *    Replaces nn.BatchNorm1d + nn.LeakyReLU between convs (util/networks.py:26-27,43-44).
- *    sgb_col_stats      : partials[rows][2][c] of (sum, sum of squares) for a matrix that was
+ *    sgb_col_stats      : partials[rows][3][c] of (count, mean, M2) for a matrix that was
  *                         not produced by one of our kernels.
- *    sgb_bn_finalize    : fp64 reduction of the partials -> mean, invstd (biased var, eps),
- *                         scale = gamma*invstd, shift = beta - mean*scale; updates running
- *                         stats (momentum, unbiased var) when running_mean != NULL.
- *    sgb_bn_act_apply   : Z = lrelu(Y*scale + shift, slope).
+ *    sgb_bn_finalize    : fp64 Chan merge of the partials -> mean, invstd (biased var, eps),
+ *                         scale = gamma*invstd, shift = beta; updates running stats
+ *                         (momentum, unbiased var) when running_mean != NULL.
+ *    sgb_bn_act_apply   : Z = lrelu((Y - mean)*scale + shift, slope).
  *    sgb_bn_act_bwd_reduce / _apply : dY from dZ (two-pass: per-channel sums, then apply).
  * ------------------------------------------------------------------------------------ */
 SGB_API int sgb_col_stat_rows(int64_t m, int c);
@@ -142,9 +144,9 @@ SGB_API int sgb_bn_finalize(const float* partials, int rows, int c, int64_t coun
                     const float* gamma, const float* beta, float eps, float momentum,
                     float* running_mean, float* running_var,
                     float* mean, float* invstd, float* scale, float* shift, void* stream);
-SGB_API int sgb_bn_act_apply(const float* y, int64_t ldy, int64_t m, int c, const float* scale,
+SGB_API int sgb_bn_act_apply(const float* y, int64_t ldy, int64_t m, int c, const float* mean, const float* scale,
                      const float* shift, float slope, float* z, int64_t ldz, void* stream);
-/* partials[rows][2][c]: (sum dA, sum dA*xhat) with dA = dZ * lrelu'(Y*scale+shift) */
+/* partials[rows][2][c]: (sum dA, sum dA*xhat) with dA = dZ * lrelu'((Y-mean)*scale+shift) */
 SGB_API int sgb_bn_act_bwd_reduce(const float* dz, int64_t lddz, const float* y, int64_t ldy, int64_t m, int c,
                           const float* scale, const float* shift, const float* mean, const float* invstd,
                           float slope, float* partials, void* stream);

@@ -30,11 +30,11 @@ SIGNATURES = {
     "sgb_graph_build_workspace_bytes": (_sz, [_i64, _i64]),
     "sgb_graph_build": (_i32, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sgb_spmm_stat_rows": (_i32, [_i64, _i32]),
-    "sgb_spmm": (_i32, [_vp, _vp, _vp, _i32, _vp, _i64, _i64, _i32, _vp, _vp, _f32, _f32, _vp, _i64, _f32,
+    "sgb_spmm": (_i32, [_vp, _vp, _vp, _i32, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _f32, _f32, _vp, _i64, _f32,
                         _vp, _vp, _i64, _vp, _vp]),
     "sgb_gemm_stat_rows": (_i32, [_i64]),
     "sgb_gemm_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
-    "sgb_gemm": (_i32, [_i32, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _f32, _vp, _i32,
+    "sgb_gemm": (_i32, [_i32, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _i32,
                         _vp, _vp, _sz, _i32, _vp]),
     "sgb_gemm_tn_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "sgb_gemm_tn": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _sz, _i32, _vp]),
@@ -43,7 +43,7 @@ SIGNATURES = {
     "sgb_col_stat_rows": (_i32, [_i64, _i32]),
     "sgb_col_stats": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp]),
     "sgb_bn_finalize": (_i32, [_vp, _i32, _i32, _i64, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "sgb_bn_act_apply": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _f32, _vp, _i64, _vp]),
+    "sgb_bn_act_apply": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _f32, _vp, _i64, _vp]),
     "sgb_bn_act_bwd_reduce": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _f32, _vp, _vp]),
     "sgb_bn_bwd_finalize": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp]),
     "sgb_bn_act_bwd_apply": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _i32,

@@ -21,7 +21,7 @@ struct ColArgs {
     int64_t m; int c;
     const float* scale; const float* shift; const float* mean; const float* invstd;
     float slope;
-    float* partials;                    // [gridDim.x][2][c]
+    float* partials;                    // STATS: [gridDim.x][3][c] (count, mean, M2); others: [gridDim.x][2][c] sums
 };
 
 // One thread owns VEC channels of one row-lane; rows are grid-strided; fixed-order smem
@@ -29,6 +29,7 @@ struct ColArgs {
 template <int OP, int VEC>
 __global__ void __launch_bounds__(kColThreads) k_col_reduce(const ColArgs a, int tpr /* threads per row, pow2 <= 256 */) {
     __shared__ float red[2][kColThreads * VEC];
+    __shared__ float redn[kColThreads];
     const int cl = threadIdx.x % tpr;
     const int rl = threadIdx.x / tpr;
     const int rows_per_pass = kColThreads / tpr;
@@ -68,30 +69,56 @@ __global__ void __launch_bounds__(kColThreads) k_col_reduce(const ColArgs a, int
                     } else if (OP == COL_SUM) {
                         s1[q] += (double)yv[q];
                     } else {
-                        const float pre = fmaf(yv[q], sc[q], sh[q]);
+                        const float ctr = yv[q] - mu[q];
+                        const float pre = fmaf(ctr, sc[q], sh[q]);
                         const float da = pre > 0.f ? dv[q] : dv[q] * a.slope;
-                        const float xh = (yv[q] - mu[q]) * is[q];
+                        const float xh = ctr * is[q];
                         s1[q] += (double)da;
                         s2[q] += (double)da * (double)xh;
                     }
                 }
             }
         }
+        if (OP == COL_STATS) {
+            // rows this thread visited: r = blockIdx.x*rpp + rl + i*gridDim.x*rpp < m
+            const int64_t first = (int64_t)blockIdx.x * rows_per_pass + rl;
+            const int64_t stride = (int64_t)gridDim.x * rows_per_pass;
+            const double nrows = first < a.m ? (double)((a.m - 1 - first) / stride + 1) : 0.0;
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) {
-            red[0][(rl * tpr + cl) * VEC + q] = (float)s1[q];
-            red[1][(rl * tpr + cl) * VEC + q] = (float)s2[q];
+            for (int q = 0; q < VEC; ++q) {
+                const double mean = nrows > 0.0 ? s1[q] / nrows : 0.0;
+                double m2 = nrows > 0.0 ? s2[q] - s1[q] * mean : 0.0;
+                if (m2 < 0.0) m2 = 0.0;
+                red[0][(rl * tpr + cl) * VEC + q] = (float)mean;
+                red[1][(rl * tpr + cl) * VEC + q] = (float)m2;
+            }
+            if (cl == 0) redn[rl] = (float)nrows;
+        } else {
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) {
+                red[0][(rl * tpr + cl) * VEC + q] = (float)s1[q];
+                red[1][(rl * tpr + cl) * VEC + q] = (float)s2[q];
+            }
         }
         __syncthreads();
         for (int i = threadIdx.x; i < tpr * VEC; i += kColThreads) {
             if (c0 + i < a.c) {
-                float t1 = 0.f, t2 = 0.f;
-                for (int r = 0; r < rows_per_pass; ++r) {
-                    t1 += red[0][r * tpr * VEC + i];
-                    t2 += red[1][r * tpr * VEC + i];
+                if (OP == COL_STATS) {
+                    Moments acc{0.f, 0.f, 0.f};
+                    for (int r = 0; r < rows_per_pass; ++r)
+                        acc = merge(acc, Moments{redn[r], red[0][r * tpr * VEC + i], red[1][r * tpr * VEC + i]});
+                    a.partials[((int64_t)blockIdx.x * 3 + 0) * a.c + c0 + i] = acc.n;
+                    a.partials[((int64_t)blockIdx.x * 3 + 1) * a.c + c0 + i] = acc.mean;
+                    a.partials[((int64_t)blockIdx.x * 3 + 2) * a.c + c0 + i] = acc.m2;
+                } else {
+                    float t1 = 0.f, t2 = 0.f;
+                    for (int r = 0; r < rows_per_pass; ++r) {
+                        t1 += red[0][r * tpr * VEC + i];
+                        t2 += red[1][r * tpr * VEC + i];
+                    }
+                    a.partials[((int64_t)blockIdx.x * 2 + 0) * a.c + c0 + i] = t1;
+                    a.partials[((int64_t)blockIdx.x * 2 + 1) * a.c + c0 + i] = t2;
                 }
-                a.partials[((int64_t)blockIdx.x * 2 + 0) * a.c + c0 + i] = t1;
-                a.partials[((int64_t)blockIdx.x * 2 + 1) * a.c + c0 + i] = t2;
             }
         }
         __syncthreads();
@@ -124,8 +151,9 @@ static int col_launch(const ColArgs& a, bool vec_ok, cudaStream_t stream) {
     int vec = (a.c % 4 == 0 && vec_ok) ? 4 : 1;
     int grid = col_rows_cfg(a.m, a.c, vec);
     int rows = col_rows(a.m, a.c);
+    const int planes = OP == COL_STATS ? 3 : 2;
     if (rows > grid)
-        if (cudaMemsetAsync(a.partials + (size_t)grid * 2 * a.c, 0, (size_t)(rows - grid) * 2 * a.c * sizeof(float), stream) != cudaSuccess) {
+        if (cudaMemsetAsync(a.partials + (size_t)grid * planes * a.c, 0, (size_t)(rows - grid) * planes * a.c * sizeof(float), stream) != cudaSuccess) {
             set_error("col_reduce: memset failed");
             return SGB_ECUDA;
         }
@@ -149,67 +177,90 @@ struct FinArgs {
 };
 
 __global__ void __launch_bounds__(1024) k_finalize(const FinArgs f) {
-    __shared__ double r1[32][33], r2[32][33];
+    __shared__ double r1[32][33], r2[32][33], r3[32][33];
     const int ch = blockIdx.x * 32 + threadIdx.x;
-    double s1 = 0.0, s2 = 0.0;
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
     if (ch < f.c) {
-        for (int r = threadIdx.y; r < f.rows; r += 32) {
-            s1 += (double)__ldg(f.partials + ((int64_t)r * 2 + 0) * f.c + ch);
-            s2 += (double)__ldg(f.partials + ((int64_t)r * 2 + 1) * f.c + ch);
+        if (f.kind == 0) {       // (count, mean, M2) rows: Chan merge in fp64, fixed order
+            for (int r = threadIdx.y; r < f.rows; r += 32) {
+                const double nb = (double)__ldg(f.partials + ((int64_t)r * 3 + 0) * f.c + ch);
+                if (nb == 0.0) continue;
+                const double mb = (double)__ldg(f.partials + ((int64_t)r * 3 + 1) * f.c + ch);
+                const double qb = (double)__ldg(f.partials + ((int64_t)r * 3 + 2) * f.c + ch);
+                const double nt = s1 + nb, d = mb - s2;
+                s3 += qb + d * d * s1 * nb / nt;
+                s2 += d * nb / nt;
+                s1 = nt;
+            }
+        } else {
+            for (int r = threadIdx.y; r < f.rows; r += 32) {
+                s1 += (double)__ldg(f.partials + ((int64_t)r * 2 + 0) * f.c + ch);
+                s2 += (double)__ldg(f.partials + ((int64_t)r * 2 + 1) * f.c + ch);
+            }
         }
     }
     r1[threadIdx.y][threadIdx.x] = s1;
     r2[threadIdx.y][threadIdx.x] = s2;
+    r3[threadIdx.y][threadIdx.x] = s3;
     __syncthreads();
     if (threadIdx.y == 0 && ch < f.c) {
-        double t1 = 0.0, t2 = 0.0;
-        for (int r = 0; r < 32; ++r) { t1 += r1[r][threadIdx.x]; t2 += r2[r][threadIdx.x]; }
         if (f.kind == 0) {
-            const double n = (double)f.count;
-            const double mean = t1 / n;
-            double var = t2 / n - mean * mean;
+            double n = 0.0, mean = 0.0, m2 = 0.0;
+            for (int r = 0; r < 32; ++r) {
+                const double nb = r1[r][threadIdx.x];
+                if (nb == 0.0) continue;
+                const double nt = n + nb, d = r2[r][threadIdx.x] - mean;
+                m2 += r3[r][threadIdx.x] + d * d * n * nb / nt;
+                mean += d * nb / nt;
+                n = nt;
+            }
+            double var = n > 0.0 ? m2 / n : 0.0;
             if (var < 0.0) var = 0.0;
             const double invstd = 1.0 / sqrt(var + (double)f.eps);
             const double g = f.gamma ? (double)f.gamma[ch] : 1.0;
             const double b = f.beta ? (double)f.beta[ch] : 0.0;
             f.mean[ch] = (float)mean;
             f.invstd[ch] = (float)invstd;
-            const float scale = (float)(g * invstd);
-            f.scale[ch] = scale;
-            f.shift[ch] = (float)(b - mean * (double)scale);
+            f.scale[ch] = (float)(g * invstd);
+            f.shift[ch] = (float)b;            // centred form: z = (y - mean) * scale + beta
             if (f.running_mean) {
-                const double unb = n > 1.0 ? var * n / (n - 1.0) : var;
+                const double unb = n > 1.0 ? m2 / (n - 1.0) : var;
                 f.running_mean[ch] = (float)((1.0 - f.momentum) * (double)f.running_mean[ch] + f.momentum * mean);
                 f.running_var[ch] = (float)((1.0 - f.momentum) * (double)f.running_var[ch] + f.momentum * unb);
             }
-        } else if (f.kind == 1) {
-            f.sums[ch] = (float)t1;
-            f.sums[f.c + ch] = (float)t2;
-            if (f.dbeta) f.dbeta[ch] = f.accumulate ? f.dbeta[ch] + (float)t1 : (float)t1;
-            if (f.dgamma) f.dgamma[ch] = f.accumulate ? f.dgamma[ch] + (float)t2 : (float)t2;
         } else {
-            f.sums[ch] = f.accumulate ? f.sums[ch] + (float)t1 : (float)t1;
+            double t1 = 0.0, t2 = 0.0;
+            for (int r = 0; r < 32; ++r) { t1 += r1[r][threadIdx.x]; t2 += r2[r][threadIdx.x]; }
+            if (f.kind == 1) {
+                f.sums[ch] = (float)t1;
+                f.sums[f.c + ch] = (float)t2;
+                if (f.dbeta) f.dbeta[ch] = f.accumulate ? f.dbeta[ch] + (float)t1 : (float)t1;
+                if (f.dgamma) f.dgamma[ch] = f.accumulate ? f.dgamma[ch] + (float)t2 : (float)t2;
+            } else {
+                f.sums[ch] = f.accumulate ? f.sums[ch] + (float)t1 : (float)t1;
+            }
         }
     }
 }
 
 // ---- elementwise ------------------------------------------------------------------------
 template <int VEC>
-__global__ void k_bn_act_apply(const float* __restrict__ y, int64_t ldy, int64_t m, int c, const float* __restrict__ scale,
-                               const float* __restrict__ shift, float slope, float* __restrict__ z, int64_t ldz) {
+__global__ void k_bn_act_apply(const float* __restrict__ y, int64_t ldy, int64_t m, int c, const float* __restrict__ mean,
+                               const float* __restrict__ scale, const float* __restrict__ shift, float slope,
+                               float* __restrict__ z, int64_t ldz) {
     const int cv = c / VEC;
     const int64_t total = m * cv;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / cv;
         const int ch = (int)(i % cv) * VEC;
         if (VEC == 4) {
-            const float4 v = ldg4(y + r * ldy + ch), s = ldg4(scale + ch), b = ldg4(shift + ch);
+            const float4 v = ldg4(y + r * ldy + ch), mu = ldg4(mean + ch), s = ldg4(scale + ch), b = ldg4(shift + ch);
             float4 o;
-            o.x = lrelu(fmaf(v.x, s.x, b.x), slope); o.y = lrelu(fmaf(v.y, s.y, b.y), slope);
-            o.z = lrelu(fmaf(v.z, s.z, b.z), slope); o.w = lrelu(fmaf(v.w, s.w, b.w), slope);
+            o.x = bn_lrelu(v.x, mu.x, s.x, b.x, slope); o.y = bn_lrelu(v.y, mu.y, s.y, b.y, slope);
+            o.z = bn_lrelu(v.z, mu.z, s.z, b.z, slope); o.w = bn_lrelu(v.w, mu.w, s.w, b.w, slope);
             st4(z + r * ldz + ch, o);
         } else {
-            z[r * ldz + ch] = lrelu(fmaf(__ldg(y + r * ldy + ch), __ldg(scale + ch), __ldg(shift + ch)), slope);
+            z[r * ldz + ch] = bn_lrelu(__ldg(y + r * ldy + ch), __ldg(mean + ch), __ldg(scale + ch), __ldg(shift + ch), slope);
         }
     }
 }
@@ -240,10 +291,11 @@ __global__ void k_bn_act_bwd_apply(const BwdArgs a) {
 #pragma unroll
         for (int q = 0; q < VEC; ++q) {
             const float sc = __ldg(a.scale + ch + q), sh = __ldg(a.shift + ch + q);
-            const float pre = fmaf(yv[q], sc, sh);
+            const float ctr = yv[q] - __ldg(a.mean + ch + q);
+            const float pre = fmaf(ctr, sc, sh);
             const float da = pre > 0.f ? dv[q] : dv[q] * a.slope;
             if (a.training) {
-                const float xh = (yv[q] - __ldg(a.mean + ch + q)) * __ldg(a.invstd + ch + q);
+                const float xh = ctr * __ldg(a.invstd + ch + q);
                 const float sb = __ldg(a.sums + ch + q) * inv_m, sg = __ldg(a.sums + a.c + ch + q) * inv_m;
                 out[q] = sc * (da - sb - xh * sg);
             } else {
@@ -291,13 +343,13 @@ extern "C" int sgb_bn_finalize(const float* partials, int rows, int c, int64_t c
     return SGB_OK;
 }
 
-extern "C" int sgb_bn_act_apply(const float* y, int64_t ldy, int64_t m, int c, const float* scale, const float* shift, float slope,
-                                float* z, int64_t ldz, void* stream) {
-    SGB_CHECK_ARG(y && z && scale && shift && m >= 0 && c > 0 && ldy >= c && ldz >= c, "sgb_bn_act_apply: bad argument");
+extern "C" int sgb_bn_act_apply(const float* y, int64_t ldy, int64_t m, int c, const float* mean, const float* scale,
+                                const float* shift, float slope, float* z, int64_t ldz, void* stream) {
+    SGB_CHECK_ARG(y && z && mean && scale && shift && m >= 0 && c > 0 && ldy >= c && ldz >= c, "sgb_bn_act_apply: bad argument");
     if (m == 0) return SGB_OK;
-    bool vec = c % 4 == 0 && al16(y) && al16(z) && al16(scale) && al16(shift) && ldy % 4 == 0 && ldz % 4 == 0;
-    if (vec) k_bn_act_apply<4><<<ew_grid(m * (c / 4)), 256, 0, (cudaStream_t)stream>>>(y, ldy, m, c, scale, shift, slope, z, ldz);
-    else k_bn_act_apply<1><<<ew_grid(m * c), 256, 0, (cudaStream_t)stream>>>(y, ldy, m, c, scale, shift, slope, z, ldz);
+    bool vec = c % 4 == 0 && al16(y) && al16(z) && al16(mean) && al16(scale) && al16(shift) && ldy % 4 == 0 && ldz % 4 == 0;
+    if (vec) k_bn_act_apply<4><<<ew_grid(m * (c / 4)), 256, 0, (cudaStream_t)stream>>>(y, ldy, m, c, mean, scale, shift, slope, z, ldz);
+    else k_bn_act_apply<1><<<ew_grid(m * c), 256, 0, (cudaStream_t)stream>>>(y, ldy, m, c, mean, scale, shift, slope, z, ldz);
     SGB_CHECK_LAUNCH("k_bn_act_apply");
     return SGB_OK;
 }
@@ -329,7 +381,7 @@ extern "C" int sgb_bn_act_bwd_apply(const float* dz, int64_t lddz, const float* 
                                     int training, float* dy, int64_t lddy, void* stream) {
     SGB_CHECK_ARG(dz && y && dy && scale && shift && m >= 0 && c > 0 && ldy >= c && lddz >= c && lddy >= c,
                   "sgb_bn_act_bwd_apply: bad argument");
-    SGB_CHECK_ARG(!training || (mean && invstd && sums), "sgb_bn_act_bwd_apply: training mode needs mean/invstd/sums");
+    SGB_CHECK_ARG(mean && (!training || (invstd && sums)), "sgb_bn_act_bwd_apply: mean required; training mode also needs invstd/sums");
     if (m == 0) return SGB_OK;
     BwdArgs a{dz, lddz, y, ldy, m, c, scale, shift, mean, invstd, sums, slope, training, dy, lddy};
     bool vec = c % 4 == 0 && al16(y) && al16(dz) && al16(dy) && ldy % 4 == 0 && lddz % 4 == 0 && lddy % 4 == 0;

@@ -43,6 +43,39 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
 
+// fused BatchNorm + LeakyReLU on load: centred form (x - mean) * scale + beta.  The uncentred
+// x*scale + (beta - mean*scale) cancels catastrophically when |mean| >> std (near-constant channels).
+__device__ __forceinline__ float bn_lrelu(float x, float mean, float scale, float beta, float slope) {
+    return lrelu(fmaf(x - mean, scale, beta), slope);
+}
+
+// BatchNorm statistic partials are (count, mean, M2 = sum (x-mean)^2) triples, merged with Chan's
+// parallel formula -- sum / sum-of-squares partials lose the variance of near-constant channels.
+struct Moments {
+    float n, mean, m2;
+};
+__device__ __forceinline__ Moments merge(Moments a, Moments b) {
+    if (b.n == 0.f) return a;
+    if (a.n == 0.f) return b;
+    Moments r;
+    r.n = a.n + b.n;
+    const float d = b.mean - a.mean;
+    const float w = b.n / r.n;
+    r.mean = fmaf(d, w, a.mean);
+    r.m2 = a.m2 + b.m2 + d * d * a.n * w;
+    return r;
+}
+// from pivot-shifted sums: s1 = sum (x - p), s2 = sum (x - p)^2 over n values
+__device__ __forceinline__ Moments from_shifted(float n, float p, float s1, float s2) {
+    Moments r;
+    r.n = n;
+    if (n == 0.f) { r.mean = 0.f; r.m2 = 0.f; return r; }
+    const float dm = s1 / n;
+    r.mean = p + dm;
+    r.m2 = fmaxf(s2 - s1 * dm, 0.f);
+    return r;
+}
+
 // streaming 128-bit load/store helpers (read-only path; Y/Z outputs are written once)
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
@@ -54,7 +87,7 @@ struct GemmArgs {
     const float* b; int64_t ldb;
     float* c; int64_t ldc;
     int64_t m; int n; int k;
-    const float* a_scale; const float* a_shift; float slope;
+    const float* a_mean; const float* a_scale; const float* a_shift; float slope;
     const float* bias; int accumulate; float* stat_partials;
 };
 

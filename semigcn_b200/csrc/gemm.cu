@@ -11,6 +11,11 @@ bool gemm_tc_supported(int64_t m, int n, int k, int64_t lda, int64_t ldc, const 
                        const void* a_scale);
 size_t gemm_tc_workspace(int n, int k);
 int gemm_tc_launch(const GemmArgs& g, void* ws, size_t ws_bytes, cudaStream_t stream);
+bool gemm_tn_tc_supported(int64_t m, int n, int k, int64_t ldg, int64_t lda, const void* g, const void* a);
+size_t gemm_tn_tc_workspace(int64_t m, int n, int k);
+int gemm_tn_tc_launch(const float* g, int64_t ldg, const float* a, int64_t lda, float* d, int64_t ldd, int64_t m, int n, int k,
+                      int accumulate, void* ws, size_t ws_bytes, cudaStream_t stream);
+static bool tn_tc_worthwhile(int64_t m, int n, int k) { return n >= 64 && k >= 32 && m >= 4096; }
 
 // auto policy: the tensor pipe only where the transform is a real dense contraction
 static bool tc_worthwhile(int64_t m, int n, int k) { return n >= 64 && k >= 32 && m >= 2048; }
@@ -28,14 +33,15 @@ extern "C" size_t sgb_gemm_workspace_bytes(int64_t m, int n, int k, int engine) 
 }
 
 extern "C" int sgb_gemm(int transb, const float* a, int64_t lda, const float* b, int64_t ldb, float* c, int64_t ldc, int64_t m,
-                        int n, int k, const float* a_scale, const float* a_shift, float slope, const float* bias, int accumulate,
-                        float* stat_partials, void* workspace, size_t workspace_bytes, int engine, void* stream) {
+                        int n, int k, const float* a_mean, const float* a_scale, const float* a_shift, float slope, const float* bias,
+                        int accumulate, float* stat_partials, void* workspace, size_t workspace_bytes, int engine, void* stream) {
     SGB_CHECK_ARG(a && b && c && m >= 0 && n > 0 && k > 0, "sgb_gemm: bad argument m=%lld n=%d k=%d", (long long)m, n, k);
     SGB_CHECK_ARG(lda >= k && ldc >= n && ldb >= (transb ? k : n), "sgb_gemm: leading dimension too small");
-    SGB_CHECK_ARG((a_scale == nullptr) == (a_shift == nullptr), "sgb_gemm: a_scale / a_shift must come together");
+    SGB_CHECK_ARG((a_scale == nullptr) == (a_shift == nullptr) && (a_scale == nullptr) == (a_mean == nullptr),
+                  "sgb_gemm: a_mean / a_scale / a_shift must come together");
     SGB_CHECK_ARG(engine >= 0 && engine <= 2, "sgb_gemm: bad engine %d", engine);
     if (m == 0) return SGB_OK;
-    GemmArgs g{transb, a, lda, b, ldb, c, ldc, m, n, k, a_scale, a_shift, slope, bias, accumulate, stat_partials};
+    GemmArgs g{transb, a, lda, b, ldb, c, ldc, m, n, k, a_mean, a_scale, a_shift, slope, bias, accumulate, stat_partials};
     const bool tc_ok = gemm_tc_supported(m, n, k, lda, ldc, a, c, bias, a_scale);
     if (engine == 2) {
         if (!tc_ok) {
@@ -51,7 +57,8 @@ extern "C" int sgb_gemm(int transb, const float* a, int64_t lda, const float* b,
 
 extern "C" size_t sgb_gemm_tn_workspace_bytes(int64_t m, int n, int k) {
     if (m < 0 || n <= 0 || k <= 0) return 0;
-    return gemm_tn_simt_workspace(m, n, k);
+    size_t a = gemm_tn_simt_workspace(m, n, k), b = (n % 4 == 0 && k % 4 == 0) ? gemm_tn_tc_workspace(m, n, k) : 0;
+    return a > b ? a : b;
 }
 
 extern "C" int sgb_gemm_tn(const float* g, int64_t ldg, const float* a, int64_t lda, float* d, int64_t ldd, int64_t m, int n, int k,
@@ -59,9 +66,15 @@ extern "C" int sgb_gemm_tn(const float* g, int64_t ldg, const float* a, int64_t 
     SGB_CHECK_ARG(g && a && d && m >= 0 && n > 0 && k > 0, "sgb_gemm_tn: bad argument");
     SGB_CHECK_ARG(ldg >= n && lda >= k && ldd >= k, "sgb_gemm_tn: leading dimension too small");
     SGB_CHECK_ARG(engine >= 0 && engine <= 2, "sgb_gemm_tn: bad engine %d", engine);
+    const bool tc_ok = gemm_tn_tc_supported(m, n, k, ldg, lda, g, a);
     if (engine == 2) {
-        set_error("sgb_gemm_tn: tcgen05 engine not available for this shape");
-        return SGB_ENOTSUP;
+        if (!tc_ok) {
+            set_error("sgb_gemm_tn: tcgen05 engine needs n %% 4 == 0, k %% 4 == 0 and 16-byte aligned operands");
+            return SGB_ENOTSUP;
+        }
+        return gemm_tn_tc_launch(g, ldg, a, lda, d, ldd, m, n, k, accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
     }
+    if (engine == 0 && tc_ok && tn_tc_worthwhile(m, n, k))
+        return gemm_tn_tc_launch(g, ldg, a, lda, d, ldd, m, n, k, accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
     return gemm_tn_simt_launch(g, ldg, a, lda, d, ldd, m, n, k, accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
 }

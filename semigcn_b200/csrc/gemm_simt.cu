@@ -18,8 +18,9 @@ constexpr int kGemmThreads = 256;
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads) k_gemm_simt(const GemmArgs g) {
     constexpr int BM = kGemmBM, BK = kGemmBK, TM = 8, TN = BN / 16;
-    __shared__ __align__(16) float As[BK][BM + 4];
-    __shared__ __align__(16) float Bs[BK][BN + 4];
+    __shared__ __align__(16) float smem_ab[BK * (BM + 4) + BK * (BN + 4)];
+    float (*As)[BM + 4] = reinterpret_cast<float (*)[BM + 4]>(smem_ab);
+    float (*Bs)[BN + 4] = reinterpret_cast<float (*)[BN + 4]>(smem_ab + BK * (BM + 4));
     const int tid = threadIdx.x;
     const int tx = tid % 16, ty = tid / 16;
     const int64_t m0 = (int64_t)blockIdx.x * BM;
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(kGemmThreads) k_gemm_simt(const GemmArgs g) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
                         if (k0 + kq + q < g.k)
-                            v[q] = lrelu(fmaf(v[q], __ldg(g.a_scale + k0 + kq + q), __ldg(g.a_shift + k0 + kq + q)), g.slope);
+                            v[q] = bn_lrelu(v[q], __ldg(g.a_mean + k0 + kq + q), __ldg(g.a_scale + k0 + kq + q), __ldg(g.a_shift + k0 + kq + q), g.slope);
                 }
             }
 #pragma unroll
@@ -121,46 +122,60 @@ __global__ void __launch_bounds__(kGemmThreads) k_gemm_simt(const GemmArgs g) {
         __syncthreads();
     }
 
-    // ---- epilogue: (+C) + bias, store, per-tile column statistics
-    float cs1[TN], cs2[TN];
-#pragma unroll
-    for (int j = 0; j < TN; ++j) { cs1[j] = 0.f; cs2[j] = 0.f; }
+    // ---- epilogue: (+C) + bias, store, per-tile column moments (count, mean, M2)
+    Moments mo[TN];
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
+        mo[j] = Moments{0.f, 0.f, 0.f};
         const int gn = n0 + tx + 16 * j;
         if (gn >= g.n) continue;
         const float bj = g.bias ? __ldg(g.bias + gn) : 0.f;
+        float vals[TM];
+        float cnt = 0.f, sum = 0.f;
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
             const int64_t gm = m0 + ty * TM + i;
+            vals[i] = 0.f;
             if (gm >= g.m) continue;
             float* cp = g.c + gm * g.ldc + gn;
             float v = acc[i][j];
             if (g.accumulate) v += *cp;
             v += bj;
             *cp = v;
-            cs1[j] += v;
-            cs2[j] = fmaf(v, v, cs2[j]);
+            vals[i] = v;
+            cnt += 1.f;
+            sum += v;
+        }
+        if (cnt > 0.f) {          // two-pass over the thread's own 8 rows
+            const float mean = sum / cnt;
+            float m2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+                if (m0 + ty * TM + i < g.m) { const float d = vals[i] - mean; m2 = fmaf(d, d, m2); }
+            mo[j] = Moments{cnt, mean, m2};
         }
     }
     if (g.stat_partials) {
         __syncthreads();
-        float* r1 = &As[0][0];           // reuse: [16 ty][BN]
-        float* r2 = &Bs[0][0];
-        static_assert(16 * BN <= BK * (BM + 4) && 16 * BN <= BK * (BN + 4), "reduction scratch");
+        __shared__ float red[3 * 16 * BN];   // 3 planes of [16 ty][BN]
+        float* r0 = red;
+        float* r1 = r0 + 16 * BN;
+        float* r2 = r1 + 16 * BN;
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-            r1[ty * BN + tx + 16 * j] = cs1[j];
-            r2[ty * BN + tx + 16 * j] = cs2[j];
+            r0[ty * BN + tx + 16 * j] = mo[j].n;
+            r1[ty * BN + tx + 16 * j] = mo[j].mean;
+            r2[ty * BN + tx + 16 * j] = mo[j].m2;
         }
         __syncthreads();
         for (int cl = tid; cl < BN; cl += kGemmThreads) {
             if (n0 + cl < g.n) {
-                float t1 = 0.f, t2 = 0.f;
+                Moments a{0.f, 0.f, 0.f};
 #pragma unroll
-                for (int r = 0; r < 16; ++r) { t1 += r1[r * BN + cl]; t2 += r2[r * BN + cl]; }
-                g.stat_partials[((int64_t)blockIdx.x * 2 + 0) * g.n + n0 + cl] = t1;
-                g.stat_partials[((int64_t)blockIdx.x * 2 + 1) * g.n + n0 + cl] = t2;
+                for (int r = 0; r < 16; ++r) a = merge(a, Moments{r0[r * BN + cl], r1[r * BN + cl], r2[r * BN + cl]});
+                g.stat_partials[((int64_t)blockIdx.x * 3 + 0) * g.n + n0 + cl] = a.n;
+                g.stat_partials[((int64_t)blockIdx.x * 3 + 1) * g.n + n0 + cl] = a.mean;
+                g.stat_partials[((int64_t)blockIdx.x * 3 + 2) * g.n + n0 + cl] = a.m2;
             }
         }
     }

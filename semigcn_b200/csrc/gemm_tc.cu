@@ -115,8 +115,8 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 
 // shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout_type=0 [61,64))
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 0) {
+    uint64_t d = (uint64_t)(layout_type & 7) << 61;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
@@ -155,7 +155,7 @@ struct TcArgs {
     int64_t m; int n; int k;
     int bn;                           // columns per n-tile (multiple of 16, <= 256); all n-tiles but the last are full
     int n_tiles; int k_chunks; int stages;
-    const float* a_scale; const float* a_shift; float slope;
+    const float* a_mean; const float* a_scale; const float* a_shift; float slope;
     const float* bias; int accumulate;
     uint32_t tmem_cols;
     int acc_stride;                   // TMEM columns between the two accumulator buffers (multiple of 32)
@@ -237,8 +237,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const TcArgs g) {
                     v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (gm < g.m && kcol < g.k) v[i] = ldg4(g.a + gm * g.lda + kcol);   // K % 4 == 0 guaranteed by the dispatcher
                 }
-                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (pro && kcol < g.k) { sc = ldg4(g.a_scale + kcol); sh = ldg4(g.a_shift + kcol); }
+                float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pro && kcol < g.k) { mu = ldg4(g.a_mean + kcol); sc = ldg4(g.a_scale + kcol); sh = ldg4(g.a_shift + kcol); }
                 mbar_wait(&empty[s], ph ^ 1);
                 uint8_t* a_hi = smem + (size_t)s * stage_bytes;
                 uint8_t* a_lo = a_hi + kTcATile;
@@ -247,8 +247,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const TcArgs g) {
                     const int r = r0 + 32 * i;
                     float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
                     if (pro) {
-                        x[0] = lrelu(fmaf(x[0], sc.x, sh.x), g.slope); x[1] = lrelu(fmaf(x[1], sc.y, sh.y), g.slope);
-                        x[2] = lrelu(fmaf(x[2], sc.z, sh.z), g.slope); x[3] = lrelu(fmaf(x[3], sc.w, sh.w), g.slope);
+                        x[0] = bn_lrelu(x[0], mu.x, sc.x, sh.x, g.slope); x[1] = bn_lrelu(x[1], mu.y, sc.y, sh.y, g.slope);
+                        x[2] = bn_lrelu(x[2], mu.z, sc.z, sh.z, g.slope); x[3] = bn_lrelu(x[3], mu.w, sc.w, sh.w, g.slope);
                         if (m0 + r >= g.m || kcol >= g.k) { x[0] = x[1] = x[2] = x[3] = 0.f; }
                     }
                     float h[4], l[4];
@@ -365,19 +365,212 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const TcArgs g) {
     }
 }
 
-// per-128-row-tile column statistics of C (BatchNorm partials) when the tensor-core path produced C
+// per-128-row-tile column moments of C (BatchNorm partials: count, mean, M2) when the tensor-core path produced C
 __global__ void __launch_bounds__(256) k_tile_col_stats(const float* __restrict__ c, int64_t ldc, int64_t m, int n, float* __restrict__ partials) {
     const int64_t m0 = (int64_t)blockIdx.x * kTcBM;
     const int rows = (int)min64(kTcBM, m - m0);
     for (int col = threadIdx.x; col < n; col += blockDim.x) {
+        const float p = c[m0 * ldc + col];            // pivot: first row of the tile
         float s1 = 0.f, s2 = 0.f;
         for (int r = 0; r < rows; ++r) {
-            const float v = c[(m0 + r) * ldc + col];
-            s1 += v;
-            s2 = fmaf(v, v, s2);
+            const float d = c[(m0 + r) * ldc + col] - p;
+            s1 += d;
+            s2 = fmaf(d, d, s2);
         }
-        partials[((int64_t)blockIdx.x * 2 + 0) * n + col] = s1;
-        partials[((int64_t)blockIdx.x * 2 + 1) * n + col] = s2;
+        const Moments mo = from_shifted((float)rows, p, s1, s2);
+        partials[((int64_t)blockIdx.x * 3 + 0) * n + col] = mo.n;
+        partials[((int64_t)blockIdx.x * 3 + 1) * n + col] = mo.mean;
+        partials[((int64_t)blockIdx.x * 3 + 2) * n + col] = mo.m2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight gradient on the tensor pipe:  D[n,k] = sum_m G[m,n] * A[m,k]
+//   UMMA M = 128 rows of n, UMMA N = k-tile (<= 256), UMMA K = 8 vertices per instruction.
+//   Both operands are MN-major.  For 32-bit types the tensor core accepts MN-major operands only in
+//   the SWIZZLE_128B_BASE32B layout (layout type 1; every other layout type reads zeros -- measured
+//   with tools/mma_probe.cu, whose output also fixed the address map below):
+//     atom = 4 vertices (K) x 128 B (32 consecutive n or k indices), rows 128 B apart, the 32-byte
+//     chunk index XOR-ed with the row:  byte(idx, m) = (idx/32)*LBO + (m/4)*SBO + (m%4)*128
+//                                                      + ((((idx%32)/8) ^ (m%4)) * 32) + (idx%8)*4
+//   so a row-major global row (n or k contiguous) is staged with plain 16-byte stores, no
+//   transposition anywhere, and a quarter-warp always fills one whole 128-byte row (conflict-free).
+//   One output tile + one m-slice per CTA; slices reduced afterwards in fixed order.
+// ------------------------------------------------------------------------------------------
+constexpr int kTnBM = 128;                       // rows of D (n) per CTA
+constexpr int kTnBK = 32;                        // vertices per pipeline stage
+constexpr int kTnSbo = 512;                      // K-direction atom stride (4 vertices x 128 B)
+constexpr int kTnLbo = (kTnBK / 4) * kTnSbo;     // MN-direction atom stride = 4096
+constexpr int kTnGTile = (kTnBM / 32) * kTnLbo;  // 16384 bytes per hi (or lo)
+constexpr uint32_t kLayoutSw128Base32 = 1;
+constexpr int kTnProducerWarps = 8;
+constexpr int kTnThreads = (kTnProducerWarps + 1) * 32;
+
+__host__ __device__ constexpr int tn_a_tile_bytes(int bk) { return ((bk + 31) / 32) * kTnLbo; }
+__host__ __device__ constexpr int tn_stage_bytes(int bk) { return 2 * kTnGTile + 2 * tn_a_tile_bytes(bk); }
+
+struct TnArgs {
+    const float* g; int64_t ldg;
+    const float* a; int64_t lda;
+    float* partial;                   // [splits][n][k]
+    int64_t m; int n; int k;
+    int bk;                           // UMMA N: columns of D per CTA (multiple of 16, <= 256)
+    int k_tiles; int stages;
+    int64_t m_per_split;              // multiple of kTnBK
+    uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(kTnThreads, 1) k_gemm_tn_tc(const TnArgs t) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stage_bytes = tn_stage_bytes(t.bk);
+    const int a_tile_bytes = tn_a_tile_bytes(t.bk);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)t.stages * stage_bytes);
+    uint64_t* empty = full + kTcMaxStages;
+    uint64_t* tfull = empty + kTcMaxStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < t.stages; ++s) {
+            mbar_init(&full[s], kTnProducerWarps * 32);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == kTnProducerWarps) tmem_alloc(tmem_slot, t.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n0 = (blockIdx.x / t.k_tiles) * kTnBM;
+    const int k0 = (blockIdx.x % t.k_tiles) * t.bk;
+    const int64_t ms = (int64_t)blockIdx.y * t.m_per_split;
+    const int64_t me = min64(t.m, ms + t.m_per_split);
+    const int chunks = me > ms ? (int)((me - ms + kTnBK - 1) / kTnBK) : 0;
+
+    if (warp < kTnProducerWarps) {
+        // each warp owns 4 of the 32 vertex rows of a stage; a lane owns 16-byte pieces lane, lane+32, ...
+        const int a_pieces = t.bk / 4;             // <= 64
+        for (int it = 0; it < chunks; ++it) {
+            const int s = it % t.stages;
+            const uint32_t ph = (it / t.stages) & 1;
+            float4 gv[4], av[4][2];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int64_t gm = ms + (int64_t)it * kTnBK + warp * 4 + r;
+                const bool rok = gm < me;
+                const int gn = n0 + lane * 4;
+                gv[r] = (rok && gn < t.n) ? ldg4(t.g + gm * t.ldg + gn) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int piece = lane + 32 * h;
+                    const int gk = k0 + piece * 4;
+                    av[r][h] = (rok && piece < a_pieces && gk < t.k) ? ldg4(t.a + gm * t.lda + gk) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* g_hi = smem + (size_t)s * stage_bytes;
+            uint8_t* g_lo = g_hi + kTnGTile;
+            uint8_t* a_hi = g_lo + kTnGTile;
+            uint8_t* a_lo = a_hi + a_tile_bytes;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int ml = warp * 4 + r;                                   // vertex row within the stage
+                const uint32_t row_off = (uint32_t)(ml >> 2) * kTnSbo + (uint32_t)(ml & 3) * 128;
+                const uint32_t rx = (uint32_t)(ml & 3);
+                {
+                    float x[4] = {gv[r].x, gv[r].y, gv[r].z, gv[r].w}, h4[4], l4[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) split_tf32(x[e], h4[e], l4[e]);
+                    const uint32_t off = (uint32_t)(lane >> 3) * kTnLbo + row_off + ((((uint32_t)(lane & 7) >> 1) ^ rx) << 5) + (uint32_t)(lane & 1) * 16;
+                    *reinterpret_cast<float4*>(g_hi + off) = make_float4(h4[0], h4[1], h4[2], h4[3]);
+                    *reinterpret_cast<float4*>(g_lo + off) = make_float4(l4[0], l4[1], l4[2], l4[3]);
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int piece = lane + 32 * h;
+                    if (piece < a_pieces) {
+                        float x[4] = {av[r][h].x, av[r][h].y, av[r][h].z, av[r][h].w}, h4[4], l4[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) split_tf32(x[e], h4[e], l4[e]);
+                        const uint32_t off = (uint32_t)(piece >> 3) * kTnLbo + row_off + ((((uint32_t)(piece & 7) >> 1) ^ rx) << 5) + (uint32_t)(piece & 1) * 16;
+                        *reinterpret_cast<float4*>(a_hi + off) = make_float4(h4[0], h4[1], h4[2], h4[3]);
+                        *reinterpret_cast<float4*>(a_lo + off) = make_float4(l4[0], l4[1], l4[2], l4[3]);
+                    }
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(&full[s]);
+        }
+    } else {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(kTnBM, t.bk, 1, 1);      // both operands MN-major
+            for (int it = 0; it < chunks; ++it) {
+                const int s = it % t.stages;
+                const uint32_t ph = (it / t.stages) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t g_hi = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t g_lo = g_hi + kTnGTile;
+                const uint32_t a_hi = g_lo + kTnGTile;
+                const uint32_t a_lo = a_hi + a_tile_bytes;
+#pragma unroll
+                for (int j = 0; j < kTnBK / 8; ++j) {
+                    const uint64_t dgh = make_desc(g_hi + j * 2 * kTnSbo, kTnLbo, kTnSbo, kLayoutSw128Base32);
+                    const uint64_t dgl = make_desc(g_lo + j * 2 * kTnSbo, kTnLbo, kTnSbo, kLayoutSw128Base32);
+                    const uint64_t dah = make_desc(a_hi + j * 2 * kTnSbo, kTnLbo, kTnSbo, kLayoutSw128Base32);
+                    const uint64_t dal = make_desc(a_lo + j * 2 * kTnSbo, kTnLbo, kTnSbo, kLayoutSw128Base32);
+                    umma_tf32(tmem_base, dgl, dah, idesc, (it | j) ? 1u : 0u);
+                    umma_tf32(tmem_base, dgh, dal, idesc, 1u);
+                    umma_tf32(tmem_base, dgh, dah, idesc, 1u);
+                }
+                umma_commit(&empty[s]);
+            }
+            umma_commit(tfull);
+        }
+    }
+    // epilogue: warps 0..3 (TMEM lane quarter = warp id) write the partial tile
+    if (warp < 4) {
+        float* out = t.partial + (int64_t)blockIdx.y * t.n * t.k;
+        const int gn = n0 + warp * 32 + lane;
+        if (chunks > 0) {
+            mbar_wait(tfull, 0);
+            tc_fence_after();
+        }
+        const int kcols = min(t.bk, t.k - k0);
+        for (int c0 = 0; c0 < kcols; c0 += 32) {
+            float v[32];
+            if (chunks > 0) {
+                tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] = 0.f;
+            }
+            if (gn < t.n) {
+#pragma unroll
+                for (int e = 0; e < 32; ++e)
+                    if (c0 + e < kcols) out[(int64_t)gn * t.k + k0 + c0 + e] = v[e];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kTnProducerWarps) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, t.tmem_cols);
+    }
+}
+
+__global__ void k_reduce_splits_tc(const float* __restrict__ partial, int splits, int n, int k, float* __restrict__ d, int64_t ldd,
+                                   int accumulate) {
+    const int64_t total = (int64_t)n * k;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int sidx = 0; sidx < splits; ++sidx) s += partial[(int64_t)sidx * total + i];
+        float* dp = d + (i / k) * ldd + (i % k);
+        *dp = accumulate ? *dp + s : s;
     }
 }
 
@@ -443,7 +636,7 @@ int gemm_tc_launch(const GemmArgs& g, void* ws, size_t ws_bytes, cudaStream_t st
     TcArgs t{};
     t.a = g.a; t.lda = g.lda; t.wp = wp; t.c = g.c; t.ldc = g.ldc; t.m = g.m; t.n = g.n; t.k = g.k;
     t.bn = p.bn; t.n_tiles = p.n_tiles; t.k_chunks = p.k_chunks; t.stages = p.stages;
-    t.a_scale = g.a_scale; t.a_shift = g.a_shift; t.slope = g.slope; t.bias = g.bias; t.accumulate = g.accumulate;
+    t.a_mean = g.a_mean; t.a_scale = g.a_scale; t.a_shift = g.a_shift; t.slope = g.slope; t.bias = g.bias; t.accumulate = g.accumulate;
     t.tmem_cols = p.tmem_cols; t.acc_stride = p.acc_stride;
     int64_t tiles = ceil_div(g.m, kTcBM) * p.n_tiles;
     int grid = (int)min64(tiles, num_sms());
@@ -453,6 +646,73 @@ int gemm_tc_launch(const GemmArgs& g, void* ws, size_t ws_bytes, cudaStream_t st
         k_tile_col_stats<<<(unsigned)ceil_div(g.m, kTcBM), 256, 0, stream>>>(g.c, g.ldc, g.m, g.n, g.stat_partials);
         SGB_CHECK_LAUNCH("k_tile_col_stats");
     }
+    return SGB_OK;
+}
+
+// ---- weight gradient ----
+struct TnPlan {
+    int bk, k_tiles, n_tiles, stages, splits;
+    int64_t m_per_split;
+    size_t smem_bytes, ws_bytes;
+    uint32_t tmem_cols;
+};
+
+static TnPlan tn_plan(int64_t m, int n, int k) {
+    TnPlan p;
+    int kpad = (k + 15) / 16 * 16;
+    p.bk = kpad <= 256 ? kpad : 256;
+    p.k_tiles = (k + p.bk - 1) / p.bk;
+    p.n_tiles = (n + kTnBM - 1) / kTnBM;
+    int sb = tn_stage_bytes(p.bk);
+    int st = (kSmemBudget - 256) / sb;
+    p.stages = st > kTcMaxStages ? kTcMaxStages : st;
+    p.smem_bytes = (size_t)p.stages * sb + 256;
+    int tiles = p.k_tiles * p.n_tiles;
+    int64_t want = num_sms() / tiles;
+    if (want < 1) want = 1;
+    int64_t maxs = ceil_div(m > 0 ? m : 1, 1024);
+    p.splits = (int)(want < maxs ? want : maxs);
+    p.m_per_split = ceil_div(ceil_div(m, p.splits), kTnBK) * kTnBK;
+    p.ws_bytes = (size_t)p.splits * n * k * sizeof(float);
+    uint32_t cols = 32;
+    while (cols < (uint32_t)((p.bk + 31) / 32 * 32)) cols <<= 1;
+    p.tmem_cols = cols;
+    return p;
+}
+
+bool gemm_tn_tc_supported(int64_t m, int n, int k, int64_t ldg, int64_t lda, const void* g, const void* a) {
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return n % 4 == 0 && k % 4 == 0 && ldg % 4 == 0 && lda % 4 == 0 && al16(g) && al16(a) && m >= 1;
+}
+
+size_t gemm_tn_tc_workspace(int64_t m, int n, int k) { return tn_plan(m, n, k).ws_bytes; }
+
+int gemm_tn_tc_launch(const float* g, int64_t ldg, const float* a, int64_t lda, float* d, int64_t ldd, int64_t m, int n, int k,
+                      int accumulate, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    TnPlan p = tn_plan(m, n, k);
+    if (!ws || ws_bytes < p.ws_bytes) {
+        set_error("sgb_gemm_tn: tensor-core engine needs %zu bytes of workspace, got %zu", p.ws_bytes, ws_bytes);
+        return SGB_ENOSPC;
+    }
+    if (p.stages < 2) {
+        set_error("sgb_gemm_tn: tile does not fit shared memory");
+        return SGB_ENOTSUP;
+    }
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        SGB_CUDA(cudaFuncSetAttribute(k_gemm_tn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        attr_set = true;
+    }
+    TnArgs t{};
+    t.g = g; t.ldg = ldg; t.a = a; t.lda = lda; t.partial = (float*)ws; t.m = m; t.n = n; t.k = k;
+    t.bk = p.bk; t.k_tiles = p.k_tiles; t.stages = p.stages; t.m_per_split = p.m_per_split; t.tmem_cols = p.tmem_cols;
+    dim3 grid((unsigned)(p.n_tiles * p.k_tiles), (unsigned)p.splits);
+    k_gemm_tn_tc<<<grid, kTnThreads, p.smem_bytes, stream>>>(t);
+    SGB_CHECK_LAUNCH("k_gemm_tn_tc");
+    int64_t total = (int64_t)n * k;
+    int rgrid = (int)min64(ceil_div(total, 256), (int64_t)num_sms() * 8);
+    k_reduce_splits_tc<<<rgrid, 256, 0, stream>>>((const float*)ws, p.splits, n, k, d, ldd, accumulate);
+    SGB_CHECK_LAUNCH("k_reduce_splits");
     return SGB_OK;
 }
 

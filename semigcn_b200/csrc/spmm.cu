@@ -51,6 +51,7 @@ struct SpmmArgs {
     int64_t ldx;
     int64_t n;
     int c;
+    const float* in_mean;
     const float* in_scale;
     const float* in_shift;
     float slope;
@@ -76,27 +77,30 @@ __global__ void __launch_bounds__(kSpmmThreads) k_spmm(const SpmmArgs a) {
     const bool pro = a.in_scale != nullptr;
     const bool stats = a.stat_partials != nullptr;
     __shared__ float red[2][kSpmmThreads * VEC * ITERS];
+    __shared__ float redn[kSpmmThreads];
 
     for (int c0 = 0; c0 < a.c; c0 += CH) {
         int ch[ITERS];
         bool act[ITERS];
-        Vec<VEC> sc[ITERS], sh[ITERS], bs[ITERS];
+        Vec<VEC> mu[ITERS], sc[ITERS], sh[ITERS], bs[ITERS];
 #pragma unroll
         for (int t = 0; t < ITERS; ++t) {
             ch[t] = c0 + (t * LPV + l) * VEC;
             act[t] = ch[t] < a.c;
 #pragma unroll
-            for (int q = 0; q < VEC; ++q) { sc[t].v[q] = 1.f; sh[t].v[q] = 0.f; bs[t].v[q] = 0.f; }
+            for (int q = 0; q < VEC; ++q) { mu[t].v[q] = 0.f; sc[t].v[q] = 1.f; sh[t].v[q] = 0.f; bs[t].v[q] = 0.f; }
             if (act[t]) {
-                if (pro) { sc[t].load(a.in_scale + ch[t]); sh[t].load(a.in_shift + ch[t]); }
+                if (pro) { mu[t].load(a.in_mean + ch[t]); sc[t].load(a.in_scale + ch[t]); sh[t].load(a.in_shift + ch[t]); }
                 if (a.bias) bs[t].load(a.bias + ch[t]);
             }
         }
-        float s1[ITERS][VEC], s2[ITERS][VEC];
+        // statistics: pivot-shifted sums per thread (pivot = first value seen), see common.cuh
+        float s1[ITERS][VEC], s2[ITERS][VEC], pv[ITERS][VEC];
+        float nseen = 0.f;
 #pragma unroll
         for (int t = 0; t < ITERS; ++t)
 #pragma unroll
-            for (int q = 0; q < VEC; ++q) { s1[t][q] = 0.f; s2[t][q] = 0.f; }
+            for (int q = 0; q < VEC; ++q) { s1[t][q] = 0.f; s2[t][q] = 0.f; pv[t][q] = 0.f; }
 
         // all 32 lanes of a warp iterate together (shuffles below are full-warp)
         const int64_t v0 = (int64_t)blockIdx.x * GROUPS + grp;
@@ -153,7 +157,7 @@ __global__ void __launch_bounds__(kSpmmThreads) k_spmm(const SpmmArgs a) {
 #pragma unroll
                                     for (int q = 0; q < VEC; ++q) {
                                         float xx = xv[b][t].v[q];
-                                        if (pro) xx = lrelu(fmaf(xx, sc[t].v[q], sh[t].v[q]), a.slope);
+                                        if (pro) xx = bn_lrelu(xx, mu[t].v[q], sc[t].v[q], sh[t].v[q], a.slope);
                                         acc[t].v[q] = __fadd_rn(acc[t].v[q], __fmul_rn(w[b], xx));
                                     }
                                 }
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__(kSpmmThreads) k_spmm(const SpmmArgs a) {
 #pragma unroll
                         for (int q = 0; q < VEC; ++q) {
                             float xx = xi.v[q];
-                            if (pro) xx = lrelu(fmaf(xx, sc[t].v[q], sh[t].v[q]), a.slope);
+                            if (pro) xx = bn_lrelu(xx, mu[t].v[q], sc[t].v[q], sh[t].v[q], a.slope);
                             if (a.mode == SGB_MODE_GCN) {
                                 out.v[q] = __fadd_rn(out.v[q], __fmul_rn(wii, xx));
                             } else {   // CHEB: the (+1, -1) loop pair of ChebConv.__norm__, not cancelled
@@ -200,32 +204,35 @@ __global__ void __launch_bounds__(kSpmmThreads) k_spmm(const SpmmArgs a) {
                     if (stats) {
 #pragma unroll
                         for (int q = 0; q < VEC; ++q) {
-                            s1[t][q] += out.v[q];
-                            s2[t][q] = fmaf(out.v[q], out.v[q], s2[t][q]);
+                            if (nseen == 0.f) pv[t][q] = out.v[q];
+                            const float dv = out.v[q] - pv[t][q];
+                            s1[t][q] += dv;
+                            s2[t][q] = fmaf(dv, dv, s2[t][q]);
                         }
                     }
                 }
+                nseen += 1.f;
             }
         }
-        if (stats) {   // fixed-order block reduction -> partials[blockIdx.x][2][c]
+        if (stats) {   // fixed-order block merge (Chan) -> partials[blockIdx.x][3][c] = (count, mean, M2)
 #pragma unroll
             for (int t = 0; t < ITERS; ++t)
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) {
                     const int cl = (t * LPV + l) * VEC + q;     // channel within the pass
-                    red[0][grp * CH + cl] = s1[t][q];
-                    red[1][grp * CH + cl] = s2[t][q];
+                    const Moments mo = from_shifted(nseen, pv[t][q], s1[t][q], s2[t][q]);
+                    red[0][grp * CH + cl] = mo.mean;
+                    red[1][grp * CH + cl] = mo.m2;
                 }
+            if (l == 0) redn[grp] = nseen;
             __syncthreads();
             for (int cl = threadIdx.x; cl < CH; cl += kSpmmThreads) {
                 if (c0 + cl < a.c) {
-                    float t1 = 0.f, t2 = 0.f;
-                    for (int g = 0; g < GROUPS; ++g) {
-                        t1 += red[0][g * CH + cl];
-                        t2 += red[1][g * CH + cl];
-                    }
-                    a.stat_partials[((int64_t)blockIdx.x * 2 + 0) * a.c + c0 + cl] = t1;
-                    a.stat_partials[((int64_t)blockIdx.x * 2 + 1) * a.c + c0 + cl] = t2;
+                    Moments acc{0.f, 0.f, 0.f};
+                    for (int g = 0; g < GROUPS; ++g) acc = merge(acc, Moments{redn[g], red[0][g * CH + cl], red[1][g * CH + cl]});
+                    a.stat_partials[((int64_t)blockIdx.x * 3 + 0) * a.c + c0 + cl] = acc.n;
+                    a.stat_partials[((int64_t)blockIdx.x * 3 + 1) * a.c + c0 + cl] = acc.mean;
+                    a.stat_partials[((int64_t)blockIdx.x * 3 + 2) * a.c + c0 + cl] = acc.m2;
                 }
             }
             __syncthreads();
@@ -274,7 +281,7 @@ extern "C" int sgb_spmm_stat_rows(int64_t n, int c) {
 
 extern "C" int sgb_spmm(const int32_t* rowptr, const int32_t* colidx, const float* dis, int mode,
                         const float* x, int64_t ldx, int64_t n, int c,
-                        const float* in_scale, const float* in_shift, float slope,
+                        const float* in_mean, const float* in_scale, const float* in_shift, float slope,
                         float alpha, const float* addend, int64_t ld_addend, float beta,
                         const float* bias, float* y, int64_t ldy, float* stat_partials, void* stream_) {
     using namespace sgb;
@@ -283,21 +290,22 @@ extern "C" int sgb_spmm(const int32_t* rowptr, const int32_t* colidx, const floa
     SGB_CHECK_ARG(mode == SGB_MODE_GCN || mode == SGB_MODE_CHEB || mode == SGB_MODE_ADJ, "sgb_spmm: bad mode %d", mode);
     SGB_CHECK_ARG(rowptr && dis && x && y, "sgb_spmm: null pointer");
     SGB_CHECK_ARG(ldx >= c && ldy >= c && (!addend || ld_addend >= c), "sgb_spmm: leading dimension < c");
-    SGB_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr), "sgb_spmm: in_scale / in_shift must come together");
+    SGB_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr) && (in_scale == nullptr) == (in_mean == nullptr),
+                  "sgb_spmm: in_mean / in_scale / in_shift must come together");
     SGB_CHECK_ARG(x != y, "sgb_spmm: in-place aggregation is not supported");
     if (n == 0) return SGB_OK;
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     bool aligned = al16(x) && al16(y) && ldx % 4 == 0 && ldy % 4 == 0 && (!addend || (al16(addend) && ld_addend % 4 == 0)) &&
-                   (!bias || al16(bias)) && (!in_scale || (al16(in_scale) && al16(in_shift)));
+                   (!bias || al16(bias)) && (!in_scale || (al16(in_scale) && al16(in_shift) && al16(in_mean)));
     SpmmCfg k = pick_cfg(c, aligned);
     int grid = spmm_grid(n, k);
     if (stat_partials) {
         // rows the caller sized for; unused rows must read as zero
         int rows = sgb_spmm_stat_rows(n, c);
         if (rows > grid)
-            SGB_CUDA(cudaMemsetAsync(stat_partials + (size_t)grid * 2 * c, 0, (size_t)(rows - grid) * 2 * c * sizeof(float), stream));
+            SGB_CUDA(cudaMemsetAsync(stat_partials + (size_t)grid * 3 * c, 0, (size_t)(rows - grid) * 3 * c * sizeof(float), stream));
     }
-    SpmmArgs a{rowptr, colidx, dis, mode, x, ldx, n, c, in_scale, in_shift, slope, alpha, addend, ld_addend, beta, bias, y, ldy, stat_partials};
+    SpmmArgs a{rowptr, colidx, dis, mode, x, ldx, n, c, in_mean, in_scale, in_shift, slope, alpha, addend, ld_addend, beta, bias, y, ldy, stat_partials};
 #define SGB_SPMM_CASE(L, V, I)                                         \
     if (k.lpv == L && k.vec == V && k.iters == I) {                    \
         k_spmm<L, V, I><<<grid, kSpmmThreads, 0, stream>>>(a);         \

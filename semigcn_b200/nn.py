@@ -195,11 +195,8 @@ class ConvBlockFn(torch.autograd.Function):
             rv = bn.running_var if bn.track_running_stats else None
             mean, invstd, scale, shift = ops.bn_finalize(partials, y.shape[0], gamma, beta, bn.eps, momentum, rm, rv)
         else:
-            invstd = torch.rsqrt(bn.running_var + bn.eps)
-            mean = bn.running_mean
-            scale = (invstd * gamma if gamma is not None else invstd).contiguous()
-            shift = ((beta if beta is not None else 0.0) - mean * scale).contiguous()
-        z = ops.bn_act_apply(y, scale, shift, cfg.slope)
+            mean, invstd, scale, shift = ops.eval_affine(bn.running_mean, bn.running_var, gamma, beta, bn.eps)
+        z = ops.bn_act_apply(y, mean, scale, shift, cfg.slope)
         ctx.bn_mode = 2 if training else 1
         ctx.has_affine = gamma is not None
         ctx.save_for_backward(*weights, *saved_ops, y, scale, shift, mean, invstd)

@@ -14,7 +14,7 @@ from . import _lib as L
 from . import profile as _prof
 from ._lib import MODE_ADJ, MODE_CHEB, MODE_GCN, SgbError, check, ptr, require_cuda, stream_ptr
 
-Affine = Optional[Tuple[Tensor, Tensor, float]]   # (scale[c], shift[c], slope): fused BN + LeakyReLU on load
+Affine = Optional[Tuple[Tensor, Tensor, Tensor, float]]   # (mean[c], scale[c], shift[c], slope): fused centred BN + LeakyReLU on load
 
 
 def _f32c(t: Tensor, name: str) -> Tensor:
@@ -116,15 +116,15 @@ def spmm(g: MeshGraph, x: Tensor, transpose: bool = False, in_affine: Affine = N
     partials = None
     if want_stats:
         rows = lib.sgb_spmm_stat_rows(n, c)
-        partials = torch.empty((rows, 2, c), dtype=torch.float32, device=x.device)
+        partials = torch.empty((rows, 3, c), dtype=torch.float32, device=x.device)
     rowptr, colidx = g.csr(transpose)
-    sc, sh, slope = (in_affine if in_affine is not None else (None, None, 0.0))
+    mu, sc, sh, slope = (in_affine if in_affine is not None else (None, None, None, 0.0))
     nnz_eff = int(g.nnz) + (n if g.mode == MODE_GCN else 0)
     sp = _prof.span(f"spmm_c{c}", 4.0 * (2 * n * c + nnz_eff + 2 * n + 1 + (n * c if addend is not None else 0)),
                     2.0 * nnz_eff * c) if _prof.ACTIVE is not None else None
     with torch.cuda.device(x.device):
         check(lib.sgb_spmm(ptr(rowptr), ptr(colidx), ptr(g.dis), g.mode, ptr(x), x.stride(0), n, c,
-                           ptr(sc), ptr(sh), float(slope), float(alpha), ptr(addend),
+                           ptr(mu), ptr(sc), ptr(sh), float(slope), float(alpha), ptr(addend),
                            addend.stride(0) if addend is not None else 0, float(beta), ptr(bias),
                            ptr(y), y.stride(0), ptr(partials), stream_ptr(x.device)), "sgb_spmm")
     if sp is not None:
@@ -146,15 +146,15 @@ def gemm(a: Tensor, b: Tensor, transb: bool = True, a_affine: Affine = None, bia
     c = out if out is not None else torch.empty((m, n), dtype=torch.float32, device=a.device)
     partials = None
     if want_stats:
-        partials = torch.empty((lib.sgb_gemm_stat_rows(m), 2, n), dtype=torch.float32, device=a.device)
-    sc, sh, slope = (a_affine if a_affine is not None else (None, None, 0.0))
+        partials = torch.empty((lib.sgb_gemm_stat_rows(m), 3, n), dtype=torch.float32, device=a.device)
+    mu, sc, sh, slope = (a_affine if a_affine is not None else (None, None, None, 0.0))
     sp = _prof.span(f"gemm_n{n}_k{k}", 4.0 * (m * (k + n) + k * n + (m * n if accumulate else 0)), 2.0 * m * n * k) \
         if _prof.ACTIVE is not None else None
     wsb = lib.sgb_gemm_workspace_bytes(m, n, k, engine)
     ws = _ws(wsb, a.device) if wsb else None
     with torch.cuda.device(a.device):
         check(lib.sgb_gemm(1 if transb else 0, ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(c), c.stride(0), m, n, k,
-                           ptr(sc), ptr(sh), float(slope), ptr(bias), 1 if accumulate else 0, ptr(partials),
+                           ptr(mu), ptr(sc), ptr(sh), float(slope), ptr(bias), 1 if accumulate else 0, ptr(partials),
                            ptr(ws), wsb, engine, stream_ptr(a.device)), "sgb_gemm")
     if sp is not None:
         sp.close()
@@ -206,7 +206,7 @@ def col_stats(y: Tensor) -> Tensor:
     lib = L.load()
     y = _f32c(y, "y")
     m, c = y.shape
-    partials = torch.empty((lib.sgb_col_stat_rows(m, c), 2, c), dtype=torch.float32, device=y.device)
+    partials = torch.empty((lib.sgb_col_stat_rows(m, c), 3, c), dtype=torch.float32, device=y.device)
     with torch.cuda.device(y.device):
         check(lib.sgb_col_stats(ptr(y), y.stride(0), m, c, ptr(partials), stream_ptr(y.device)), "sgb_col_stats")
     L.count(1)
@@ -227,14 +227,14 @@ def bn_finalize(partials: Tensor, count: int, gamma: Optional[Tensor], beta: Opt
     return st[0], st[1], st[2], st[3]
 
 
-def bn_act_apply(y: Tensor, scale: Tensor, shift: Tensor, slope: float, out: Optional[Tensor] = None) -> Tensor:
+def bn_act_apply(y: Tensor, mean: Tensor, scale: Tensor, shift: Tensor, slope: float, out: Optional[Tensor] = None) -> Tensor:
     lib = L.load()
     y = _f32c(y, "y")
     m, c = y.shape
     z = out if out is not None else torch.empty_like(y)
     sp = _prof.span(f"bn_act_apply_c{c}", 8.0 * m * c) if _prof.ACTIVE is not None else None
     with torch.cuda.device(y.device):
-        check(lib.sgb_bn_act_apply(ptr(y), y.stride(0), m, c, ptr(scale), ptr(shift), float(slope), ptr(z), z.stride(0),
+        check(lib.sgb_bn_act_apply(ptr(y), y.stride(0), m, c, ptr(mean), ptr(scale), ptr(shift), float(slope), ptr(z), z.stride(0),
                                    stream_ptr(y.device)), "sgb_bn_act_apply")
     if sp is not None:
         sp.close()
@@ -326,6 +326,14 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None) -> Tensor:
     return LinearFn.apply(x, weight, bias)
 
 
+def eval_affine(running_mean: Tensor, running_var: Tensor, gamma: Optional[Tensor], beta: Optional[Tensor], eps: float):
+    """Eval-mode BatchNorm as the centred affine (mean, invstd, scale = gamma*invstd, shift = beta)."""
+    invstd = torch.rsqrt(running_var + eps)
+    scale = (invstd * gamma if gamma is not None else invstd).contiguous()
+    shift = (beta if beta is not None else torch.zeros_like(invstd)).contiguous()
+    return running_mean.contiguous(), invstd.contiguous(), scale, shift
+
+
 class BnActFn(torch.autograd.Function):
     """Z = lrelu(BatchNorm1d(Y)); training: batch statistics (+ running-stat update), eval: running stats."""
 
@@ -338,12 +346,8 @@ class BnActFn(torch.autograd.Function):
                 partials = col_stats(y)
             mean, invstd, scale, shift = bn_finalize(partials, m, gamma, beta, eps, momentum, running_mean, running_var)
         else:
-            invstd = torch.rsqrt(running_var + eps)
-            mean = running_mean
-            scale = invstd * gamma if gamma is not None else invstd
-            shift = (beta if beta is not None else 0.0) - mean * scale
-            scale, shift = scale.contiguous(), shift.contiguous()
-        z = bn_act_apply(y, scale, shift, slope)
+            mean, invstd, scale, shift = eval_affine(running_mean, running_var, gamma, beta, eps)
+        z = bn_act_apply(y, mean, scale, shift, slope)
         ctx.save_for_backward(y, scale, shift, mean, invstd)
         ctx.slope, ctx.training, ctx.has_affine = slope, training, gamma is not None
         return z
