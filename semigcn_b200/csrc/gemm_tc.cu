@@ -404,7 +404,12 @@ constexpr int kTnLbo = (kTnBK / 4) * kTnSbo;     // MN-direction atom stride = 4
 constexpr int kTnGTile = (kTnBM / 32) * kTnLbo;  // 16384 bytes per hi (or lo)
 constexpr uint32_t kLayoutSw128Base32 = 1;
 constexpr int kTnProducerWarps = 8;
-constexpr int kTnThreads = (kTnProducerWarps + 1) * 32;
+constexpr int kTnDrainWarps = 4;
+constexpr int kTnThreads = (kTnProducerWarps + 1 + kTnDrainWarps) * 32;
+// Tensor-core accumulation truncates (measured: error grows ~6e-9 per accumulated vertex row), so one
+// TMEM accumulator never sums more than kTnSegChunks * kTnBK = 512 vertices: segments alternate between
+// two accumulators and are drained into the CTA's partial tile with round-to-nearest fp32 adds.
+constexpr int kTnSegChunks = 16;
 
 __host__ __device__ constexpr int tn_a_tile_bytes(int bk) { return ((bk + 31) / 32) * kTnLbo; }
 __host__ __device__ constexpr int tn_stage_bytes(int bk) { return 2 * kTnGTile + 2 * tn_a_tile_bytes(bk); }
@@ -418,6 +423,7 @@ struct TnArgs {
     int k_tiles; int stages;
     int64_t m_per_split;              // multiple of kTnBK
     uint32_t tmem_cols;
+    int acc_stride;                   // TMEM columns between the two accumulators (multiple of 32)
 };
 
 __global__ void __launch_bounds__(kTnThreads, 1) k_gemm_tn_tc(const TnArgs t) {
@@ -427,15 +433,19 @@ __global__ void __launch_bounds__(kTnThreads, 1) k_gemm_tn_tc(const TnArgs t) {
     const int a_tile_bytes = tn_a_tile_bytes(t.bk);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)t.stages * stage_bytes);
     uint64_t* empty = full + kTcMaxStages;
-    uint64_t* tfull = empty + kTcMaxStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+    uint64_t* tfull = empty + kTcMaxStages;      // [2]
+    uint64_t* tempty = tfull + 2;                // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < t.stages; ++s) {
             mbar_init(&full[s], kTnProducerWarps * 32);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(tfull, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tfull[b], 1);
+            mbar_init(&tempty[b], kTnDrainWarps);
+        }
         fence_barrier_init();
     }
     if (warp == kTnProducerWarps) tmem_alloc(tmem_slot, t.tmem_cols);
@@ -449,9 +459,10 @@ __global__ void __launch_bounds__(kTnThreads, 1) k_gemm_tn_tc(const TnArgs t) {
     const int64_t ms = (int64_t)blockIdx.y * t.m_per_split;
     const int64_t me = min64(t.m, ms + t.m_per_split);
     const int chunks = me > ms ? (int)((me - ms + kTnBK - 1) / kTnBK) : 0;
+    const int segments = (chunks + kTnSegChunks - 1) / kTnSegChunks;
 
     if (warp < kTnProducerWarps) {
-        // each warp owns 4 of the 32 vertex rows of a stage; a lane owns 16-byte pieces lane, lane+32, ...
+        // each warp owns 4 of the 32 vertex rows of a stage; a lane owns 16-byte pieces lane, lane+32
         const int a_pieces = t.bk / 4;             // <= 64
         for (int it = 0; it < chunks; ++it) {
             const int s = it % t.stages;
@@ -504,12 +515,19 @@ __global__ void __launch_bounds__(kTnThreads, 1) k_gemm_tn_tc(const TnArgs t) {
             fence_proxy_async();
             mbar_arrive(&full[s]);
         }
-    } else {
+    } else if (warp == kTnProducerWarps) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(kTnBM, t.bk, 1, 1);      // both operands MN-major
             for (int it = 0; it < chunks; ++it) {
                 const int s = it % t.stages;
                 const uint32_t ph = (it / t.stages) & 1;
+                const int seg = it / kTnSegChunks, in_seg = it % kTnSegChunks;
+                const int acc = seg & 1;
+                if (in_seg == 0) {
+                    mbar_wait(&tempty[acc], ((seg >> 1) & 1) ^ 1);          // drained (passes at once for the first two segments)
+                    tc_fence_after();
+                }
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * t.acc_stride);
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 const uint32_t g_hi = smem_u32(smem + (size_t)s * stage_bytes);
@@ -522,37 +540,43 @@ __global__ void __launch_bounds__(kTnThreads, 1) k_gemm_tn_tc(const TnArgs t) {
                     const uint64_t dgl = make_desc(g_lo + j * 2 * kTnSbo, kTnLbo, kTnSbo, kLayoutSw128Base32);
                     const uint64_t dah = make_desc(a_hi + j * 2 * kTnSbo, kTnLbo, kTnSbo, kLayoutSw128Base32);
                     const uint64_t dal = make_desc(a_lo + j * 2 * kTnSbo, kTnLbo, kTnSbo, kLayoutSw128Base32);
-                    umma_tf32(tmem_base, dgl, dah, idesc, (it | j) ? 1u : 0u);
-                    umma_tf32(tmem_base, dgh, dal, idesc, 1u);
-                    umma_tf32(tmem_base, dgh, dah, idesc, 1u);
+                    umma_tf32(d_tmem, dgl, dah, idesc, (in_seg | j) ? 1u : 0u);
+                    umma_tf32(d_tmem, dgh, dal, idesc, 1u);
+                    umma_tf32(d_tmem, dgh, dah, idesc, 1u);
                 }
                 umma_commit(&empty[s]);
+                if (in_seg == kTnSegChunks - 1 || it == chunks - 1) umma_commit(&tfull[acc]);
             }
-            umma_commit(tfull);
         }
-    }
-    // epilogue: warps 0..3 (TMEM lane quarter = warp id) write the partial tile
-    if (warp < 4) {
+    } else {
+        // drain warps: TMEM lane quarter = warp % 4; running total lives in the CTA's partial tile (L2-resident),
+        // always updated by the same thread in the same order -> deterministic
+        const int quarter = warp & 3;
         float* out = t.partial + (int64_t)blockIdx.y * t.n * t.k;
-        const int gn = n0 + warp * 32 + lane;
-        if (chunks > 0) {
-            mbar_wait(tfull, 0);
-            tc_fence_after();
-        }
+        const int gn = n0 + quarter * 32 + lane;
         const int kcols = min(t.bk, t.k - k0);
-        for (int c0 = 0; c0 < kcols; c0 += 32) {
-            float v[32];
-            if (chunks > 0) {
-                tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-            } else {
+        if (segments == 0) {
+            if (gn < t.n)
+                for (int c = 0; c < kcols; ++c) out[(int64_t)gn * t.k + k0 + c] = 0.f;
+        }
+        for (int seg = 0; seg < segments; ++seg) {
+            const int acc = seg & 1;
+            mbar_wait(&tfull[acc], (seg >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * t.acc_stride);
+            for (int c0 = 0; c0 < kcols; c0 += 32) {
+                float v[32];
+                tmem_ld_32x32(taddr + (uint32_t)c0, v);
+                if (gn < t.n) {
+                    float* op = out + (int64_t)gn * t.k + k0 + c0;
 #pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = 0.f;
+                    for (int e = 0; e < 32; ++e)
+                        if (c0 + e < kcols) op[e] = seg == 0 ? v[e] : op[e] + v[e];
+                }
             }
-            if (gn < t.n) {
-#pragma unroll
-                for (int e = 0; e < 32; ++e)
-                    if (c0 + e < kcols) out[(int64_t)gn * t.k + k0 + c0 + e] = v[e];
-            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
         }
     }
     tc_fence_before();
@@ -651,7 +675,7 @@ int gemm_tc_launch(const GemmArgs& g, void* ws, size_t ws_bytes, cudaStream_t st
 
 // ---- weight gradient ----
 struct TnPlan {
-    int bk, k_tiles, n_tiles, stages, splits;
+    int bk, k_tiles, n_tiles, stages, splits, acc_stride;
     int64_t m_per_split;
     size_t smem_bytes, ws_bytes;
     uint32_t tmem_cols;
@@ -674,8 +698,9 @@ static TnPlan tn_plan(int64_t m, int n, int k) {
     p.splits = (int)(want < maxs ? want : maxs);
     p.m_per_split = ceil_div(ceil_div(m, p.splits), kTnBK) * kTnBK;
     p.ws_bytes = (size_t)p.splits * n * k * sizeof(float);
+    p.acc_stride = (p.bk + 31) / 32 * 32;
     uint32_t cols = 32;
-    while (cols < (uint32_t)((p.bk + 31) / 32 * 32)) cols <<= 1;
+    while (cols < (uint32_t)(2 * p.acc_stride)) cols <<= 1;
     p.tmem_cols = cols;
     return p;
 }
@@ -705,7 +730,7 @@ int gemm_tn_tc_launch(const float* g, int64_t ldg, const float* a, int64_t lda, 
     }
     TnArgs t{};
     t.g = g; t.ldg = ldg; t.a = a; t.lda = lda; t.partial = (float*)ws; t.m = m; t.n = n; t.k = k;
-    t.bk = p.bk; t.k_tiles = p.k_tiles; t.stages = p.stages; t.m_per_split = p.m_per_split; t.tmem_cols = p.tmem_cols;
+    t.bk = p.bk; t.k_tiles = p.k_tiles; t.stages = p.stages; t.m_per_split = p.m_per_split; t.tmem_cols = p.tmem_cols; t.acc_stride = p.acc_stride;
     dim3 grid((unsigned)(p.n_tiles * p.k_tiles), (unsigned)p.splits);
     k_gemm_tn_tc<<<grid, kTnThreads, p.smem_bytes, stream>>>(t);
     SGB_CHECK_LAUNCH("k_gemm_tn_tc");

@@ -224,11 +224,12 @@ def test_gemm_tn_and_colsum(m, n, k):
     torch.manual_seed(m)
     g, a = torch.randn(m, n), torch.randn(m, k)
     got = ops.gemm_tn(g.to(DEV), a.to(DEV))
-    assert_close(got, g.double().t() @ a.double(), 2e-6, "gemm_tn")
+    assert_close(got, g.double().t() @ a.double(), 5e-6, "gemm_tn")
     again = ops.gemm_tn(g.to(DEV), a.to(DEV))
     assert torch.equal(got, again), "split-m reduction must be deterministic"
     acc = ops.gemm_tn(g.to(DEV), a.to(DEV), out=got.clone(), accumulate=True)
-    assert_close(acc, 2 * (g.double().t() @ a.double()), 2e-6, "gemm_tn accumulate")
+    assert_close(acc, 2 * (g.double().t() @ a.double()), 5e-6, "gemm_tn accumulate")
+    assert_close(ops.gemm_tn(g.to(DEV), a.to(DEV), engine=1), g.double().t() @ a.double(), 2e-6, "gemm_tn fp32 tiles")
     assert_close(ops.colsum(g.to(DEV)), g.double().sum(0), 2e-6, "colsum")
 
 
