@@ -103,14 +103,14 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ float tf32_rn(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
+// hi = x rounded to nearest tf32 (10 explicit mantissa bits; ties away from zero), computed on the integer
+// pipe: adding half an ulp to the magnitude bits and masking is exactly cvt.rna.tf32.f32 for finite x, in 2
+// full-rate ops (ptxas expands the cvt into ~10 ops with NaN handling, which made the producers ALU-bound).
+// lo = x - hi is exact in fp32 and is fed to the tensor core as is: the hardware drops the bits below tf32
+// precision, an error <= 2^-10 |lo| <= 2^-21 |x|.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    hi = tf32_rn(x);
-    lo = tf32_rn(x - hi);
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    lo = x - hi;
 }
 
 // shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
@@ -223,44 +223,59 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const TcArgs g) {
         const bool pro = g.a_scale != nullptr;
         // chunk = 128 rows x 8 float4; thread handles rows r0 + 32*i (i<4), float4 column cq
         const int cq = ptid & 7, r0 = ptid >> 3;               // r0 in 0..31
-        uint32_t it = 0;
-        for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        // flattened (tile, k-chunk) iteration space with a two-deep register prefetch: the loads of
+        // iteration i+2 are in flight while iteration i is converted and stored
+        const int64_t my_tiles = total_tiles > blockIdx.x ? (total_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+        const int64_t total_it = my_tiles * g.k_chunks;
+        auto issue = [&](int64_t i, float4 (&v)[4]) {
+            const int64_t tile = blockIdx.x + (i / g.k_chunks) * gridDim.x;
+            const int q = (int)(i % g.k_chunks);
             const int64_t m0 = (tile / g.n_tiles) * kTcBM;
-            for (int q = 0; q < g.k_chunks; ++q, ++it) {
-                const int s = it % g.stages;
-                const uint32_t ph = (it / g.stages) & 1;
-                const int kcol = q * kTcBK + cq * 4;
-                float4 v[4];
+            const int kcol = q * kTcBK + cq * 4;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int64_t gm = m0 + r0 + 32 * i;
-                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (gm < g.m && kcol < g.k) v[i] = ldg4(g.a + gm * g.lda + kcol);   // K % 4 == 0 guaranteed by the dispatcher
-                }
-                float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (pro && kcol < g.k) { mu = ldg4(g.a_mean + kcol); sc = ldg4(g.a_scale + kcol); sh = ldg4(g.a_shift + kcol); }
-                mbar_wait(&empty[s], ph ^ 1);
-                uint8_t* a_hi = smem + (size_t)s * stage_bytes;
-                uint8_t* a_lo = a_hi + kTcATile;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = r0 + 32 * i;
-                    float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-                    if (pro) {
-                        x[0] = bn_lrelu(x[0], mu.x, sc.x, sh.x, g.slope); x[1] = bn_lrelu(x[1], mu.y, sc.y, sh.y, g.slope);
-                        x[2] = bn_lrelu(x[2], mu.z, sc.z, sh.z, g.slope); x[3] = bn_lrelu(x[3], mu.w, sc.w, sh.w, g.slope);
-                        if (m0 + r >= g.m || kcol >= g.k) { x[0] = x[1] = x[2] = x[3] = 0.f; }
-                    }
-                    float h[4], l[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) split_tf32(x[e], h[e], l[e]);
-                    const uint32_t off = (uint32_t)(r >> 3) * kTcASbo + (uint32_t)cq * kTcALbo + (uint32_t)(r & 7) * 16;
-                    *reinterpret_cast<float4*>(a_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
-                    *reinterpret_cast<float4*>(a_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
-                }
-                fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-                mbar_arrive(&full[s]);
+            for (int r = 0; r < 4; ++r) {
+                const int64_t gm = m0 + r0 + 32 * r;
+                v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < total_it && gm < g.m && kcol < g.k) v[r] = ldg4(g.a + gm * g.lda + kcol);   // K % 4 == 0 guaranteed by the dispatcher
             }
+        };
+        float4 nxt0[4], nxt1[4];      // iterations it and it+1 (plain registers: no dynamic indexing)
+        issue(0, nxt0);
+        issue(1, nxt1);
+        for (int64_t it = 0; it < total_it; ++it) {
+            const int s = (int)(it % g.stages);
+            const uint32_t ph = (uint32_t)((it / g.stages) & 1);
+            const int64_t tile = blockIdx.x + (it / g.k_chunks) * gridDim.x;
+            const int q = (int)(it % g.k_chunks);
+            const int64_t m0 = (tile / g.n_tiles) * kTcBM;
+            const int kcol = q * kTcBK + cq * 4;
+            float4 v[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { v[r] = nxt0[r]; nxt0[r] = nxt1[r]; }
+            issue(it + 2, nxt1);
+            float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pro && kcol < g.k) { mu = ldg4(g.a_mean + kcol); sc = ldg4(g.a_scale + kcol); sh = ldg4(g.a_shift + kcol); }
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* a_hi = smem + (size_t)s * stage_bytes;
+            uint8_t* a_lo = a_hi + kTcATile;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = r0 + 32 * i;
+                float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+                if (pro) {
+                    x[0] = bn_lrelu(x[0], mu.x, sc.x, sh.x, g.slope); x[1] = bn_lrelu(x[1], mu.y, sc.y, sh.y, g.slope);
+                    x[2] = bn_lrelu(x[2], mu.z, sc.z, sh.z, g.slope); x[3] = bn_lrelu(x[3], mu.w, sc.w, sh.w, g.slope);
+                    if (m0 + r >= g.m || kcol >= g.k) { x[0] = x[1] = x[2] = x[3] = 0.f; }
+                }
+                float h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split_tf32(x[e], h[e], l[e]);
+                const uint32_t off = (uint32_t)(r >> 3) * kTcASbo + (uint32_t)cq * kTcALbo + (uint32_t)(r & 7) * 16;
+                *reinterpret_cast<float4*>(a_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(a_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+            }
+            fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            mbar_arrive(&full[s]);
         }
     } else if (warp == kTcProducerWarps) {
         // ================= B copy: one bulk copy of the pre-tiled hi|lo weight image per stage =================
@@ -555,6 +570,7 @@ __global__ void __launch_bounds__(kTnThreads, 1) k_gemm_tn_tc(const TnArgs t) {
         float* out = t.partial + (int64_t)blockIdx.y * t.n * t.k;
         const int gn = n0 + quarter * 32 + lane;
         const int kcols = min(t.bk, t.k - k0);
+        const bool vec_ok = (t.k % 4 == 0) && (k0 % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
         if (segments == 0) {
             if (gn < t.n)
                 for (int c = 0; c < kcols; ++c) out[(int64_t)gn * t.k + k0 + c] = 0.f;
@@ -569,9 +585,23 @@ __global__ void __launch_bounds__(kTnThreads, 1) k_gemm_tn_tc(const TnArgs t) {
                 tmem_ld_32x32(taddr + (uint32_t)c0, v);
                 if (gn < t.n) {
                     float* op = out + (int64_t)gn * t.k + k0 + c0;
+                    if (vec_ok && c0 + 32 <= kcols) {
+                        float4 old[8];
+                        if (seg != 0) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e)
-                        if (c0 + e < kcols) op[e] = seg == 0 ? v[e] : op[e] + v[e];
+                            for (int e = 0; e < 8; ++e) old[e] = *reinterpret_cast<const float4*>(op + 4 * e);
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float4 o = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                            if (seg != 0) { o.x += old[e].x; o.y += old[e].y; o.z += old[e].z; o.w += old[e].w; }
+                            *reinterpret_cast<float4*>(op + 4 * e) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e)
+                            if (c0 + e < kcols) op[e] = seg == 0 ? v[e] : op[e] + v[e];
+                    }
                 }
             }
             tc_fence_before();

@@ -22,7 +22,6 @@
 namespace sgb {
 
 constexpr int kSpmmThreads = 256;
-constexpr int kSpmmCtasPerSm = 4;
 
 template <int VEC>
 struct Vec;
@@ -65,19 +64,56 @@ struct SpmmArgs {
     float* stat_partials;
 };
 
-template <int LPV, int VEC, int ITERS>
-__global__ void __launch_bounds__(kSpmmThreads) k_spmm(const SpmmArgs a) {
-    constexpr int NB = (8 / ITERS) < 2 ? 2 : (8 / ITERS);   // neighbours batched per round of loads
+constexpr int kSpmmVpc = 64;      // vertices per chunk (contiguous ids); a CTA owns a contiguous range of chunks
+constexpr int kSpmmEcap = 1024;   // neighbour indices staged in shared memory per chunk (mesh: ~6 * 64 = 384)
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// Pipeline per CTA: while chunk c is being gathered, the CSR slice of chunk c+1 (colidx) and the row
+// pointers of chunk c+2 are already in flight (cp.async into the other half of the double buffer).
+// Per vertex there is exactly ONE round of dependent global loads: the neighbour rows, the self row
+// and the dis[] entries are all issued together (indices come from shared memory).
+template <int LPV, int VEC, int ITERS, bool PRO, bool STATS>
+__global__ void __launch_bounds__(kSpmmThreads, (VEC == 4) ? 2 : 3) k_spmm(const SpmmArgs a) {
+    constexpr int NB = 6;                                   // neighbour rows loaded per round (+ the self row in round 0)
+    constexpr int VPI = (ITERS == 1) ? 2 : 1;               // vertices in flight per sub-warp
     constexpr int CH = LPV * VEC * ITERS;                   // channels per pass
-    constexpr int GROUPS = kSpmmThreads / LPV;
-    const unsigned full = 0xffffffffu;
+    constexpr int GROUPS = kSpmmThreads / LPV;              // sub-warps per CTA
     const int l = threadIdx.x & (LPV - 1);
     const int grp = threadIdx.x / LPV;
-    const int64_t gstride = (int64_t)gridDim.x * GROUPS;
-    const bool pro = a.in_scale != nullptr;
-    const bool stats = a.stat_partials != nullptr;
+    constexpr bool pro = PRO;        // compile-time: the BatchNorm vectors / statistics accumulators cost ~30 registers
+    constexpr bool stats = STATS;
+    const bool self_slot = a.mode != SGB_MODE_ADJ;
     __shared__ float red[2][kSpmmThreads * VEC * ITERS];
     __shared__ float redn[kSpmmThreads];
+    __shared__ int s_rowptr[2][kSpmmVpc + 1];
+    __shared__ int s_col[2][kSpmmEcap];
+    const int64_t nchunks = (a.n + kSpmmVpc - 1) / kSpmmVpc;
+    const int64_t cpc = (nchunks + gridDim.x - 1) / gridDim.x;
+    const int64_t cbeg = (int64_t)blockIdx.x * cpc;
+    const int64_t cend = min64(nchunks, cbeg + cpc);
+
+    auto stage_rowptr = [&](int64_t chunk, int buf) {      // async; chunk may be past the end
+        if (chunk < cend) {
+            const int64_t v0 = chunk * kSpmmVpc;
+            const int nv = (int)min64(kSpmmVpc, a.n - v0);
+            for (int i = threadIdx.x; i <= nv; i += kSpmmThreads) cp_async4(&s_rowptr[buf][i], a.rowptr + v0 + i);
+        }
+    };
+    auto stage_col = [&](int64_t chunk, int buf) {         // needs s_rowptr[buf] of that chunk to be visible
+        if (chunk < cend) {
+            const int64_t v0 = chunk * kSpmmVpc;
+            const int nv = (int)min64(kSpmmVpc, a.n - v0);
+            const int e0 = s_rowptr[buf][0], ne = s_rowptr[buf][nv] - e0;
+            if (ne <= kSpmmEcap)
+                for (int i = threadIdx.x; i < ne; i += kSpmmThreads) cp_async4(&s_col[buf][i], a.colidx + e0 + i);
+        }
+    };
 
     for (int c0 = 0; c0 < a.c; c0 += CH) {
         int ch[ITERS];
@@ -102,118 +138,146 @@ __global__ void __launch_bounds__(kSpmmThreads) k_spmm(const SpmmArgs a) {
 #pragma unroll
             for (int q = 0; q < VEC; ++q) { s1[t][q] = 0.f; s2[t][q] = 0.f; pv[t][q] = 0.f; }
 
-        // all 32 lanes of a warp iterate together (shuffles below are full-warp)
-        const int64_t v0 = (int64_t)blockIdx.x * GROUPS + grp;
-        for (int64_t vbase = v0 - grp % (32 / LPV); vbase < a.n; vbase += gstride) {
-            const int64_t v = vbase + grp % (32 / LPV);
-            const bool vok = v < a.n;
-            int start = 0, end = 0;
-            float di = 0.f;
-            if (vok) {
-                start = __ldg(a.rowptr + v);
-                end = __ldg(a.rowptr + v + 1);
-                di = __ldg(a.dis + v);
-            }
-            Vec<VEC> acc[ITERS];
-#pragma unroll
-            for (int t = 0; t < ITERS; ++t)
-#pragma unroll
-                for (int q = 0; q < VEC; ++q) acc[t].v[q] = 0.f;
+        // ---- pipeline prologue: rowptr(cbeg) -> colidx(cbeg) + rowptr(cbeg+1)
+        __syncthreads();
+        stage_rowptr(cbeg, 0);
+        cp_async_commit_wait_all();
+        __syncthreads();
+        stage_col(cbeg, 0);
+        stage_rowptr(cbeg + 1, 1);
 
-            for (int base = start; __any_sync(full, base < end); base += LPV) {
-                const int mine = base + l;
-                int cj = -1;
-                float dj = 0.f;
-                if (mine < end) {
-                    cj = __ldg(a.colidx + mine);
-                    dj = __ldg(a.dis + cj);
+        for (int64_t chunk = cbeg; chunk < cend; ++chunk) {
+            const int buf = (int)((chunk - cbeg) & 1);
+            cp_async_commit_wait_all();
+            __syncthreads();                                  // chunk's colidx + next chunk's rowptr have landed; previous gather done
+            stage_col(chunk + 1, buf ^ 1);
+            // (rowptr of chunk+2 goes into the buffer this chunk is reading: issued after the gather below)
+            const int64_t v0 = chunk * kSpmmVpc;
+            const int nv = (int)min64(kSpmmVpc, a.n - v0);
+            const int e0 = s_rowptr[buf][0];
+            const bool staged = (s_rowptr[buf][nv] - e0) <= kSpmmEcap;
+            const int* scol = s_col[buf];
+            const int* srp = s_rowptr[buf];
+
+            for (int vb = grp; vb < nv; vb += GROUPS * VPI) {
+                int vi[VPI], kbeg[VPI], kend[VPI];
+                float di[VPI];
+                Vec<VEC> acc[VPI][ITERS], xself[VPI][ITERS];
+#pragma unroll
+                for (int u = 0; u < VPI; ++u) {
+                    vi[u] = vb + u * GROUPS;
+                    const bool vok = vi[u] < nv;
+                    kbeg[u] = vok ? srp[vi[u]] - e0 : 0;
+                    kend[u] = vok ? srp[vi[u] + 1] - e0 : -1;   // -1 => no vertex
+                    di[u] = vok ? __ldg(a.dis + v0 + vi[u]) : 0.f;
+#pragma unroll
+                    for (int t = 0; t < ITERS; ++t)
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) { acc[u][t].v[q] = 0.f; xself[u][t].v[q] = 0.f; }
                 }
-                const int cnt = min(LPV, end - base);
-                for (int k0 = 0; __any_sync(full, k0 < cnt); k0 += NB) {
-                    Vec<VEC> xv[NB][ITERS];
-                    float w[NB];
-                    bool ok[NB];
+                for (int r = 0;; r += NB) {
+                    bool more = false;
+                    Vec<VEC> xv[VPI][NB][ITERS];
+                    float dj[VPI][NB];
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) {
-                        const int j = __shfl_sync(full, cj, k0 + b, LPV);
-                        const float djb = __shfl_sync(full, dj, k0 + b, LPV);
-                        ok[b] = (k0 + b) < cnt;
-                        // w = fl(dis[row] * dis[col]) (A.1 step 1); CHEB negates (exact); ADJ = 1
-                        float wb = __fmul_rn(djb, di);
-                        if (a.mode == SGB_MODE_CHEB) wb = -wb;
-                        if (a.mode == SGB_MODE_ADJ) wb = 1.f;
-                        w[b] = wb;
+                    for (int u = 0; u < VPI; ++u) {
+                        if (r == 0 && self_slot && kend[u] >= 0) {          // self row rides along with the first round
 #pragma unroll
-                        for (int t = 0; t < ITERS; ++t) {
-                            if (ok[b] && act[t]) xv[b][t].load(a.x + (int64_t)j * a.ldx + ch[t]);
+                            for (int t = 0; t < ITERS; ++t)
+                                if (act[t]) xself[u][t].load(a.x + (v0 + vi[u]) * a.ldx + ch[t]);
                         }
+#pragma unroll
+                        for (int b = 0; b < NB; ++b) {
+                            const int k = kbeg[u] + r + b;
+                            dj[u][b] = 0.f;
+                            if (k < kend[u]) {
+                                const int64_t j = staged ? scol[k] : __ldg(a.colidx + e0 + k);
+                                dj[u][b] = __ldg(a.dis + j);
+#pragma unroll
+                                for (int t = 0; t < ITERS; ++t)
+                                    if (act[t]) xv[u][b][t].load(a.x + j * a.ldx + ch[t]);
+                            }
+                        }
+                        more |= (kbeg[u] + r + NB) < kend[u];
                     }
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) {
-                        if (ok[b]) {
+                    for (int u = 0; u < VPI; ++u) {
 #pragma unroll
-                            for (int t = 0; t < ITERS; ++t) {
-                                if (act[t]) {
+                        for (int b = 0; b < NB; ++b) {
+                            const int k = kbeg[u] + r + b;
+                            if (k < kend[u]) {
+                                // w = fl(dis[row] * dis[col]) (A.1 step 1); CHEB negates (exact); ADJ = 1
+                                float w = __fmul_rn(dj[u][b], di[u]);
+                                if (a.mode == SGB_MODE_CHEB) w = -w;
+                                if (a.mode == SGB_MODE_ADJ) w = 1.f;
 #pragma unroll
-                                    for (int q = 0; q < VEC; ++q) {
-                                        float xx = xv[b][t].v[q];
-                                        if (pro) xx = bn_lrelu(xx, mu[t].v[q], sc[t].v[q], sh[t].v[q], a.slope);
-                                        acc[t].v[q] = __fadd_rn(acc[t].v[q], __fmul_rn(w[b], xx));
+                                for (int t = 0; t < ITERS; ++t)
+                                    if (act[t]) {
+#pragma unroll
+                                        for (int q = 0; q < VEC; ++q) {
+                                            float xx = xv[u][b][t].v[q];
+                                            if (pro) xx = bn_lrelu(xx, mu[t].v[q], sc[t].v[q], sh[t].v[q], a.slope);
+                                            acc[u][t].v[q] = __fadd_rn(acc[u][t].v[q], __fmul_rn(w, xx));
+                                        }
                                     }
+                            }
+                        }
+                    }
+                    if (!more) break;
+                }
+#pragma unroll
+                for (int u = 0; u < VPI; ++u) {
+                    if (vi[u] >= nv) continue;
+                    const int64_t v = v0 + vi[u];
+#pragma unroll
+                    for (int t = 0; t < ITERS; ++t) {
+                        if (!act[t]) continue;
+                        Vec<VEC> out = acc[u][t];
+                        if (self_slot) {
+                            const float wii = __fmul_rn(di[u], di[u]);
+#pragma unroll
+                            for (int q = 0; q < VEC; ++q) {
+                                float xx = xself[u][t].v[q];
+                                if (pro) xx = bn_lrelu(xx, mu[t].v[q], sc[t].v[q], sh[t].v[q], a.slope);
+                                if (a.mode == SGB_MODE_GCN) {
+                                    out.v[q] = __fadd_rn(out.v[q], __fmul_rn(wii, xx));
+                                } else {   // CHEB: the (+1, -1) loop pair of ChebConv.__norm__, not cancelled
+                                    out.v[q] = __fadd_rn(__fadd_rn(out.v[q], xx), -xx);
                                 }
                             }
                         }
-                    }
-                }
-            }
-            if (vok) {
+                        if (a.addend) {
+                            Vec<VEC> ad;
+                            ad.load(a.addend + v * a.ld_addend + ch[t]);
 #pragma unroll
-                for (int t = 0; t < ITERS; ++t) {
-                    if (!act[t]) continue;
-                    Vec<VEC> out = acc[t];
-                    if (a.mode != SGB_MODE_ADJ) {
-                        Vec<VEC> xi;
-                        xi.load(a.x + v * a.ldx + ch[t]);
-                        const float wii = __fmul_rn(di, di);
+                            for (int q = 0; q < VEC; ++q)
+                                out.v[q] = __fadd_rn(__fmul_rn(a.alpha, out.v[q]), __fmul_rn(a.beta, ad.v[q]));
+                        } else if (a.alpha != 1.f) {
 #pragma unroll
-                        for (int q = 0; q < VEC; ++q) {
-                            float xx = xi.v[q];
-                            if (pro) xx = bn_lrelu(xx, mu[t].v[q], sc[t].v[q], sh[t].v[q], a.slope);
-                            if (a.mode == SGB_MODE_GCN) {
-                                out.v[q] = __fadd_rn(out.v[q], __fmul_rn(wii, xx));
-                            } else {   // CHEB: the (+1, -1) loop pair of ChebConv.__norm__, not cancelled
-                                out.v[q] = __fadd_rn(__fadd_rn(out.v[q], xx), -xx);
+                            for (int q = 0; q < VEC; ++q) out.v[q] = __fmul_rn(a.alpha, out.v[q]);
+                        }
+                        if (a.bias) {
+#pragma unroll
+                            for (int q = 0; q < VEC; ++q) out.v[q] = __fadd_rn(out.v[q], bs[t].v[q]);
+                        }
+                        out.store(a.y + v * a.ldy + ch[t]);
+                        if (stats) {
+#pragma unroll
+                            for (int q = 0; q < VEC; ++q) {
+                                if (nseen == 0.f) pv[t][q] = out.v[q];
+                                const float dv = out.v[q] - pv[t][q];
+                                s1[t][q] += dv;
+                                s2[t][q] = fmaf(dv, dv, s2[t][q]);
                             }
                         }
                     }
-                    if (a.addend) {
-                        Vec<VEC> ad;
-                        ad.load(a.addend + v * a.ld_addend + ch[t]);
-#pragma unroll
-                        for (int q = 0; q < VEC; ++q)
-                            out.v[q] = __fadd_rn(__fmul_rn(a.alpha, out.v[q]), __fmul_rn(a.beta, ad.v[q]));
-                    } else if (a.alpha != 1.f) {
-#pragma unroll
-                        for (int q = 0; q < VEC; ++q) out.v[q] = __fmul_rn(a.alpha, out.v[q]);
-                    }
-                    if (a.bias) {
-#pragma unroll
-                        for (int q = 0; q < VEC; ++q) out.v[q] = __fadd_rn(out.v[q], bs[t].v[q]);
-                    }
-                    out.store(a.y + v * a.ldy + ch[t]);
-                    if (stats) {
-#pragma unroll
-                        for (int q = 0; q < VEC; ++q) {
-                            if (nseen == 0.f) pv[t][q] = out.v[q];
-                            const float dv = out.v[q] - pv[t][q];
-                            s1[t][q] += dv;
-                            s2[t][q] = fmaf(dv, dv, s2[t][q]);
-                        }
-                    }
+                    nseen += 1.f;
                 }
-                nseen += 1.f;
             }
+            __syncthreads();                                  // everyone is done reading s_rowptr[buf]
+            stage_rowptr(chunk + 2, buf);
         }
+        cp_async_commit_wait_all();
         if (stats) {   // fixed-order block merge (Chan) -> partials[blockIdx.x][3][c] = (count, mean, M2)
 #pragma unroll
             for (int t = 0; t < ITERS; ++t)
@@ -262,9 +326,9 @@ static SpmmCfg pick_cfg(int c, bool aligned) {
 }
 
 static int spmm_grid(int64_t n, const SpmmCfg& k) {
-    int groups = kSpmmThreads / k.lpv;
-    int64_t need = ceil_div(n > 0 ? n : 1, groups);
-    int64_t cap = (int64_t)num_sms() * kSpmmCtasPerSm;
+    int64_t need = ceil_div(n > 0 ? n : 1, kSpmmVpc);
+    int per_sm = (k.vec == 4) ? 2 : 3;
+    int64_t cap = (int64_t)num_sms() * per_sm;
     return (int)(need < cap ? need : cap);
 }
 
@@ -306,11 +370,15 @@ extern "C" int sgb_spmm(const int32_t* rowptr, const int32_t* colidx, const floa
             SGB_CUDA(cudaMemsetAsync(stat_partials + (size_t)grid * 3 * c, 0, (size_t)(rows - grid) * 3 * c * sizeof(float), stream));
     }
     SpmmArgs a{rowptr, colidx, dis, mode, x, ldx, n, c, in_mean, in_scale, in_shift, slope, alpha, addend, ld_addend, beta, bias, y, ldy, stat_partials};
-#define SGB_SPMM_CASE(L, V, I)                                         \
-    if (k.lpv == L && k.vec == V && k.iters == I) {                    \
-        k_spmm<L, V, I><<<grid, kSpmmThreads, 0, stream>>>(a);         \
-        SGB_CHECK_LAUNCH("k_spmm");                                    \
-        return SGB_OK;                                                 \
+    const bool pro = in_scale != nullptr, st = stat_partials != nullptr;
+#define SGB_SPMM_CASE(L, V, I)                                                                  \
+    if (k.lpv == L && k.vec == V && k.iters == I) {                                             \
+        if (pro && st) k_spmm<L, V, I, true, true><<<grid, kSpmmThreads, 0, stream>>>(a);       \
+        else if (pro) k_spmm<L, V, I, true, false><<<grid, kSpmmThreads, 0, stream>>>(a);       \
+        else if (st) k_spmm<L, V, I, false, true><<<grid, kSpmmThreads, 0, stream>>>(a);        \
+        else k_spmm<L, V, I, false, false><<<grid, kSpmmThreads, 0, stream>>>(a);               \
+        SGB_CHECK_LAUNCH("k_spmm");                                                             \
+        return SGB_OK;                                                                          \
     }
     SGB_SPMM_CASE(1, 4, 1)
     SGB_SPMM_CASE(2, 4, 1)
