@@ -51,6 +51,13 @@ extern "C" {
 #define SGB_MODE_ADJ 2  /* plain adjacency sum (weights 1, no loops): mesh_laplacian_loss
                            (util/loss.py:60-76), mask dilation (util/datamaker.py:124-127)    */
 
+/* one CSR entry as the aggregation kernel consumes it: neighbour id + its normalised weight
+ * (GCN: dis[src]*dis[dst]; CHEB: -dis[src]*dis[dst]; ADJ: 1), 8 bytes, streamed once per SpMM */
+typedef struct sgb_edge {
+    int32_t col;
+    float w;
+} sgb_edge_t;
+
 SGB_API int sgb_version(void);
 SGB_API const char* sgb_last_error(void);
 /* number of SMs of the current device (used by callers to size stat-partial buffers) */
@@ -65,19 +72,22 @@ SGB_API int sgb_num_sms(void);
  *    `deg.pow_(-0.5)`; deg = 0 -> 0.
  *    Replaces: gcn_norm / get_laplacian / add_remaining_self_loops executed inside every
  *    GCNConv / ChebConv forward; input contract util/mesh.py:229-230.
+ *    edges[slot] = (colidx[slot], weight) with weight = fl(dis[src] * dis[dst]) (negated for
+ *    CHEB, 1 for ADJ) -- the per-edge `norm` of gcn_norm / ChebConv.__norm__, bit-exact; this
+ *    packed stream is what sgb_spmm reads (one 8-byte load per neighbour).
  *    perm[e] = slot of edge e in colidx, or -1 for a dropped self loop.
  *    err_flag (device int32[1], zero-initialised by the call): 1 if an index was outside
  *    [0, n).
  * ------------------------------------------------------------------------------------ */
 SGB_API size_t sgb_graph_build_workspace_bytes(int64_t nnz, int64_t n);
 SGB_API int sgb_graph_build(const int64_t* edge_index, int64_t nnz, int64_t n, int mode, int transpose,
-                    int32_t* rowptr /* [n+1] */, int32_t* colidx /* [nnz] */, float* dis /* [n] */,
-                    int32_t* perm /* [nnz] or NULL */, int32_t* err_flag /* [1] */,
+                    int32_t* rowptr /* [n+1] */, int32_t* colidx /* [nnz] */, sgb_edge_t* edges /* [nnz] or NULL */,
+                    float* dis /* [n] */, int32_t* perm /* [nnz] or NULL */, int32_t* err_flag /* [1] */,
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------ *
  * 2. SpMM: Y = alpha * (S f(X)) + beta * ADDEND + bias, row-parallel gather, one
- *    sub-warp per vertex, 128-bit loads, atomic-free; S is defined by (rowptr, colidx,
+ *    sub-warp per vertex, 128-bit loads, atomic-free; S is defined by (rowptr, edges,
  *    dis, mode); accumulation order per row = CSR order then the self-loop term(s), with
  *    separately rounded multiply and add -- the op order of PyG's message/aggregate
  *    (SURVEY.md A.1 step 3, A.6), so the result is bit-identical to the CPU path.
@@ -92,7 +102,7 @@ SGB_API int sgb_graph_build(const int64_t* edge_index, int64_t nnz, int64_t n, i
  *    called with the transpose CSR, bwd.
  * ------------------------------------------------------------------------------------ */
 SGB_API int sgb_spmm_stat_rows(int64_t n, int c);
-SGB_API int sgb_spmm(const int32_t* rowptr, const int32_t* colidx, const float* dis, int mode,
+SGB_API int sgb_spmm(const int32_t* rowptr, const sgb_edge_t* edges, const float* dis, int mode,
              const float* x, int64_t ldx, int64_t n, int c,
              const float* in_mean, const float* in_scale, const float* in_shift, float slope,
              float alpha, const float* addend, int64_t ld_addend, float beta,

@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libsemigcn_b200.so")
+LIB_PATH = os.environ.get("SGB_LIB_PATH") or os.path.join(CSRC, "libsemigcn_b200.so")   # override: A/B builds of the same ABI
 
 MODE_GCN, MODE_CHEB, MODE_ADJ = 0, 1, 2
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
@@ -28,7 +28,7 @@ SIGNATURES = {
     "sgb_last_error": (C.c_char_p, []),
     "sgb_num_sms": (_i32, []),
     "sgb_graph_build_workspace_bytes": (_sz, [_i64, _i64]),
-    "sgb_graph_build": (_i32, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "sgb_graph_build": (_i32, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sgb_spmm_stat_rows": (_i32, [_i64, _i32]),
     "sgb_spmm": (_i32, [_vp, _vp, _vp, _i32, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _f32, _f32, _vp, _i64, _f32,
                         _vp, _vp, _i64, _vp, _vp]),

@@ -10,8 +10,8 @@
 //   k_count   : histogram of group keys + degree keys (int atomics: exact, order-free)
 //   scan x3   : exclusive scan -> rowptr
 //   k_fill    : bucket edge ids (unordered inside a bucket)
-//   k_rank    : per row, rank edge ids (8 lanes per row) -> stable colidx + perm
 //   k_dis     : dis[i] = deg ? 1/sqrt(deg (+1 for GCN)) : 0
+//   k_rank    : per row, rank edge ids (8 lanes per row) -> stable colidx + perm + packed (col, weight) stream
 #include "common.cuh"
 
 namespace sgb {
@@ -129,9 +129,9 @@ __global__ void k_fill(const int64_t* __restrict__ ei, int64_t nnz, int64_t n, i
 }
 
 // 8 lanes per row: rank every bucketed edge id among its row's ids -> stable position.
-__global__ void k_rank(const int64_t* __restrict__ ei, int64_t nnz, int64_t n, int transpose,
-                       const int32_t* __restrict__ rowptr, const int32_t* __restrict__ tmp,
-                       int32_t* __restrict__ colidx, int32_t* __restrict__ perm) {
+__global__ void k_rank(const int64_t* __restrict__ ei, int64_t nnz, int64_t n, int mode, int transpose,
+                       const int32_t* __restrict__ rowptr, const int32_t* __restrict__ tmp, const float* __restrict__ dis,
+                       int32_t* __restrict__ colidx, int2* __restrict__ edges, int32_t* __restrict__ perm) {
     constexpr int G = 8;
     int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
     int sub = threadIdx.x & (G - 1);
@@ -144,6 +144,15 @@ __global__ void k_rank(const int64_t* __restrict__ ei, int64_t nnz, int64_t n, i
             for (int q = s; q < t; ++q) rank += (tmp[q] < e);
             int64_t other = transpose ? ei[nnz + e] : ei[e];
             colidx[s + rank] = (int32_t)other;
+            if (edges) {
+                // norm_e = fl(fl(dis[src] * 1) * dis[dst]) (A.1 step 1 / A.2 step 1); CHEB negates (exact); ADJ = 1
+                float w = 1.f;
+                if (mode != SGB_MODE_ADJ) {
+                    w = __fmul_rn(dis[other], dis[row]);
+                    if (mode == SGB_MODE_CHEB) w = -w;
+                }
+                edges[s + rank] = make_int2((int32_t)other, __float_as_int(w));
+            }
             if (perm) perm[e] = s + rank;
         }
     }
@@ -188,7 +197,7 @@ extern "C" size_t sgb_graph_build_workspace_bytes(int64_t nnz, int64_t n) {
 }
 
 extern "C" int sgb_graph_build(const int64_t* edge_index, int64_t nnz, int64_t n, int mode, int transpose,
-                               int32_t* rowptr, int32_t* colidx, float* dis, int32_t* perm, int32_t* err_flag,
+                               int32_t* rowptr, int32_t* colidx, sgb_edge_t* edges, float* dis, int32_t* perm, int32_t* err_flag,
                                void* workspace, size_t workspace_bytes, void* stream_) {
     using namespace sgb;
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -224,11 +233,14 @@ extern "C" int sgb_graph_build(const int64_t* edge_index, int64_t nnz, int64_t n
     if (nnz > 0) {
         k_fill<<<egrid, threads, 0, stream>>>(edge_index, nnz, n, transpose, rowptr, w.cursor, w.tmp);
         SGB_CHECK_LAUNCH("k_fill");
-        int rgrid = (int)min64(ceil_div(n * 8, threads), (int64_t)num_sms() * 32);
-        k_rank<<<rgrid, threads, 0, stream>>>(edge_index, nnz, n, transpose, rowptr, w.tmp, colidx, perm);
-        SGB_CHECK_LAUNCH("k_rank");
     }
     k_dis<<<ngrid, threads, 0, stream>>>(w.deg, n, mode, dis);
     SGB_CHECK_LAUNCH("k_dis");
+    if (nnz > 0) {
+        int rgrid = (int)min64(ceil_div(n * 8, threads), (int64_t)num_sms() * 32);
+        k_rank<<<rgrid, threads, 0, stream>>>(edge_index, nnz, n, mode, transpose, rowptr, w.tmp, dis, colidx,
+                                              reinterpret_cast<int2*>(edges), perm);
+        SGB_CHECK_LAUNCH("k_rank");
+    }
     return SGB_OK;
 }

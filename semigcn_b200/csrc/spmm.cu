@@ -18,6 +18,7 @@
 //
 // HBM roofline: algorithmic bytes = 2*N*C*4 + (nnz + 2N + 1)*4.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace sgb {
 
@@ -43,7 +44,7 @@ struct Vec<1> {
 
 struct SpmmArgs {
     const int32_t* rowptr;
-    const int32_t* colidx;
+    const int2* edges;                // [nnz] (col, float bits of the edge weight), CSR order
     const float* dis;
     int mode;
     const float* x;
@@ -62,74 +63,87 @@ struct SpmmArgs {
     float* y;
     int64_t ldy;
     float* stat_partials;
+    int strided;                      // 1: CTA b takes chunks b, b+grid, ... (co-resident CTAs sweep one window of X -> L2 reuse)
 };
 
-constexpr int kSpmmVpc = 64;      // vertices per chunk (contiguous ids); a CTA owns a contiguous range of chunks
-constexpr int kSpmmEcap = 1024;   // neighbour indices staged in shared memory per chunk (mesh: ~6 * 64 = 384)
+// vertices per chunk / staged edges per chunk as a function of the sub-warp width: every sub-warp of the CTA
+// gets at least one vertex per chunk
+__host__ __device__ constexpr int spmm_vpc(int lpv) { return (kSpmmThreads / lpv) > 64 ? (kSpmmThreads / lpv) : 64; }
+__host__ __device__ constexpr int spmm_ecap(int lpv) { return spmm_vpc(lpv) * 12 < 1536 ? spmm_vpc(lpv) * 12 : 1536; }
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-// Pipeline per CTA: while chunk c is being gathered, the CSR slice of chunk c+1 (colidx) and the row
-// pointers of chunk c+2 are already in flight (cp.async into the other half of the double buffer).
-// Per vertex there is exactly ONE round of dependent global loads: the neighbour rows, the self row
-// and the dis[] entries are all issued together (indices come from shared memory).
+// Pipeline per CTA: while chunk i is being gathered, the (col, weight) slice of chunk i+1 and the row
+// pointers of chunk i+2 are already in flight (cp.async into the other half of the double buffer).
+// Per vertex there is exactly ONE round of dependent global loads for degree <= NB: the neighbour rows
+// and the self row are all issued together (indices and weights come from shared memory).
 template <int LPV, int VEC, int ITERS, bool PRO, bool STATS>
-__global__ void __launch_bounds__(kSpmmThreads, (VEC == 4) ? 2 : 3) k_spmm(const SpmmArgs a) {
-    constexpr int NB = 6;                                   // neighbour rows loaded per round (+ the self row in round 0)
-    constexpr int VPI = (ITERS == 1) ? 2 : 1;               // vertices in flight per sub-warp
+#ifndef SGB_SPMM_MINB
+#define SGB_SPMM_MINB 2
+#endif
+__global__ void __launch_bounds__(kSpmmThreads, (VEC == 4) ? SGB_SPMM_MINB : 3) k_spmm(const SpmmArgs a) {
+#ifndef SGB_SPMM_NB
+#define SGB_SPMM_NB 6
+#endif
+    constexpr int NB = (VEC * ITERS >= 8) ? SGB_SPMM_NB : 8;  // neighbour rows in flight per round (register budget)
     constexpr int CH = LPV * VEC * ITERS;                   // channels per pass
     constexpr int GROUPS = kSpmmThreads / LPV;              // sub-warps per CTA
+    constexpr int VPC = spmm_vpc(LPV);
+    constexpr int ECAP = spmm_ecap(LPV);
     const int l = threadIdx.x & (LPV - 1);
     const int grp = threadIdx.x / LPV;
-    constexpr bool pro = PRO;        // compile-time: the BatchNorm vectors / statistics accumulators cost ~30 registers
-    constexpr bool stats = STATS;
-    const bool self_slot = a.mode != SGB_MODE_ADJ;
-    __shared__ float red[2][kSpmmThreads * VEC * ITERS];
-    __shared__ float redn[kSpmmThreads];
-    __shared__ int s_rowptr[2][kSpmmVpc + 1];
-    __shared__ int s_col[2][kSpmmEcap];
-    const int64_t nchunks = (a.n + kSpmmVpc - 1) / kSpmmVpc;
+    __shared__ float red[STATS ? 2 : 1][STATS ? kSpmmThreads * VEC * ITERS : 1];
+    __shared__ float redn[STATS ? kSpmmThreads : 1];
+    __shared__ int s_rowptr[2][VPC + 1];
+    __shared__ int2 s_edge[2][ECAP];
+    const int64_t nchunks = (a.n + VPC - 1) / VPC;
+    // chunk schedule: chunk(i) = cfirst + i * cstep for i < ccount
     const int64_t cpc = (nchunks + gridDim.x - 1) / gridDim.x;
-    const int64_t cbeg = (int64_t)blockIdx.x * cpc;
-    const int64_t cend = min64(nchunks, cbeg + cpc);
+    const int64_t cstep = a.strided ? (int64_t)gridDim.x : 1;
+    const int64_t cfirst = a.strided ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * cpc;
+    const int64_t ccount = a.strided ? (nchunks > blockIdx.x ? (nchunks - 1 - blockIdx.x) / gridDim.x + 1 : 0)
+                                     : (min64(nchunks, cfirst + cpc) > cfirst ? min64(nchunks, cfirst + cpc) - cfirst : 0);
 
-    auto stage_rowptr = [&](int64_t chunk, int buf) {      // async; chunk may be past the end
-        if (chunk < cend) {
-            const int64_t v0 = chunk * kSpmmVpc;
-            const int nv = (int)min64(kSpmmVpc, a.n - v0);
+    auto stage_rowptr = [&](int64_t ci, int buf) {         // async; ci (schedule position) may be past the end
+        if (ci < ccount) {
+            const int64_t v0 = (cfirst + ci * cstep) * VPC;
+            const int nv = (int)min64(VPC, a.n - v0);
             for (int i = threadIdx.x; i <= nv; i += kSpmmThreads) cp_async4(&s_rowptr[buf][i], a.rowptr + v0 + i);
         }
     };
-    auto stage_col = [&](int64_t chunk, int buf) {         // needs s_rowptr[buf] of that chunk to be visible
-        if (chunk < cend) {
-            const int64_t v0 = chunk * kSpmmVpc;
-            const int nv = (int)min64(kSpmmVpc, a.n - v0);
+    auto stage_edges = [&](int64_t ci, int buf) {          // needs s_rowptr[buf] of that chunk to be visible
+        if (ci < ccount) {
+            const int64_t v0 = (cfirst + ci * cstep) * VPC;
+            const int nv = (int)min64(VPC, a.n - v0);
             const int e0 = s_rowptr[buf][0], ne = s_rowptr[buf][nv] - e0;
-            if (ne <= kSpmmEcap)
-                for (int i = threadIdx.x; i < ne; i += kSpmmThreads) cp_async4(&s_col[buf][i], a.colidx + e0 + i);
+            if (ne <= ECAP)
+                for (int i = threadIdx.x; i < ne; i += kSpmmThreads) cp_async8(&s_edge[buf][i], a.edges + e0 + i);
         }
     };
 
     for (int c0 = 0; c0 < a.c; c0 += CH) {
         int ch[ITERS];
         bool act[ITERS];
-        Vec<VEC> mu[ITERS], sc[ITERS], sh[ITERS], bs[ITERS];
+        Vec<VEC> mu[ITERS], sc[ITERS], sh[ITERS];
 #pragma unroll
         for (int t = 0; t < ITERS; ++t) {
             ch[t] = c0 + (t * LPV + l) * VEC;
             act[t] = ch[t] < a.c;
 #pragma unroll
-            for (int q = 0; q < VEC; ++q) { mu[t].v[q] = 0.f; sc[t].v[q] = 1.f; sh[t].v[q] = 0.f; bs[t].v[q] = 0.f; }
+            for (int q = 0; q < VEC; ++q) { mu[t].v[q] = 0.f; sc[t].v[q] = 1.f; sh[t].v[q] = 0.f; }
             if (act[t]) {
-                if (pro) { mu[t].load(a.in_mean + ch[t]); sc[t].load(a.in_scale + ch[t]); sh[t].load(a.in_shift + ch[t]); }
-                if (a.bias) bs[t].load(a.bias + ch[t]);
+                if (PRO) { mu[t].load(a.in_mean + ch[t]); sc[t].load(a.in_scale + ch[t]); sh[t].load(a.in_shift + ch[t]); }
             }
         }
+        const float* xl = a.x + ch[0];                       // this lane's first channel; iteration t adds t * LPV * VEC
         // statistics: pivot-shifted sums per thread (pivot = first value seen), see common.cuh
         float s1[ITERS][VEC], s2[ITERS][VEC], pv[ITERS][VEC];
         float nseen = 0.f;
@@ -138,107 +152,86 @@ __global__ void __launch_bounds__(kSpmmThreads, (VEC == 4) ? 2 : 3) k_spmm(const
 #pragma unroll
             for (int q = 0; q < VEC; ++q) { s1[t][q] = 0.f; s2[t][q] = 0.f; pv[t][q] = 0.f; }
 
-        // ---- pipeline prologue: rowptr(cbeg) -> colidx(cbeg) + rowptr(cbeg+1)
+        // ---- pipeline prologue: rowptr(0) -> edges(0) + rowptr(1)
         __syncthreads();
-        stage_rowptr(cbeg, 0);
+        stage_rowptr(0, 0);
         cp_async_commit_wait_all();
         __syncthreads();
-        stage_col(cbeg, 0);
-        stage_rowptr(cbeg + 1, 1);
+        stage_edges(0, 0);
+        stage_rowptr(1, 1);
 
-        for (int64_t chunk = cbeg; chunk < cend; ++chunk) {
-            const int buf = (int)((chunk - cbeg) & 1);
+        for (int64_t ci = 0; ci < ccount; ++ci) {
+            const int buf = (int)(ci & 1);
             cp_async_commit_wait_all();
-            __syncthreads();                                  // chunk's colidx + next chunk's rowptr have landed; previous gather done
-            stage_col(chunk + 1, buf ^ 1);
-            // (rowptr of chunk+2 goes into the buffer this chunk is reading: issued after the gather below)
-            const int64_t v0 = chunk * kSpmmVpc;
-            const int nv = (int)min64(kSpmmVpc, a.n - v0);
+            __syncthreads();                                  // chunk's edges + next chunk's rowptr have landed; previous gather done
+            stage_edges(ci + 1, buf ^ 1);
+            // (rowptr of chunk ci+2 goes into the buffer this chunk is reading: issued after the gather below)
+            const int64_t v0 = (cfirst + ci * cstep) * VPC;
+            const int nv = (int)min64(VPC, a.n - v0);
             const int e0 = s_rowptr[buf][0];
-            const bool staged = (s_rowptr[buf][nv] - e0) <= kSpmmEcap;
-            const int* scol = s_col[buf];
+            const bool staged = (s_rowptr[buf][nv] - e0) <= ECAP;
+            const int2* sedge = s_edge[buf];
             const int* srp = s_rowptr[buf];
 
-            for (int vb = grp; vb < nv; vb += GROUPS * VPI) {
-                int vi[VPI], kbeg[VPI], kend[VPI];
-                float di[VPI];
-                Vec<VEC> acc[VPI][ITERS], xself[VPI][ITERS];
-#pragma unroll
-                for (int u = 0; u < VPI; ++u) {
-                    vi[u] = vb + u * GROUPS;
-                    const bool vok = vi[u] < nv;
-                    kbeg[u] = vok ? srp[vi[u]] - e0 : 0;
-                    kend[u] = vok ? srp[vi[u] + 1] - e0 : -1;   // -1 => no vertex
-                    di[u] = vok ? __ldg(a.dis + v0 + vi[u]) : 0.f;
-#pragma unroll
+            // one instantiation per edge source (shared-memory slice, or global for chunks whose rows are too long to
+            // stage): a per-neighbour select between the two would turn into a branch and serialise the gathers
+            auto gather = [&](auto fetch_edge) {
+                for (int vi = grp; vi < nv; vi += GROUPS) {
+                    const int kb = srp[vi] - e0, ke = srp[vi + 1] - e0;
+                    const int64_t v = v0 + vi;
+                    Vec<VEC> acc[ITERS], xself[ITERS];
+                    float di = 0.f;
+    #pragma unroll
                     for (int t = 0; t < ITERS; ++t)
-#pragma unroll
-                        for (int q = 0; q < VEC; ++q) { acc[u][t].v[q] = 0.f; xself[u][t].v[q] = 0.f; }
-                }
-                for (int r = 0;; r += NB) {
-                    bool more = false;
-                    Vec<VEC> xv[VPI][NB][ITERS];
-                    float dj[VPI][NB];
-#pragma unroll
-                    for (int u = 0; u < VPI; ++u) {
-                        if (r == 0 && self_slot && kend[u] >= 0) {          // self row rides along with the first round
-#pragma unroll
-                            for (int t = 0; t < ITERS; ++t)
-                                if (act[t]) xself[u][t].load(a.x + (v0 + vi[u]) * a.ldx + ch[t]);
-                        }
-#pragma unroll
+    #pragma unroll
+                        for (int q = 0; q < VEC; ++q) { acc[t].v[q] = 0.f; xself[t].v[q] = 0.f; }
+                    if (a.mode != SGB_MODE_ADJ) {                 // the self row rides along with the first round of gathers
+                        if (a.mode == SGB_MODE_GCN) di = __ldg(a.dis + v);
+    #pragma unroll
+                        for (int t = 0; t < ITERS; ++t)
+                            if (act[t]) xself[t].load(xl + v * a.ldx + t * LPV * VEC);
+                    }
+                    for (int r = kb; r < ke; r += NB) {
+                        Vec<VEC> xv[NB][ITERS];
+                        float w[NB];
+    #pragma unroll
                         for (int b = 0; b < NB; ++b) {
-                            const int k = kbeg[u] + r + b;
-                            dj[u][b] = 0.f;
-                            if (k < kend[u]) {
-                                const int64_t j = staged ? scol[k] : __ldg(a.colidx + e0 + k);
-                                dj[u][b] = __ldg(a.dis + j);
-#pragma unroll
+                            if (r + b < ke) {
+                                const int2 ed = fetch_edge(r + b);
+                                w[b] = __int_as_float(ed.y);
+                                const float* xr = xl + (int64_t)ed.x * a.ldx;
+    #pragma unroll
                                 for (int t = 0; t < ITERS; ++t)
-                                    if (act[t]) xv[u][b][t].load(a.x + j * a.ldx + ch[t]);
+                                    if (act[t]) xv[b][t].load(xr + t * LPV * VEC);
                             }
                         }
-                        more |= (kbeg[u] + r + NB) < kend[u];
-                    }
-#pragma unroll
-                    for (int u = 0; u < VPI; ++u) {
-#pragma unroll
+    #pragma unroll
                         for (int b = 0; b < NB; ++b) {
-                            const int k = kbeg[u] + r + b;
-                            if (k < kend[u]) {
-                                // w = fl(dis[row] * dis[col]) (A.1 step 1); CHEB negates (exact); ADJ = 1
-                                float w = __fmul_rn(dj[u][b], di[u]);
-                                if (a.mode == SGB_MODE_CHEB) w = -w;
-                                if (a.mode == SGB_MODE_ADJ) w = 1.f;
-#pragma unroll
+                            if (r + b < ke) {
+                                // msg = fl(w * x_j), acc = fl(acc + msg): PyG's message / aggregate op order (A.1 step 3)
+    #pragma unroll
                                 for (int t = 0; t < ITERS; ++t)
                                     if (act[t]) {
-#pragma unroll
+    #pragma unroll
                                         for (int q = 0; q < VEC; ++q) {
-                                            float xx = xv[u][b][t].v[q];
-                                            if (pro) xx = bn_lrelu(xx, mu[t].v[q], sc[t].v[q], sh[t].v[q], a.slope);
-                                            acc[u][t].v[q] = __fadd_rn(acc[u][t].v[q], __fmul_rn(w, xx));
+                                            float xx = xv[b][t].v[q];
+                                            if (PRO) xx = bn_lrelu(xx, mu[t].v[q], sc[t].v[q], sh[t].v[q], a.slope);
+                                            acc[t].v[q] = __fadd_rn(acc[t].v[q], __fmul_rn(w[b], xx));
                                         }
                                     }
                             }
                         }
                     }
-                    if (!more) break;
-                }
-#pragma unroll
-                for (int u = 0; u < VPI; ++u) {
-                    if (vi[u] >= nv) continue;
-                    const int64_t v = v0 + vi[u];
-#pragma unroll
+                    const float wii = __fmul_rn(di, di);
+    #pragma unroll
                     for (int t = 0; t < ITERS; ++t) {
                         if (!act[t]) continue;
-                        Vec<VEC> out = acc[u][t];
-                        if (self_slot) {
-                            const float wii = __fmul_rn(di[u], di[u]);
-#pragma unroll
+                        Vec<VEC> out = acc[t];
+                        if (a.mode != SGB_MODE_ADJ) {
+    #pragma unroll
                             for (int q = 0; q < VEC; ++q) {
-                                float xx = xself[u][t].v[q];
-                                if (pro) xx = bn_lrelu(xx, mu[t].v[q], sc[t].v[q], sh[t].v[q], a.slope);
+                                float xx = xself[t].v[q];
+                                if (PRO) xx = bn_lrelu(xx, mu[t].v[q], sc[t].v[q], sh[t].v[q], a.slope);
                                 if (a.mode == SGB_MODE_GCN) {
                                     out.v[q] = __fadd_rn(out.v[q], __fmul_rn(wii, xx));
                                 } else {   // CHEB: the (+1, -1) loop pair of ChebConv.__norm__, not cancelled
@@ -249,20 +242,22 @@ __global__ void __launch_bounds__(kSpmmThreads, (VEC == 4) ? 2 : 3) k_spmm(const
                         if (a.addend) {
                             Vec<VEC> ad;
                             ad.load(a.addend + v * a.ld_addend + ch[t]);
-#pragma unroll
+    #pragma unroll
                             for (int q = 0; q < VEC; ++q)
                                 out.v[q] = __fadd_rn(__fmul_rn(a.alpha, out.v[q]), __fmul_rn(a.beta, ad.v[q]));
                         } else if (a.alpha != 1.f) {
-#pragma unroll
+    #pragma unroll
                             for (int q = 0; q < VEC; ++q) out.v[q] = __fmul_rn(a.alpha, out.v[q]);
                         }
-                        if (a.bias) {
-#pragma unroll
-                            for (int q = 0; q < VEC; ++q) out.v[q] = __fadd_rn(out.v[q], bs[t].v[q]);
+                        if (a.bias) {                             // L1-resident; not worth 4*ITERS registers across the gather loop
+                            Vec<VEC> bs;
+                            bs.load(a.bias + ch[t]);
+    #pragma unroll
+                            for (int q = 0; q < VEC; ++q) out.v[q] = __fadd_rn(out.v[q], bs.v[q]);
                         }
                         out.store(a.y + v * a.ldy + ch[t]);
-                        if (stats) {
-#pragma unroll
+                        if (STATS) {
+    #pragma unroll
                             for (int q = 0; q < VEC; ++q) {
                                 if (nseen == 0.f) pv[t][q] = out.v[q];
                                 const float dv = out.v[q] - pv[t][q];
@@ -273,12 +268,18 @@ __global__ void __launch_bounds__(kSpmmThreads, (VEC == 4) ? 2 : 3) k_spmm(const
                     }
                     nseen += 1.f;
                 }
-            }
+            };
+#ifndef SGB_SPMM_BRANCH
+            gather([&](int k) { return staged ? sedge[k] : __ldg(a.edges + e0 + k); });
+#else
+            if (staged) gather([&](int k) { return sedge[k]; });
+            else gather([&](int k) { return __ldg(a.edges + e0 + k); });
+#endif
             __syncthreads();                                  // everyone is done reading s_rowptr[buf]
-            stage_rowptr(chunk + 2, buf);
+            stage_rowptr(ci + 2, buf);
         }
         cp_async_commit_wait_all();
-        if (stats) {   // fixed-order block merge (Chan) -> partials[blockIdx.x][3][c] = (count, mean, M2)
+        if (STATS) {   // fixed-order block merge (Chan) -> partials[blockIdx.x][3][c] = (count, mean, M2)
 #pragma unroll
             for (int t = 0; t < ITERS; ++t)
 #pragma unroll
@@ -286,14 +287,14 @@ __global__ void __launch_bounds__(kSpmmThreads, (VEC == 4) ? 2 : 3) k_spmm(const
                     const int cl = (t * LPV + l) * VEC + q;     // channel within the pass
                     const Moments mo = from_shifted(nseen, pv[t][q], s1[t][q], s2[t][q]);
                     red[0][grp * CH + cl] = mo.mean;
-                    red[1][grp * CH + cl] = mo.m2;
+                    red[STATS ? 1 : 0][grp * CH + cl] = mo.m2;
                 }
             if (l == 0) redn[grp] = nseen;
             __syncthreads();
             for (int cl = threadIdx.x; cl < CH; cl += kSpmmThreads) {
                 if (c0 + cl < a.c) {
                     Moments acc{0.f, 0.f, 0.f};
-                    for (int g = 0; g < GROUPS; ++g) acc = merge(acc, Moments{redn[g], red[0][g * CH + cl], red[1][g * CH + cl]});
+                    for (int g = 0; g < GROUPS; ++g) acc = merge(acc, Moments{redn[g], red[0][g * CH + cl], red[STATS ? 1 : 0][g * CH + cl]});
                     a.stat_partials[((int64_t)blockIdx.x * 3 + 0) * a.c + c0 + cl] = acc.n;
                     a.stat_partials[((int64_t)blockIdx.x * 3 + 1) * a.c + c0 + cl] = acc.mean;
                     a.stat_partials[((int64_t)blockIdx.x * 3 + 2) * a.c + c0 + cl] = acc.m2;
@@ -311,12 +312,17 @@ struct SpmmCfg {
 static SpmmCfg pick_cfg(int c, bool aligned) {
     SpmmCfg k;
     if (c % 4 == 0 && aligned) {
+        // 128-bit lanes, two per lane wherever the row is wide enough: halves the per-vertex index / address
+        // instruction overhead (the kernel is issue-bound, not DRAM-bound, at one float4 per lane)
         k.vec = 4;
-        int lanes = c / 4;
-        int p = 1;
-        while (p < lanes && p < 32) p <<= 1;
-        k.lpv = p;
-        k.iters = lanes > 32 ? 2 : 1;
+        const int lanes = c / 4;
+        if (lanes == 1) { k.lpv = 1; k.iters = 1; }
+        else {
+            int p = 1;
+            while (p * 2 < lanes && p < 32) p <<= 1;
+            k.lpv = p;
+            k.iters = 2;
+        }
     } else {
         k.vec = 1;
         k.lpv = c <= 4 ? 4 : 32;
@@ -326,8 +332,8 @@ static SpmmCfg pick_cfg(int c, bool aligned) {
 }
 
 static int spmm_grid(int64_t n, const SpmmCfg& k) {
-    int64_t need = ceil_div(n > 0 ? n : 1, kSpmmVpc);
-    int per_sm = (k.vec == 4) ? 2 : 3;
+    int64_t need = ceil_div(n > 0 ? n : 1, spmm_vpc(k.lpv));
+    int per_sm = (k.vec == 4) ? SGB_SPMM_MINB : 3;
     int64_t cap = (int64_t)num_sms() * per_sm;
     return (int)(need < cap ? need : cap);
 }
@@ -343,7 +349,7 @@ extern "C" int sgb_spmm_stat_rows(int64_t n, int c) {
     return g1 > g2 ? g1 : g2;
 }
 
-extern "C" int sgb_spmm(const int32_t* rowptr, const int32_t* colidx, const float* dis, int mode,
+extern "C" int sgb_spmm(const int32_t* rowptr, const sgb_edge_t* edges, const float* dis, int mode,
                         const float* x, int64_t ldx, int64_t n, int c,
                         const float* in_mean, const float* in_scale, const float* in_shift, float slope,
                         float alpha, const float* addend, int64_t ld_addend, float beta,
@@ -353,6 +359,7 @@ extern "C" int sgb_spmm(const int32_t* rowptr, const int32_t* colidx, const floa
     SGB_CHECK_ARG(n >= 0 && c > 0, "sgb_spmm: bad shape n=%lld c=%d", (long long)n, c);
     SGB_CHECK_ARG(mode == SGB_MODE_GCN || mode == SGB_MODE_CHEB || mode == SGB_MODE_ADJ, "sgb_spmm: bad mode %d", mode);
     SGB_CHECK_ARG(rowptr && dis && x && y, "sgb_spmm: null pointer");
+    SGB_CHECK_ARG((reinterpret_cast<uintptr_t>(edges) & 7) == 0, "sgb_spmm: edges must be 8-byte aligned");
     SGB_CHECK_ARG(ldx >= c && ldy >= c && (!addend || ld_addend >= c), "sgb_spmm: leading dimension < c");
     SGB_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr) && (in_scale == nullptr) == (in_mean == nullptr),
                   "sgb_spmm: in_mean / in_scale / in_shift must come together");
@@ -369,7 +376,8 @@ extern "C" int sgb_spmm(const int32_t* rowptr, const int32_t* colidx, const floa
         if (rows > grid)
             SGB_CUDA(cudaMemsetAsync(stat_partials + (size_t)grid * 3 * c, 0, (size_t)(rows - grid) * 3 * c * sizeof(float), stream));
     }
-    SpmmArgs a{rowptr, colidx, dis, mode, x, ldx, n, c, in_mean, in_scale, in_shift, slope, alpha, addend, ld_addend, beta, bias, y, ldy, stat_partials};
+    static const int sched = [] { const char* e = getenv("SGB_SPMM_SCHED"); return e ? atoi(e) : 1; }();
+    SpmmArgs a{rowptr, reinterpret_cast<const int2*>(edges), dis, mode, x, ldx, n, c, in_mean, in_scale, in_shift, slope, alpha, addend, ld_addend, beta, bias, y, ldy, stat_partials, sched};
     const bool pro = in_scale != nullptr, st = stat_partials != nullptr;
 #define SGB_SPMM_CASE(L, V, I)                                                                  \
     if (k.lpv == L && k.vec == V && k.iters == I) {                                             \
@@ -381,11 +389,11 @@ extern "C" int sgb_spmm(const int32_t* rowptr, const int32_t* colidx, const floa
         return SGB_OK;                                                                          \
     }
     SGB_SPMM_CASE(1, 4, 1)
-    SGB_SPMM_CASE(2, 4, 1)
-    SGB_SPMM_CASE(4, 4, 1)
-    SGB_SPMM_CASE(8, 4, 1)
-    SGB_SPMM_CASE(16, 4, 1)
-    SGB_SPMM_CASE(32, 4, 1)
+    SGB_SPMM_CASE(1, 4, 2)
+    SGB_SPMM_CASE(2, 4, 2)
+    SGB_SPMM_CASE(4, 4, 2)
+    SGB_SPMM_CASE(8, 4, 2)
+    SGB_SPMM_CASE(16, 4, 2)
     SGB_SPMM_CASE(32, 4, 2)
     SGB_SPMM_CASE(4, 1, 1)
     SGB_SPMM_CASE(32, 1, 1)

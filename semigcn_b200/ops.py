@@ -60,18 +60,25 @@ class MeshGraph:
             for transpose in (0, 1):
                 rowptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
                 colidx = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+                edges = torch.empty((max(nnz, 1), 2), dtype=torch.int32, device=dev)     # sgb_edge_t[nnz]
                 perm = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev) if with_perm else None
-                check(lib.sgb_graph_build(ptr(ei), nnz, n, mode, transpose, ptr(rowptr), ptr(colidx), ptr(self.dis),
-                                          ptr(perm), ptr(err), ptr(ws), wsb, stream_ptr(dev)), "sgb_graph_build")
+                check(lib.sgb_graph_build(ptr(ei), nnz, n, mode, transpose, ptr(rowptr), ptr(colidx), ptr(edges),
+                                          ptr(self.dis), ptr(perm), ptr(err), ptr(ws), wsb, stream_ptr(dev)), "sgb_graph_build")
                 L.count(7)
-                out.append((rowptr, colidx, perm))
+                out.append((rowptr, colidx, perm, edges))
         # one host sync per (edge_index, mode), at cache-fill time only
         if int(err.item()) != 0:
             raise SgbError("edge_index contains vertex ids outside [0, num_nodes)")
-        (self.rowptr, self.colidx, self.perm), (self.rowptr_t, self.colidx_t, self.perm_t) = out
+        (self.rowptr, self.colidx, self.perm, self.edges), (self.rowptr_t, self.colidx_t, self.perm_t, self.edges_t) = out
 
     def csr(self, transpose: bool):
-        return (self.rowptr_t, self.colidx_t) if transpose else (self.rowptr, self.colidx)
+        """(rowptr, packed (col, weight) stream) of the forward (by target) or backward (by source) operator."""
+        return (self.rowptr_t, self.edges_t) if transpose else (self.rowptr, self.edges)
+
+    def edge_weights(self, transpose: bool = False) -> Tensor:
+        """Per-slot normalised weights (float32 view of the packed stream), CSR order."""
+        e = self.edges_t if transpose else self.edges
+        return e[:, 1].view(torch.float32)
 
 
 _GRAPH_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
@@ -117,13 +124,13 @@ def spmm(g: MeshGraph, x: Tensor, transpose: bool = False, in_affine: Affine = N
     if want_stats:
         rows = lib.sgb_spmm_stat_rows(n, c)
         partials = torch.empty((rows, 3, c), dtype=torch.float32, device=x.device)
-    rowptr, colidx = g.csr(transpose)
+    rowptr, edges = g.csr(transpose)
     mu, sc, sh, slope = (in_affine if in_affine is not None else (None, None, None, 0.0))
     nnz_eff = int(g.nnz) + (n if g.mode == MODE_GCN else 0)
     sp = _prof.span(f"spmm_c{c}", 4.0 * (2 * n * c + nnz_eff + 2 * n + 1 + (n * c if addend is not None else 0)),
                     2.0 * nnz_eff * c) if _prof.ACTIVE is not None else None
     with torch.cuda.device(x.device):
-        check(lib.sgb_spmm(ptr(rowptr), ptr(colidx), ptr(g.dis), g.mode, ptr(x), x.stride(0), n, c,
+        check(lib.sgb_spmm(ptr(rowptr), ptr(edges), ptr(g.dis), g.mode, ptr(x), x.stride(0), n, c,
                            ptr(mu), ptr(sc), ptr(sh), float(slope), float(alpha), ptr(addend),
                            addend.stride(0) if addend is not None else 0, float(beta), ptr(bias),
                            ptr(y), y.stride(0), ptr(partials), stream_ptr(x.device)), "sgb_spmm")

@@ -69,6 +69,14 @@ def test_graph_build_bit_exact(kw, mode):
     dis = deg.pow_(-0.5)
     dis[dis == float("inf")] = 0
     assert_bit_equal(g.dis, dis, "dis")
+    # packed (col, weight) stream == the oracle's per-edge norm (gcn_norm / ChebConv.__norm__), slot by slot
+    ei2, w = (O.gcn_norm if mode == 0 else O.cheb_norm)(ei, n)
+    m = int(keep.sum())
+    assert torch.equal(ei2[:, :m], ei[:, keep])                 # the oracle keeps non-loop edges first, in order
+    for by_source, edges, perm in ((False, g.edges, g.perm), (True, g.edges_t, g.perm_t)):
+        slots, edges = perm.cpu().long()[keep], edges.cpu()
+        assert_bit_equal(edges[:, 0][slots], (ei[0] if not by_source else ei[1])[keep].to(torch.int32), "edges.col")
+        assert_bit_equal(edges[:, 1].view(torch.float32)[slots], w[:m], "edges.w")
 
 
 def test_graph_build_all_degrees_bit_exact():
