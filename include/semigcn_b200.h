@@ -108,6 +108,17 @@ SGB_API int sgb_spmm(const int32_t* rowptr, const sgb_edge_t* edges, const float
              float alpha, const float* addend, int64_t ld_addend, float beta,
              const float* bias, float* y, int64_t ldy, float* stat_partials, void* stream);
 
+/* Vertex-partitioned variant (one mesh over several GPUs): rows [0, n) are the
+ * vertices this rank owns; neighbour ids >= n_split address the halo block x_ghost (rows received
+ * from the owning ranks, sgb_gather_rows + all-to-all).  x_ghost = NULL is sgb_spmm.          */
+SGB_API int sgb_spmm_halo(const int32_t* rowptr, const sgb_edge_t* edges, const float* dis, int mode,
+                  const float* x, int64_t ldx, int64_t n, int c, const float* x_ghost, int64_t ld_ghost, int64_t n_split,
+                  const float* in_mean, const float* in_scale, const float* in_shift, float slope,
+                  float alpha, const float* addend, int64_t ld_addend, float beta,
+                  const float* bias, float* y, int64_t ldy, float* stat_partials, void* stream);
+/* out[k, :] = x[idx[k], :] (halo pack; also MeshUnpool-style row gathers), c floats per row */
+SGB_API int sgb_gather_rows(const float* x, int64_t ldx, const int32_t* idx, int64_t count, int c, float* out, int64_t ldo, void* stream);
+
 /* ------------------------------------------------------------------------------------ *
  * 3. Dense feature transform (the per-layer `lin` of GCNConv / `lins[k]` of ChebConv,
  *    nn.Linear of util/networks.py:35,52,58-61) and its two gradients.
@@ -167,6 +178,40 @@ SGB_API int sgb_bn_bwd_finalize(const float* partials, int rows, int c, float* s
 SGB_API int sgb_bn_act_bwd_apply(const float* dz, int64_t lddz, const float* y, int64_t ldy, int64_t m, int c,
                          const float* scale, const float* shift, const float* mean, const float* invstd,
                          const float* sums, float slope, int training, float* dy, int64_t lddy, void* stream);
+
+/* ------------------------------------------------------------------------------------ *
+ * 5. Step-path mesh losses as fused gather/reduce kernels (fp64 accumulation, deterministic).
+ *    Replaces Models.compute_fn (util/models.py:121-126), Loss.mask_pos_rec_loss "rmse"
+ *    (util/loss.py:14-34), Loss.mask_norm_rec_loss "l1mae" (util/loss.py:78-107) as called
+ *    per step by sgcn.py:130-132 / mgcn.py:137-143, and Loss.mesh_laplacian_loss "rmse"
+ *    (util/loss.py:60-76).
+ *    sgb_incidence_build: faces[nf,3] (int64) -> vertex -> face-corner CSR (entries 3*f + corner,
+ *                         ascending inside a row); the backward pass gathers over it (no atomics).
+ *    sgb_step_loss_fwd  : out[0] = loss_p = sqrt(sum_{vmask} |target_pos - pos|^2 / |vmask| + 1e-6)
+ *                         out[1] = loss_n = sum_{fmask} |n_f(pos) - target_fn_f|_1 / |fmask|
+ *                         out[2], out[3] = |vmask|, |fmask|.  target_* are fp64 (target_f64 = 1, the
+ *                         sgcn.py case) or fp32; NULL target_pos / faces skip that term; NULL masks =
+ *                         all; fn_out (optional, [nf,3]) receives the unit face normals (compute_fn).
+ *                         partials: double[sgb_loss_partial_rows()][4].
+ *    sgb_step_loss_bwd  : dpos[n,3] = grads[0] * dloss_p/dpos + grads[1] * dloss_n/dpos.
+ *    sgb_lap_loss_fwd   : diff[n,3] = pos - (Adj pos)/deg over an SGB_MODE_ADJ (or any) CSR;
+ *                         out[0] = sqrt(mean_v |diff_v|^2 + 1e-12).   _bwd: dpos from diff.
+ * ------------------------------------------------------------------------------------ */
+SGB_API int sgb_loss_partial_rows(void);
+SGB_API size_t sgb_incidence_build_workspace_bytes(int64_t nf, int64_t n);
+SGB_API int sgb_incidence_build(const int64_t* faces, int64_t nf, int64_t n, int32_t* rowptr /* [n+1] */, int32_t* inc /* [3 nf] */,
+                        int32_t* err_flag, void* workspace, size_t workspace_bytes, void* stream);
+SGB_API int sgb_step_loss_fwd(const float* pos, int64_t ldp, int64_t n, const void* target_pos, int target_f64, const uint8_t* vmask,
+                      const int64_t* faces, int64_t nf, const void* target_fn, const uint8_t* fmask, float* fn_out,
+                      double* partials, double* out /* [4] */, void* stream);
+SGB_API int sgb_step_loss_bwd(const float* pos, int64_t ldp, int64_t n, const void* target_pos, int target_f64, const uint8_t* vmask,
+                      const int64_t* faces, int64_t nf, const void* target_fn, const uint8_t* fmask,
+                      const int32_t* inc_rowptr, const int32_t* inc, const double* out, const double* grads /* [2] */,
+                      float* dpos, int64_t lddpos, void* stream);
+SGB_API int sgb_lap_loss_fwd(const float* pos, int64_t ldp, int64_t n, const int32_t* rowptr, const sgb_edge_t* edges, float* diff /* [n,3] */,
+                     double* partials, double* out /* [1] */, void* stream);
+SGB_API int sgb_lap_loss_bwd(const float* diff, int64_t n, const int32_t* rowptr, const int32_t* rowptr_t, const sgb_edge_t* edges_t,
+                     const double* out, const double* grad /* [1] */, float* dpos, int64_t lddpos, void* stream);
 
 #ifdef __cplusplus
 }

@@ -32,6 +32,9 @@ SIGNATURES = {
     "sgb_spmm_stat_rows": (_i32, [_i64, _i32]),
     "sgb_spmm": (_i32, [_vp, _vp, _vp, _i32, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _f32, _f32, _vp, _i64, _f32,
                         _vp, _vp, _i64, _vp, _vp]),
+    "sgb_spmm_halo": (_i32, [_vp, _vp, _vp, _i32, _vp, _i64, _i64, _i32, _vp, _i64, _i64, _vp, _vp, _vp, _f32, _f32, _vp, _i64, _f32,
+                             _vp, _vp, _i64, _vp, _vp]),
+    "sgb_gather_rows": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
     "sgb_gemm_stat_rows": (_i32, [_i64]),
     "sgb_gemm_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "sgb_gemm": (_i32, [_i32, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _i32,
@@ -48,6 +51,13 @@ SIGNATURES = {
     "sgb_bn_bwd_finalize": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp]),
     "sgb_bn_act_bwd_apply": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _i32,
                                     _vp, _i64, _vp]),
+    "sgb_loss_partial_rows": (_i32, []),
+    "sgb_incidence_build_workspace_bytes": (_sz, [_i64, _i64]),
+    "sgb_incidence_build": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "sgb_step_loss_fwd": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sgb_step_loss_bwd": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "sgb_lap_loss_fwd": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sgb_lap_loss_bwd": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

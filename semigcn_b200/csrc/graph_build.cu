@@ -166,6 +166,18 @@ __global__ void k_dis(const int32_t* __restrict__ deg, int64_t n, int mode, floa
     }
 }
 
+// exclusive scan of cnt[0..n) -> rowptr[0..n] (rowptr[n] = total); tsum: ceil(n / kScanTile) + 1 ints of scratch
+int exclusive_scan_i32(const int32_t* cnt, int64_t n, int32_t* tsum, int32_t* rowptr, cudaStream_t stream) {
+    const int ntiles = (int)ceil_div(n, kScanTile);
+    k_tile_sums<<<ntiles, kScanThreads, 0, stream>>>(cnt, n, tsum);
+    SGB_CHECK_LAUNCH("k_tile_sums");
+    k_scan_tile_sums<<<1, kScanThreads, 0, stream>>>(tsum, ntiles);
+    SGB_CHECK_LAUNCH("k_scan_tile_sums");
+    k_tile_scan<<<ntiles, kScanThreads, 0, stream>>>(cnt, n, tsum, rowptr);
+    SGB_CHECK_LAUNCH("k_tile_scan");
+    return SGB_OK;
+}
+
 struct BuildWs {
     int32_t *cnt, *cursor, *deg, *tmp, *tsum;
     size_t bytes;
@@ -219,17 +231,14 @@ extern "C" int sgb_graph_build(const int64_t* edge_index, int64_t nnz, int64_t n
     const int threads = 256;
     int egrid = (int)min64(ceil_div(nnz > 0 ? nnz : 1, threads), (int64_t)num_sms() * 16);
     int ngrid = (int)min64(ceil_div(n, threads), (int64_t)num_sms() * 16);
-    int ntiles = (int)ceil_div(n, kScanTile);
     if (nnz > 0) {
         k_count<<<egrid, threads, 0, stream>>>(edge_index, nnz, n, mode, transpose, w.cnt, w.deg, perm, err_flag);
         SGB_CHECK_LAUNCH("k_count");
     }
-    k_tile_sums<<<ntiles, kScanThreads, 0, stream>>>(w.cnt, n, w.tsum);
-    SGB_CHECK_LAUNCH("k_tile_sums");
-    k_scan_tile_sums<<<1, kScanThreads, 0, stream>>>(w.tsum, ntiles);
-    SGB_CHECK_LAUNCH("k_scan_tile_sums");
-    k_tile_scan<<<ntiles, kScanThreads, 0, stream>>>(w.cnt, n, w.tsum, rowptr);
-    SGB_CHECK_LAUNCH("k_tile_scan");
+    {
+        int rc = exclusive_scan_i32(w.cnt, n, w.tsum, rowptr, stream);
+        if (rc != SGB_OK) return rc;
+    }
     if (nnz > 0) {
         k_fill<<<egrid, threads, 0, stream>>>(edge_index, nnz, n, transpose, rowptr, w.cursor, w.tmp);
         SGB_CHECK_LAUNCH("k_fill");

@@ -63,6 +63,9 @@ struct SpmmArgs {
     float* y;
     int64_t ldy;
     float* stat_partials;
+    const float* xg;                  // ghost rows (vertex-partitioned mode): neighbour ids >= split read xg[(id - split)]
+    int64_t ldxg;
+    int32_t split;                    // INT32_MAX when there are no ghost rows
     int strided;                      // 1: CTA b takes chunks b, b+grid, ... (co-resident CTAs sweep one window of X -> L2 reuse)
 };
 
@@ -199,7 +202,8 @@ __global__ void __launch_bounds__(kSpmmThreads, (VEC == 4) ? SGB_SPMM_MINB : 3) 
                             if (r + b < ke) {
                                 const int2 ed = fetch_edge(r + b);
                                 w[b] = __int_as_float(ed.y);
-                                const float* xr = xl + (int64_t)ed.x * a.ldx;
+                                // owned rows live in x, halo (ghost) rows of the partitioned mode in xg
+                            const float* xr = ed.x < a.split ? xl + (int64_t)ed.x * a.ldx : a.xg + ch[0] + (int64_t)(ed.x - a.split) * a.ldxg;
     #pragma unroll
                                 for (int t = 0; t < ITERS; ++t)
                                     if (act[t]) xv[b][t].load(xr + t * LPV * VEC);
@@ -354,6 +358,15 @@ extern "C" int sgb_spmm(const int32_t* rowptr, const sgb_edge_t* edges, const fl
                         const float* in_mean, const float* in_scale, const float* in_shift, float slope,
                         float alpha, const float* addend, int64_t ld_addend, float beta,
                         const float* bias, float* y, int64_t ldy, float* stat_partials, void* stream_) {
+    return sgb_spmm_halo(rowptr, edges, dis, mode, x, ldx, n, c, nullptr, 0, n, in_mean, in_scale, in_shift, slope, alpha, addend, ld_addend,
+                         beta, bias, y, ldy, stat_partials, stream_);
+}
+
+extern "C" int sgb_spmm_halo(const int32_t* rowptr, const sgb_edge_t* edges, const float* dis, int mode,
+                             const float* x, int64_t ldx, int64_t n, int c, const float* x_ghost, int64_t ld_ghost, int64_t n_split,
+                             const float* in_mean, const float* in_scale, const float* in_shift, float slope,
+                             float alpha, const float* addend, int64_t ld_addend, float beta,
+                             const float* bias, float* y, int64_t ldy, float* stat_partials, void* stream_) {
     using namespace sgb;
     cudaStream_t stream = (cudaStream_t)stream_;
     SGB_CHECK_ARG(n >= 0 && c > 0, "sgb_spmm: bad shape n=%lld c=%d", (long long)n, c);
@@ -364,9 +377,10 @@ extern "C" int sgb_spmm(const int32_t* rowptr, const sgb_edge_t* edges, const fl
     SGB_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr) && (in_scale == nullptr) == (in_mean == nullptr),
                   "sgb_spmm: in_mean / in_scale / in_shift must come together");
     SGB_CHECK_ARG(x != y, "sgb_spmm: in-place aggregation is not supported");
+    SGB_CHECK_ARG(!x_ghost || (ld_ghost >= c && n_split >= 0 && n_split < (int64_t)0x7fffffff), "sgb_spmm_halo: bad ghost block");
     if (n == 0) return SGB_OK;
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-    bool aligned = al16(x) && al16(y) && ldx % 4 == 0 && ldy % 4 == 0 && (!addend || (al16(addend) && ld_addend % 4 == 0)) &&
+    bool aligned = al16(x) && al16(y) && ldx % 4 == 0 && ldy % 4 == 0 && (!x_ghost || (al16(x_ghost) && ld_ghost % 4 == 0)) && (!addend || (al16(addend) && ld_addend % 4 == 0)) &&
                    (!bias || al16(bias)) && (!in_scale || (al16(in_scale) && al16(in_shift) && al16(in_mean)));
     SpmmCfg k = pick_cfg(c, aligned);
     int grid = spmm_grid(n, k);
@@ -377,7 +391,8 @@ extern "C" int sgb_spmm(const int32_t* rowptr, const sgb_edge_t* edges, const fl
             SGB_CUDA(cudaMemsetAsync(stat_partials + (size_t)grid * 3 * c, 0, (size_t)(rows - grid) * 3 * c * sizeof(float), stream));
     }
     static const int sched = [] { const char* e = getenv("SGB_SPMM_SCHED"); return e ? atoi(e) : 1; }();
-    SpmmArgs a{rowptr, reinterpret_cast<const int2*>(edges), dis, mode, x, ldx, n, c, in_mean, in_scale, in_shift, slope, alpha, addend, ld_addend, beta, bias, y, ldy, stat_partials, sched};
+    SpmmArgs a{rowptr, reinterpret_cast<const int2*>(edges), dis, mode, x, ldx, n, c, in_mean, in_scale, in_shift, slope, alpha, addend, ld_addend, beta, bias, y, ldy, stat_partials,
+               x_ghost, ld_ghost, x_ghost ? (int32_t)n_split : (int32_t)0x7fffffff, sched};
     const bool pro = in_scale != nullptr, st = stat_partials != nullptr;
 #define SGB_SPMM_CASE(L, V, I)                                                                  \
     if (k.lpv == L && k.vec == V && k.iters == I) {                                             \
@@ -400,4 +415,37 @@ extern "C" int sgb_spmm(const int32_t* rowptr, const sgb_edge_t* edges, const fl
 #undef SGB_SPMM_CASE
     set_error("sgb_spmm: no kernel configuration for c=%d", c);
     return SGB_ENOTSUP;
+}
+
+// ---------------- row gather (halo pack): out[k, :] = x[idx[k], :] ----------------
+namespace sgb {
+template <int VEC>
+__global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ x, int64_t ldx, const int32_t* __restrict__ idx, int64_t count,
+                                                     int c, float* __restrict__ out, int64_t ldo) {
+    const int per_row = (c + VEC - 1) / VEC;
+    const int64_t total = count * per_row;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = i / per_row;
+        const int ch = (int)(i % per_row) * VEC;
+        const int64_t r = idx[k];
+        if (VEC == 4) st4(out + k * ldo + ch, ldg4(x + r * ldx + ch));
+        else out[k * ldo + ch] = __ldg(x + r * ldx + ch);
+    }
+}
+}  // namespace sgb
+
+extern "C" int sgb_gather_rows(const float* x, int64_t ldx, const int32_t* idx, int64_t count, int c, float* out, int64_t ldo, void* stream_) {
+    using namespace sgb;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SGB_CHECK_ARG(count >= 0 && c > 0 && ldx >= c && ldo >= c, "sgb_gather_rows: bad shape");
+    if (count == 0) return SGB_OK;
+    SGB_CHECK_ARG(x && idx && out, "sgb_gather_rows: null pointer");
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const bool vec = c % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && al16(x) && al16(out);
+    const int64_t total = count * (vec ? c / 4 : c);
+    const int grid = (int)min64(ceil_div(total, 256), (int64_t)num_sms() * 16);
+    if (vec) k_gather_rows<4><<<grid, 256, 0, stream>>>(x, ldx, idx, count, c, out, ldo);
+    else k_gather_rows<1><<<grid, 256, 0, stream>>>(x, ldx, idx, count, c, out, ldo);
+    SGB_CHECK_LAUNCH("k_gather_rows");
+    return SGB_OK;
 }

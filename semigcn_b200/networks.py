@@ -22,6 +22,7 @@ class SingleScaleGCN(nn.Module):
     def __init__(self, device, activation: str = "lrelu", skip: bool = False, conv: str = "chebconv", widths=None):
         super().__init__()
         self.device, self.skip = device, skip
+        self.comm = None        # set to a semigcn_b200.dist communicator in the vertex-partitioned mode
         h = list(widths) if widths is not None else list(SGCN_WIDTHS)
         self.h = h
         act = {"relu": nn.ReLU(), "lrelu": nn.LeakyReLU()}[activation]
@@ -45,6 +46,8 @@ class SingleScaleGCN(nn.Module):
     def forward(self, data, dm=None):
         z1, x_pos, edge_index = data.z1.to(self.device), data.x_pos.to(self.device), data.edge_index.to(self.device)
         z_min, z_max = torch.min(z1, dim=0, keepdim=True)[0], torch.max(z1, dim=0, keepdim=True)[0]
+        if self.comm is not None:           # bounding box of the WHOLE mesh (util/networks.py:67-68)
+            z_min, z_max = self.comm.all_reduce_min(z_min.clone()), self.comm.all_reduce_max(z_max.clone())
         z_sc = torch.max(z_max - z_min)
         zc = (z_min + z_max) * 0.5
         z1 = (z1 - zc) / z_sc

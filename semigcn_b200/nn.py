@@ -193,7 +193,8 @@ class ConvBlockFn(torch.autograd.Function):
                     momentum = 1.0 / float(bn.num_batches_tracked)
             rm = bn.running_mean if bn.track_running_stats else None
             rv = bn.running_var if bn.track_running_stats else None
-            mean, invstd, scale, shift = ops.bn_finalize(partials, y.shape[0], gamma, beta, bn.eps, momentum, rm, rv)
+            mean, invstd, scale, shift = ops.bn_finalize(partials, graph.n_global, gamma, beta, bn.eps, momentum, rm, rv,
+                                                         comm=graph.comm)
         else:
             mean, invstd, scale, shift = ops.eval_affine(bn.running_mean, bn.running_var, gamma, beta, bn.eps)
         z = ops.bn_act_apply(y, mean, scale, shift, cfg.slope)
@@ -215,7 +216,8 @@ class ConvBlockFn(torch.autograd.Function):
         else:
             saved_ops = saved[nw:-5]
             y, scale, shift, mean, invstd = saved[-5:]
-            dy, dgamma, dbeta = ops.bn_act_bwd(dz, y, scale, shift, mean, invstd, cfg.slope, ctx.bn_mode == 2)
+            dy, dgamma, dbeta = ops.bn_act_bwd(dz, y, scale, shift, mean, invstd, cfg.slope, ctx.bn_mode == 2,
+                                               comm=graph.comm, n_global=graph.n_global)
             if not ctx.has_affine:
                 dgamma = dbeta = None
         need_x = ctx.needs_input_grad[0]

@@ -51,6 +51,8 @@ class MeshGraph:
         dev = ei.device
         nnz, n = int(ei.shape[1]), int(num_nodes)
         self.n, self.nnz, self.mode, self.device = n, nnz, mode, dev
+        # vertex-partitioned mode (semigcn_b200/dist.py) overrides these three
+        self.halo, self.comm, self.n_global = None, None, n
         wsb = lib.sgb_graph_build_workspace_bytes(nnz, n)
         ws = _ws(wsb, dev)
         err = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -82,6 +84,7 @@ class MeshGraph:
 
 
 _GRAPH_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_GRAPH_CACHE_PINNED: set = set()         # partitioned operators registered by dist.register_partition: never evicted
 _GRAPH_CACHE_MAX = 16
 
 
@@ -96,13 +99,17 @@ def graph_for(edge_index: Tensor, num_nodes: int, mode: int) -> MeshGraph:
         return hit[0]
     g = MeshGraph(edge_index, num_nodes, mode)
     _GRAPH_CACHE[key] = (g, edge_index)      # keep the tensor alive so the pointer cannot be recycled
-    while len(_GRAPH_CACHE) > _GRAPH_CACHE_MAX:
-        _GRAPH_CACHE.popitem(last=False)
+    while len(_GRAPH_CACHE) > _GRAPH_CACHE_MAX + len(_GRAPH_CACHE_PINNED):
+        victim = next((k for k in _GRAPH_CACHE if k not in _GRAPH_CACHE_PINNED), None)
+        if victim is None:
+            break
+        del _GRAPH_CACHE[victim]
     return g
 
 
 def clear_graph_cache() -> None:
     _GRAPH_CACHE.clear()
+    _GRAPH_CACHE_PINNED.clear()
 
 
 # ----------------------------------------------------------------------------------------
@@ -118,6 +125,8 @@ def spmm(g: MeshGraph, x: Tensor, transpose: bool = False, in_affine: Affine = N
     if n != g.n:
         raise SgbError(f"x has {n} rows but the graph has {g.n} vertices")
     y = out if out is not None else torch.empty((n, c), dtype=torch.float32, device=x.device)
+    # partitioned mode: fetch the halo rows of x from their owners (gather -> all-to-all), then gather locally
+    xg = g.halo.exchange(x) if g.halo is not None else None
     if addend is not None:
         addend = _f32c(addend, "addend")
     partials = None
@@ -130,10 +139,11 @@ def spmm(g: MeshGraph, x: Tensor, transpose: bool = False, in_affine: Affine = N
     sp = _prof.span(f"spmm_c{c}", 4.0 * (2 * n * c + nnz_eff + 2 * n + 1 + (n * c if addend is not None else 0)),
                     2.0 * nnz_eff * c) if _prof.ACTIVE is not None else None
     with torch.cuda.device(x.device):
-        check(lib.sgb_spmm(ptr(rowptr), ptr(edges), ptr(g.dis), g.mode, ptr(x), x.stride(0), n, c,
-                           ptr(mu), ptr(sc), ptr(sh), float(slope), float(alpha), ptr(addend),
-                           addend.stride(0) if addend is not None else 0, float(beta), ptr(bias),
-                           ptr(y), y.stride(0), ptr(partials), stream_ptr(x.device)), "sgb_spmm")
+        check(lib.sgb_spmm_halo(ptr(rowptr), ptr(edges), ptr(g.dis), g.mode, ptr(x), x.stride(0), n, c,
+                                ptr(xg), xg.stride(0) if xg is not None else 0, n,
+                                ptr(mu), ptr(sc), ptr(sh), float(slope), float(alpha), ptr(addend),
+                                addend.stride(0) if addend is not None else 0, float(beta), ptr(bias),
+                                ptr(y), y.stride(0), ptr(partials), stream_ptr(x.device)), "sgb_spmm")
     if sp is not None:
         sp.close()
     L.count(1)
@@ -220,9 +230,25 @@ def col_stats(y: Tensor) -> Tensor:
     return partials
 
 
-def bn_finalize(partials: Tensor, count: int, gamma: Optional[Tensor], beta: Optional[Tensor], eps: float,
-                momentum: float, running_mean: Optional[Tensor], running_var: Optional[Tensor]):
+def gather_rows(x: Tensor, idx: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """out[k, :] = x[idx[k], :] (idx int32)."""
     lib = L.load()
+    require_cuda(x, idx)
+    x = _f32c(x, "x")
+    count, c = int(idx.numel()), int(x.shape[1])
+    o = out if out is not None else torch.empty((count, c), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.sgb_gather_rows(ptr(x), x.stride(0), ptr(idx), count, c, ptr(o), o.stride(0), stream_ptr(x.device)), "sgb_gather_rows")
+    L.count(1)
+    return o
+
+
+def bn_finalize(partials: Tensor, count: int, gamma: Optional[Tensor], beta: Optional[Tensor], eps: float,
+                momentum: float, running_mean: Optional[Tensor], running_var: Optional[Tensor], comm=None):
+    lib = L.load()
+    if comm is not None:
+        # SyncBN: every rank merges the same (count, mean, M2) rows in the same order -> identical statistics
+        partials = comm.all_gather_cat(partials.contiguous())
     rows, _, c = partials.shape
     dev = partials.device
     st = torch.empty((4, c), dtype=torch.float32, device=dev)     # mean, invstd, scale, shift
@@ -250,7 +276,7 @@ def bn_act_apply(y: Tensor, mean: Tensor, scale: Tensor, shift: Tensor, slope: f
 
 
 def bn_act_bwd(dz: Tensor, y: Tensor, scale: Tensor, shift: Tensor, mean: Optional[Tensor], invstd: Optional[Tensor],
-               slope: float, training: bool, want_param_grads: bool = True):
+               slope: float, training: bool, want_param_grads: bool = True, comm=None, n_global: Optional[int] = None):
     """dY (and dgamma, dbeta) of Z = lrelu(BN(Y)) given dZ."""
     lib = L.load()
     dz, y = _f32c(dz, "dz"), _f32c(y, "y")
@@ -274,6 +300,11 @@ def bn_act_bwd(dz: Tensor, y: Tensor, scale: Tensor, shift: Tensor, mean: Option
             check(lib.sgb_bn_bwd_finalize(ptr(partials), rows, c, ptr(sums), ptr(dgamma), ptr(dbeta), 0, stream_ptr(dev)),
                   "sgb_bn_bwd_finalize")
             L.count(2)
+            if comm is not None and training:
+                # dgamma / dbeta stay LOCAL contributions (summed with the other parameter gradients later);
+                # the apply pass needs the GLOBAL sums over all n_global vertices: the kernel divides by the
+                # local row count m, hence the m / n_global factor
+                sums = comm.all_reduce_sum(sums.clone()) * (float(m) / float(n_global))
         check(lib.sgb_bn_act_bwd_apply(ptr(dz), dz.stride(0), ptr(y), y.stride(0), m, c, ptr(scale), ptr(shift), ptr(mean),
                                        ptr(invstd), ptr(sums), float(slope), 1 if training else 0, ptr(dy), dy.stride(0),
                                        stream_ptr(dev)), "sgb_bn_act_bwd_apply")

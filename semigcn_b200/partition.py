@@ -1,0 +1,100 @@
+"""Vertex partition of one large mesh graph over P ranks (BASELINE.json configs[3]).
+
+The reference is single-device (sgcn.py:77) and its ``Mesh`` cannot even hold such a mesh
+(dense N x N, util/mesh.py:267), so there is no reference counterpart: this is the scaling layer
+around the drop-in convs.  Pure index arithmetic on torch tensors (CPU or CUDA), no communication:
+
+  * ranks own contiguous vertex ranges of the given numbering (mesh generators / a prior BFS or
+    space-filling-curve renumbering give the locality; cut quality = how few edges cross ranges);
+  * a rank keeps every directed edge with an owned endpoint; non-owned endpoints become ghost
+    vertices, numbered after the owned ones in ascending global id (= grouped by owner);
+  * ``send_idx`` lists, per destination rank, the owned vertices that rank needs as ghosts; by
+    construction rank q's ghost block from rank r has the same order as r's send block to q.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+
+def vertex_ranges(n: int, world: int) -> List[Tuple[int, int]]:
+    """Balanced contiguous ranges [lo, hi) (first n % world ranks get one extra vertex)."""
+    base, extra = divmod(int(n), int(world))
+    out, lo = [], 0
+    for r in range(world):
+        hi = lo + base + (1 if r < extra else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+@dataclass
+class PartitionPlan:
+    rank: int
+    world: int
+    n_global: int
+    lo: int
+    hi: int
+    ghost_gid: Tensor            # int64 [n_ghost], ascending global ids (grouped by owner rank)
+    send_idx: Tensor             # int32 [n_send], LOCAL owned ids grouped by destination rank, ascending inside a group
+    send_counts: List[int]       # rows sent to each rank
+    recv_counts: List[int]       # ghost rows received from each rank
+    edge_index: Tensor           # int64 [2, m] local ids: owned in [0, n_own), ghosts in [n_own, n_own + n_ghost)
+
+    @property
+    def n_own(self) -> int:
+        return self.hi - self.lo
+
+    @property
+    def n_ghost(self) -> int:
+        return int(self.ghost_gid.numel())
+
+    @property
+    def n_local(self) -> int:
+        return self.n_own + self.n_ghost
+
+    def to(self, device) -> "PartitionPlan":
+        return PartitionPlan(self.rank, self.world, self.n_global, self.lo, self.hi, self.ghost_gid.to(device),
+                             self.send_idx.to(device), list(self.send_counts), list(self.recv_counts), self.edge_index.to(device))
+
+
+def build_plan(edge_index: Tensor, n: int, rank: int, world: int,
+               ranges: Optional[Sequence[Tuple[int, int]]] = None) -> PartitionPlan:
+    """Plan of ``rank`` from the GLOBAL ``edge_index`` [2, nnz] (every rank holds it in the synthetic benchmarks;
+    a loader that only sees its own edges would exchange the ghost lists instead)."""
+    ranges = list(ranges) if ranges is not None else vertex_ranges(n, world)
+    lo, hi = ranges[rank]
+    row, col = edge_index[0], edge_index[1]
+    own_r = (row >= lo) & (row < hi)
+    own_c = (col >= lo) & (col < hi)
+    keep = own_r | own_c
+    r_k, c_k = row[keep], col[keep]
+    ghosts = torch.unique(torch.cat([r_k[~own_r[keep]], c_k[~own_c[keep]]]))          # sorted ascending
+    n_own = hi - lo
+
+    def to_local(v: Tensor) -> Tensor:
+        owned = (v >= lo) & (v < hi)
+        g_pos = torch.searchsorted(ghosts, v.clamp(min=0))
+        g_pos = g_pos.clamp(max=max(int(ghosts.numel()) - 1, 0))
+        return torch.where(owned, v - lo, n_own + g_pos)
+
+    ei_local = torch.stack([to_local(r_k), to_local(c_k)]).contiguous()
+    bounds = torch.tensor([b for (b, _) in ranges] + [ranges[-1][1]], dtype=torch.int64, device=edge_index.device)
+    owner_of_ghost = torch.searchsorted(bounds, ghosts, right=True) - 1
+    recv_counts = torch.bincount(owner_of_ghost, minlength=world).tolist() if ghosts.numel() else [0] * world
+    send_parts, send_counts = [], []
+    for q in range(world):
+        if q == rank:
+            send_counts.append(0)
+            continue
+        qlo, qhi = ranges[q]
+        q_r = (row >= qlo) & (row < qhi)
+        q_c = (col >= qlo) & (col < qhi)
+        mine = torch.unique(torch.cat([row[own_r & q_c], col[own_c & q_r]]))           # owned vertices adjacent to q's
+        send_parts.append(mine - lo)
+        send_counts.append(int(mine.numel()))
+    send_idx = (torch.cat(send_parts) if send_parts else torch.zeros(0, dtype=torch.int64, device=edge_index.device)).to(torch.int32)
+    return PartitionPlan(rank, world, int(n), lo, hi, ghosts, send_idx, send_counts, [int(c) for c in recv_counts], ei_local)
