@@ -19,10 +19,21 @@
 // HBM roofline: algorithmic bytes = 2*N*C*4 + (nnz + 2N + 1)*4.
 #include "common.cuh"
 #include <stdlib.h>
+#include <type_traits>
 
 namespace sgb {
 
-constexpr int kSpmmThreads = 256;
+#ifndef SGB_SPMM_MINB2
+#define SGB_SPMM_MINB2 4          // resident CTAs per SM for the two-float4-per-lane configurations
+#endif
+#ifndef SGB_SPMM_NB2
+#define SGB_SPMM_NB2 6
+#endif
+#ifndef SGB_SPMM_ITERS
+#define SGB_SPMM_ITERS 2
+#endif
+constexpr int kSpmmThreads = 128;                       // 4 autonomous warps per CTA
+constexpr int kSpmmWarps = kSpmmThreads / 32;
 
 template <int VEC>
 struct Vec;
@@ -66,13 +77,15 @@ struct SpmmArgs {
     const float* xg;                  // ghost rows (vertex-partitioned mode): neighbour ids >= split read xg[(id - split)]
     int64_t ldxg;
     int32_t split;                    // INT32_MAX when there are no ghost rows
-    int strided;                      // 1: CTA b takes chunks b, b+grid, ... (co-resident CTAs sweep one window of X -> L2 reuse)
 };
 
-// vertices per chunk / staged edges per chunk as a function of the sub-warp width: every sub-warp of the CTA
-// gets at least one vertex per chunk
-__host__ __device__ constexpr int spmm_vpc(int lpv) { return (kSpmmThreads / lpv) > 64 ? (kSpmmThreads / lpv) : 64; }
-__host__ __device__ constexpr int spmm_ecap(int lpv) { return spmm_vpc(lpv) * 12 < 1536 ? spmm_vpc(lpv) * 12 : 1536; }
+// A warp owns "runs" of VPW consecutive vertices; run r of the grid goes to warp (r mod total warps), so the
+// co-resident warps sweep one window of X together (neighbour rows are served by L1/L2, DRAM sees X once) and the
+// warps of a CTA cover 4 adjacent runs (L1 reuse along a mesh row).
+__host__ __device__ constexpr int spmm_vpw(int) { return 32; }                          // vertices per run
+__host__ __device__ constexpr int spmm_ecap(int lpv) { return spmm_vpw(lpv) * 8; }      // staged edges per run (mean degree 6)
+__host__ __device__ constexpr int kSpmmNB(int vec, int iters) { return vec * iters >= 8 ? SGB_SPMM_NB2 : 8; }
+constexpr int kSpmmSlack = 8;                           // >= NB: a round may read up to NB - 1 slots past the staged slice
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
@@ -84,69 +97,75 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-// Pipeline per CTA: while chunk i is being gathered, the (col, weight) slice of chunk i+1 and the row
-// pointers of chunk i+2 are already in flight (cp.async into the other half of the double buffer).
-// Per vertex there is exactly ONE round of dependent global loads for degree <= NB: the neighbour rows
-// and the self row are all issued together (indices and weights come from shared memory).
-template <int LPV, int VEC, int ITERS, bool PRO, bool STATS>
-#ifndef SGB_SPMM_MINB
-#define SGB_SPMM_MINB 2
-#endif
-__global__ void __launch_bounds__(kSpmmThreads, (VEC == 4) ? SGB_SPMM_MINB : 3) k_spmm(const SpmmArgs a) {
-#ifndef SGB_SPMM_NB
-#define SGB_SPMM_NB 6
-#endif
-    constexpr int NB = (VEC * ITERS >= 8) ? SGB_SPMM_NB : 8;  // neighbour rows in flight per round (register budget)
+// Warp-autonomous pipeline (no CTA barrier in the main loop): while run i is gathered, the (col, weight) slice
+// of run i+1 and the row pointers of run i+2 are in flight (cp.async into the warp's private double buffer).
+// Per vertex there is ONE round of dependent global loads for degree <= NB: the NB neighbour rows and the self
+// row are issued together, branch-free -- slots past the row's degree re-read its last neighbour with weight 0
+// (acc + 0*x is exact), so the gather code is straight-line and the loads of a whole round are in flight at once.
+// FULL: c is a multiple of the pass width (every lane active, no channel predicates).
+template <int LPV, int VEC, int ITERS, bool FULL, bool HALO, bool PRO, bool STATS>
+__global__ void __launch_bounds__(kSpmmThreads, (VEC * ITERS >= 8) ? (STATS ? SGB_SPMM_MINB2 - 1 : SGB_SPMM_MINB2) : 6) k_spmm(const SpmmArgs a) {
+    constexpr int NB = kSpmmNB(VEC, ITERS);                 // neighbour rows in flight per round (register budget)
     constexpr int CH = LPV * VEC * ITERS;                   // channels per pass
-    constexpr int GROUPS = kSpmmThreads / LPV;              // sub-warps per CTA
-    constexpr int VPC = spmm_vpc(LPV);
+    constexpr int SUB = 32 / LPV;                           // sub-warps (vertices in lock-step) per warp
+    constexpr int VPW = spmm_vpw(LPV);
     constexpr int ECAP = spmm_ecap(LPV);
-    const int l = threadIdx.x & (LPV - 1);
-    const int grp = threadIdx.x / LPV;
-    __shared__ float red[STATS ? 2 : 1][STATS ? kSpmmThreads * VEC * ITERS : 1];
-    __shared__ float redn[STATS ? kSpmmThreads : 1];
-    __shared__ int s_rowptr[2][VPC + 1];
-    __shared__ int2 s_edge[2][ECAP];
-    const int64_t nchunks = (a.n + VPC - 1) / VPC;
-    // chunk schedule: chunk(i) = cfirst + i * cstep for i < ccount
-    const int64_t cpc = (nchunks + gridDim.x - 1) / gridDim.x;
-    const int64_t cstep = a.strided ? (int64_t)gridDim.x : 1;
-    const int64_t cfirst = a.strided ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * cpc;
-    const int64_t ccount = a.strided ? (nchunks > blockIdx.x ? (nchunks - 1 - blockIdx.x) / gridDim.x + 1 : 0)
-                                     : (min64(nchunks, cfirst + cpc) > cfirst ? min64(nchunks, cfirst + cpc) - cfirst : 0);
+    constexpr int STAT_FLOATS = STATS ? 2 * kSpmmThreads * VEC * ITERS + kSpmmThreads : 0;
+    constexpr int EBUF = ECAP + kSpmmSlack;                 // int2 slots per edge buffer
+    constexpr int STAGE_INTS = kSpmmWarps * 2 * ((VPW + 2) + 2 * EBUF);
+    constexpr int SMEM_INTS = STAGE_INTS > STAT_FLOATS ? STAGE_INTS : STAT_FLOATS;
+    __shared__ __align__(16) int smem_raw[SMEM_INTS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int l = lane & (LPV - 1);
+    const int sub = lane / LPV;
+    // warp-private staging: [2][ECAP] int2 edges, then [2][VPW + 2] row pointers
+    int2* const w_edge = reinterpret_cast<int2*>(smem_raw) + (size_t)warp * 2 * EBUF;
+    int* const w_rp = smem_raw + kSpmmWarps * 4 * EBUF + warp * 2 * (VPW + 2);
+    const uint32_t ldx_b = (uint32_t)a.ldx * 4u, ldxg_b = (uint32_t)a.ldxg * 4u;     // row strides in bytes (host checks they fit)
+    auto row_of = [](const float* base, uint32_t row, uint32_t stride_b) {           // one IMAD.WIDE.U32
+        return reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + (uint64_t)row * stride_b);
+    };
 
-    auto stage_rowptr = [&](int64_t ci, int buf) {         // async; ci (schedule position) may be past the end
-        if (ci < ccount) {
-            const int64_t v0 = (cfirst + ci * cstep) * VPC;
-            const int nv = (int)min64(VPC, a.n - v0);
-            for (int i = threadIdx.x; i <= nv; i += kSpmmThreads) cp_async4(&s_rowptr[buf][i], a.rowptr + v0 + i);
+    const int64_t nruns = (a.n + VPW - 1) / VPW;
+    const int64_t gw = (int64_t)blockIdx.x * kSpmmWarps + warp;
+    const int64_t tw = (int64_t)gridDim.x * kSpmmWarps;
+    const int64_t rcount = nruns > gw ? (nruns - 1 - gw) / tw + 1 : 0;
+
+    auto stage_rowptr = [&](int64_t ri, int buf) {         // async; ri (schedule position) may be past the end
+        if (ri < rcount) {
+            const int64_t v0 = (gw + ri * tw) * VPW;
+            const int nv = (int)min64(VPW, a.n - v0);
+            for (int i = lane; i <= nv; i += 32) cp_async4(&w_rp[buf * (VPW + 2) + i], a.rowptr + v0 + i);
         }
     };
-    auto stage_edges = [&](int64_t ci, int buf) {          // needs s_rowptr[buf] of that chunk to be visible
-        if (ci < ccount) {
-            const int64_t v0 = (cfirst + ci * cstep) * VPC;
-            const int nv = (int)min64(VPC, a.n - v0);
-            const int e0 = s_rowptr[buf][0], ne = s_rowptr[buf][nv] - e0;
+    auto stage_edges = [&](int64_t ri, int buf) {          // needs the row pointers of that run to be visible
+        if (ri < rcount) {
+            const int64_t v0 = (gw + ri * tw) * VPW;
+            const int nv = (int)min64(VPW, a.n - v0);
+            const int e0 = w_rp[buf * (VPW + 2)], ne = w_rp[buf * (VPW + 2) + nv] - e0;
             if (ne <= ECAP)
-                for (int i = threadIdx.x; i < ne; i += kSpmmThreads) cp_async8(&s_edge[buf][i], a.edges + e0 + i);
+                for (int i = lane; i < ne; i += 32) cp_async8(&w_edge[buf * EBUF + i], a.edges + e0 + i);
         }
     };
 
     for (int c0 = 0; c0 < a.c; c0 += CH) {
+        // every staged slot must always hold a valid vertex id: rounds read (and discard, weight 0) slots past a row's
+        // end.  (Per pass: the statistics merge of the previous pass reused this memory.)
+        for (int i = lane; i < 2 * EBUF; i += 32) w_edge[i] = make_int2(0, 0);
         int ch[ITERS];
         bool act[ITERS];
         Vec<VEC> mu[ITERS], sc[ITERS], sh[ITERS];
 #pragma unroll
         for (int t = 0; t < ITERS; ++t) {
             ch[t] = c0 + (t * LPV + l) * VEC;
-            act[t] = ch[t] < a.c;
+            act[t] = FULL || ch[t] < a.c;
 #pragma unroll
             for (int q = 0; q < VEC; ++q) { mu[t].v[q] = 0.f; sc[t].v[q] = 1.f; sh[t].v[q] = 0.f; }
-            if (act[t]) {
-                if (PRO) { mu[t].load(a.in_mean + ch[t]); sc[t].load(a.in_scale + ch[t]); sh[t].load(a.in_shift + ch[t]); }
-            }
+            if (PRO && a.in_scale && act[t]) { mu[t].load(a.in_mean + ch[t]); sc[t].load(a.in_scale + ch[t]); sh[t].load(a.in_shift + ch[t]); }
         }
-        const float* xl = a.x + ch[0];                       // this lane's first channel; iteration t adds t * LPV * VEC
+        // inactive lanes (c not a multiple of the pass width) gather channel 0 of their slot instead: harmless, never stored
+        const float* xl = a.x + (act[0] ? ch[0] : 0);
+        const float* xgl = HALO ? a.xg + (act[0] ? ch[0] : 0) : nullptr;
         // statistics: pivot-shifted sums per thread (pivot = first value seen), see common.cuh
         float s1[ITERS][VEC], s2[ITERS][VEC], pv[ITERS][VEC];
         float nseen = 0.f;
@@ -156,83 +175,87 @@ __global__ void __launch_bounds__(kSpmmThreads, (VEC == 4) ? SGB_SPMM_MINB : 3) 
             for (int q = 0; q < VEC; ++q) { s1[t][q] = 0.f; s2[t][q] = 0.f; pv[t][q] = 0.f; }
 
         // ---- pipeline prologue: rowptr(0) -> edges(0) + rowptr(1)
-        __syncthreads();
+        __syncwarp();
         stage_rowptr(0, 0);
         cp_async_commit_wait_all();
-        __syncthreads();
+        __syncwarp();
         stage_edges(0, 0);
         stage_rowptr(1, 1);
 
-        for (int64_t ci = 0; ci < ccount; ++ci) {
-            const int buf = (int)(ci & 1);
+        for (int64_t ri = 0; ri < rcount; ++ri) {
+            const int buf = (int)(ri & 1);
             cp_async_commit_wait_all();
-            __syncthreads();                                  // chunk's edges + next chunk's rowptr have landed; previous gather done
-            stage_edges(ci + 1, buf ^ 1);
-            // (rowptr of chunk ci+2 goes into the buffer this chunk is reading: issued after the gather below)
-            const int64_t v0 = (cfirst + ci * cstep) * VPC;
-            const int nv = (int)min64(VPC, a.n - v0);
-            const int e0 = s_rowptr[buf][0];
-            const bool staged = (s_rowptr[buf][nv] - e0) <= ECAP;
-            const int2* sedge = s_edge[buf];
-            const int* srp = s_rowptr[buf];
+            __syncwarp();                                     // this run's edges + next run's row pointers have landed
+            stage_edges(ri + 1, buf ^ 1);
+            const int64_t v0 = (gw + ri * tw) * VPW;
+            const int nv = (int)min64(VPW, a.n - v0);
+            const int* srp = w_rp + buf * (VPW + 2);
+            const int e0 = srp[0];
+            const bool staged = (srp[nv] - e0) <= ECAP;
+            const int2* sedge = w_edge + buf * EBUF;
 
-            // one instantiation per edge source (shared-memory slice, or global for chunks whose rows are too long to
-            // stage): a per-neighbour select between the two would turn into a branch and serialise the gathers
-            auto gather = [&](auto fetch_edge) {
-                for (int vi = grp; vi < nv; vi += GROUPS) {
+            // one instantiation per edge source (the warp's shared-memory slice, or global memory for runs whose
+            // rows are too long to stage)
+            auto gather = [&](auto staged_tag) {
+                constexpr bool STAGED = decltype(staged_tag)::value;
+#pragma unroll 1
+                for (int vi = sub; vi < nv; vi += SUB) {
                     const int kb = srp[vi] - e0, ke = srp[vi + 1] - e0;
                     const int64_t v = v0 + vi;
                     Vec<VEC> acc[ITERS], xself[ITERS];
                     float di = 0.f;
-    #pragma unroll
+#pragma unroll
                     for (int t = 0; t < ITERS; ++t)
-    #pragma unroll
+#pragma unroll
                         for (int q = 0; q < VEC; ++q) { acc[t].v[q] = 0.f; xself[t].v[q] = 0.f; }
                     if (a.mode != SGB_MODE_ADJ) {                 // the self row rides along with the first round of gathers
                         if (a.mode == SGB_MODE_GCN) di = __ldg(a.dis + v);
-    #pragma unroll
+                        const float* xs = row_of(xl, (uint32_t)v, ldx_b);
+#pragma unroll
                         for (int t = 0; t < ITERS; ++t)
-                            if (act[t]) xself[t].load(xl + v * a.ldx + t * LPV * VEC);
+                            if (t == 0 || act[t]) xself[t].load(xs + t * LPV * VEC);
                     }
+#pragma unroll 1
                     for (int r = kb; r < ke; r += NB) {
                         Vec<VEC> xv[NB][ITERS];
                         float w[NB];
-    #pragma unroll
+                        const int left = ke - r;
+#pragma unroll
                         for (int b = 0; b < NB; ++b) {
-                            if (r + b < ke) {
-                                const int2 ed = fetch_edge(r + b);
-                                w[b] = __int_as_float(ed.y);
-                                // owned rows live in x, halo (ghost) rows of the partitioned mode in xg
-                            const float* xr = ed.x < a.split ? xl + (int64_t)ed.x * a.ldx : a.xg + ch[0] + (int64_t)(ed.x - a.split) * a.ldxg;
-    #pragma unroll
-                                for (int t = 0; t < ITERS; ++t)
-                                    if (act[t]) xv[b][t].load(xr + t * LPV * VEC);
+                            // slots past the row's end: a valid (stale or next-row) vertex id with weight 0
+                            const int2 ed = STAGED ? sedge[r + b] : __ldg(a.edges + e0 + min(r + b, ke - 1));
+                            w[b] = (b < left) ? __int_as_float(ed.y) : 0.f;
+                            // owned rows live in x, halo (ghost) rows of the partitioned mode in xg
+                            const float* xr = (!HALO || ed.x < a.split) ? row_of(xl, (uint32_t)ed.x, ldx_b) : row_of(xgl, (uint32_t)(ed.x - a.split), ldxg_b);
+#pragma unroll
+                            for (int t = 0; t < ITERS; ++t) {
+                                if (t == 0 || act[t]) xv[b][t].load(xr + t * LPV * VEC);
+                                else {
+#pragma unroll
+                                    for (int q = 0; q < VEC; ++q) xv[b][t].v[q] = 0.f;
+                                }
                             }
                         }
-    #pragma unroll
+#pragma unroll
                         for (int b = 0; b < NB; ++b) {
-                            if (r + b < ke) {
-                                // msg = fl(w * x_j), acc = fl(acc + msg): PyG's message / aggregate op order (A.1 step 3)
-    #pragma unroll
-                                for (int t = 0; t < ITERS; ++t)
-                                    if (act[t]) {
-    #pragma unroll
-                                        for (int q = 0; q < VEC; ++q) {
-                                            float xx = xv[b][t].v[q];
-                                            if (PRO) xx = bn_lrelu(xx, mu[t].v[q], sc[t].v[q], sh[t].v[q], a.slope);
-                                            acc[t].v[q] = __fadd_rn(acc[t].v[q], __fmul_rn(w[b], xx));
-                                        }
-                                    }
-                            }
+                            // msg = fl(w * x_j), acc = fl(acc + msg): PyG's message / aggregate op order (A.1 step 3)
+#pragma unroll
+                            for (int t = 0; t < ITERS; ++t)
+#pragma unroll
+                                for (int q = 0; q < VEC; ++q) {
+                                    float xx = xv[b][t].v[q];
+                                    if (PRO) xx = bn_lrelu(xx, mu[t].v[q], sc[t].v[q], sh[t].v[q], a.slope);
+                                    acc[t].v[q] = __fadd_rn(acc[t].v[q], __fmul_rn(w[b], xx));
+                                }
                         }
                     }
                     const float wii = __fmul_rn(di, di);
-    #pragma unroll
+#pragma unroll
                     for (int t = 0; t < ITERS; ++t) {
                         if (!act[t]) continue;
                         Vec<VEC> out = acc[t];
                         if (a.mode != SGB_MODE_ADJ) {
-    #pragma unroll
+#pragma unroll
                             for (int q = 0; q < VEC; ++q) {
                                 float xx = xself[t].v[q];
                                 if (PRO) xx = bn_lrelu(xx, mu[t].v[q], sc[t].v[q], sh[t].v[q], a.slope);
@@ -246,22 +269,22 @@ __global__ void __launch_bounds__(kSpmmThreads, (VEC == 4) ? SGB_SPMM_MINB : 3) 
                         if (a.addend) {
                             Vec<VEC> ad;
                             ad.load(a.addend + v * a.ld_addend + ch[t]);
-    #pragma unroll
+#pragma unroll
                             for (int q = 0; q < VEC; ++q)
                                 out.v[q] = __fadd_rn(__fmul_rn(a.alpha, out.v[q]), __fmul_rn(a.beta, ad.v[q]));
                         } else if (a.alpha != 1.f) {
-    #pragma unroll
+#pragma unroll
                             for (int q = 0; q < VEC; ++q) out.v[q] = __fmul_rn(a.alpha, out.v[q]);
                         }
                         if (a.bias) {                             // L1-resident; not worth 4*ITERS registers across the gather loop
                             Vec<VEC> bs;
                             bs.load(a.bias + ch[t]);
-    #pragma unroll
+#pragma unroll
                             for (int q = 0; q < VEC; ++q) out.v[q] = __fadd_rn(out.v[q], bs.v[q]);
                         }
                         out.store(a.y + v * a.ldy + ch[t]);
                         if (STATS) {
-    #pragma unroll
+#pragma unroll
                             for (int q = 0; q < VEC; ++q) {
                                 if (nseen == 0.f) pv[t][q] = out.v[q];
                                 const float dv = out.v[q] - pv[t][q];
@@ -273,32 +296,34 @@ __global__ void __launch_bounds__(kSpmmThreads, (VEC == 4) ? SGB_SPMM_MINB : 3) 
                     nseen += 1.f;
                 }
             };
-#ifndef SGB_SPMM_BRANCH
-            gather([&](int k) { return staged ? sedge[k] : __ldg(a.edges + e0 + k); });
-#else
-            if (staged) gather([&](int k) { return sedge[k]; });
-            else gather([&](int k) { return __ldg(a.edges + e0 + k); });
-#endif
-            __syncthreads();                                  // everyone is done reading s_rowptr[buf]
-            stage_rowptr(ci + 2, buf);
+            if (staged) gather(std::true_type{});
+            else gather(std::false_type{});
+            __syncwarp();                                     // every lane is done reading this run's row pointers
+            stage_rowptr(ri + 2, buf);
         }
         cp_async_commit_wait_all();
         if (STATS) {   // fixed-order block merge (Chan) -> partials[blockIdx.x][3][c] = (count, mean, M2)
+            constexpr int GROUPS = kSpmmThreads / LPV;
+            float* red0 = reinterpret_cast<float*>(smem_raw);
+            float* red1 = red0 + kSpmmThreads * VEC * ITERS;
+            float* redn = red1 + kSpmmThreads * VEC * ITERS;
+            const int grp = threadIdx.x / LPV;
+            __syncthreads();                                  // all warps are done with their staging buffers
 #pragma unroll
             for (int t = 0; t < ITERS; ++t)
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) {
                     const int cl = (t * LPV + l) * VEC + q;     // channel within the pass
                     const Moments mo = from_shifted(nseen, pv[t][q], s1[t][q], s2[t][q]);
-                    red[0][grp * CH + cl] = mo.mean;
-                    red[STATS ? 1 : 0][grp * CH + cl] = mo.m2;
+                    red0[grp * CH + cl] = mo.mean;
+                    red1[grp * CH + cl] = mo.m2;
                 }
             if (l == 0) redn[grp] = nseen;
             __syncthreads();
             for (int cl = threadIdx.x; cl < CH; cl += kSpmmThreads) {
                 if (c0 + cl < a.c) {
                     Moments acc{0.f, 0.f, 0.f};
-                    for (int g = 0; g < GROUPS; ++g) acc = merge(acc, Moments{redn[g], red[0][g * CH + cl], red[STATS ? 1 : 0][g * CH + cl]});
+                    for (int g = 0; g < GROUPS; ++g) acc = merge(acc, Moments{redn[g], red0[g * CH + cl], red1[g * CH + cl]});
                     a.stat_partials[((int64_t)blockIdx.x * 3 + 0) * a.c + c0 + cl] = acc.n;
                     a.stat_partials[((int64_t)blockIdx.x * 3 + 1) * a.c + c0 + cl] = acc.mean;
                     a.stat_partials[((int64_t)blockIdx.x * 3 + 2) * a.c + c0 + cl] = acc.m2;
@@ -326,6 +351,12 @@ static SpmmCfg pick_cfg(int c, bool aligned) {
             while (p * 2 < lanes && p < 32) p <<= 1;
             k.lpv = p;
             k.iters = 2;
+            if (SGB_SPMM_ITERS == 1) {     // experiment: one float4 per lane (more warps per SM, more index instructions per byte)
+                p = 1;
+                while (p < lanes && p < 32) p <<= 1;
+                k.lpv = p;
+                k.iters = 1;
+            }
         }
     } else {
         k.vec = 1;
@@ -335,10 +366,11 @@ static SpmmCfg pick_cfg(int c, bool aligned) {
     return k;
 }
 
-static int spmm_grid(int64_t n, const SpmmCfg& k) {
-    int64_t need = ceil_div(n > 0 ? n : 1, spmm_vpc(k.lpv));
-    int per_sm = (k.vec == 4) ? SGB_SPMM_MINB : 3;
-    int64_t cap = (int64_t)num_sms() * per_sm;
+static int spmm_per_sm(const SpmmCfg& k, bool stats) { return (k.vec * k.iters >= 8) ? (stats ? SGB_SPMM_MINB2 - 1 : SGB_SPMM_MINB2) : 6; }
+
+static int spmm_grid(int64_t n, const SpmmCfg& k, bool stats) {
+    int64_t need = ceil_div(ceil_div(n > 0 ? n : 1, spmm_vpw(k.lpv)), kSpmmWarps);
+    int64_t cap = (int64_t)num_sms() * spmm_per_sm(k, stats);
     return (int)(need < cap ? need : cap);
 }
 
@@ -348,8 +380,8 @@ extern "C" int sgb_spmm_stat_rows(int64_t n, int c) {
     if (n < 0 || c <= 0) return 0;
     // alignment of x/y is not known here: the row count must not depend on it, so both
     // candidate configurations are sized and the larger grid is reported.
-    int g1 = sgb::spmm_grid(n, sgb::pick_cfg(c, true));
-    int g2 = sgb::spmm_grid(n, sgb::pick_cfg(c, false));
+    int g1 = sgb::spmm_grid(n, sgb::pick_cfg(c, true), true);
+    int g2 = sgb::spmm_grid(n, sgb::pick_cfg(c, false), true);
     return g1 > g2 ? g1 : g2;
 }
 
@@ -377,34 +409,44 @@ extern "C" int sgb_spmm_halo(const int32_t* rowptr, const sgb_edge_t* edges, con
     SGB_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr) && (in_scale == nullptr) == (in_mean == nullptr),
                   "sgb_spmm: in_mean / in_scale / in_shift must come together");
     SGB_CHECK_ARG(x != y, "sgb_spmm: in-place aggregation is not supported");
+    SGB_CHECK_ARG(ldx < (int64_t)1 << 30 && ld_ghost < (int64_t)1 << 30 && n < (int64_t)0x7fffffff, "sgb_spmm: row stride / vertex count out of range");
     SGB_CHECK_ARG(!x_ghost || (ld_ghost >= c && n_split >= 0 && n_split < (int64_t)0x7fffffff), "sgb_spmm_halo: bad ghost block");
     if (n == 0) return SGB_OK;
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     bool aligned = al16(x) && al16(y) && ldx % 4 == 0 && ldy % 4 == 0 && (!x_ghost || (al16(x_ghost) && ld_ghost % 4 == 0)) && (!addend || (al16(addend) && ld_addend % 4 == 0)) &&
                    (!bias || al16(bias)) && (!in_scale || (al16(in_scale) && al16(in_shift) && al16(in_mean)));
     SpmmCfg k = pick_cfg(c, aligned);
-    int grid = spmm_grid(n, k);
+    int grid = spmm_grid(n, k, stat_partials != nullptr);
     if (stat_partials) {
         // rows the caller sized for; unused rows must read as zero
         int rows = sgb_spmm_stat_rows(n, c);
         if (rows > grid)
             SGB_CUDA(cudaMemsetAsync(stat_partials + (size_t)grid * 3 * c, 0, (size_t)(rows - grid) * 3 * c * sizeof(float), stream));
     }
-    static const int sched = [] { const char* e = getenv("SGB_SPMM_SCHED"); return e ? atoi(e) : 1; }();
+    const bool pro = in_scale != nullptr, st = stat_partials != nullptr, halo = x_ghost != nullptr;
+    if (!pro) slope = 1.f;            // the general instantiation applies lrelu((x - 0) * 1 + 0, slope): identity
     SpmmArgs a{rowptr, reinterpret_cast<const int2*>(edges), dis, mode, x, ldx, n, c, in_mean, in_scale, in_shift, slope, alpha, addend, ld_addend, beta, bias, y, ldy, stat_partials,
-               x_ghost, ld_ghost, x_ghost ? (int32_t)n_split : (int32_t)0x7fffffff, sched};
-    const bool pro = in_scale != nullptr, st = stat_partials != nullptr;
-#define SGB_SPMM_CASE(L, V, I)                                                                  \
-    if (k.lpv == L && k.vec == V && k.iters == I) {                                             \
-        if (pro && st) k_spmm<L, V, I, true, true><<<grid, kSpmmThreads, 0, stream>>>(a);       \
-        else if (pro) k_spmm<L, V, I, true, false><<<grid, kSpmmThreads, 0, stream>>>(a);       \
-        else if (st) k_spmm<L, V, I, false, true><<<grid, kSpmmThreads, 0, stream>>>(a);        \
-        else k_spmm<L, V, I, false, false><<<grid, kSpmmThreads, 0, stream>>>(a);               \
-        SGB_CHECK_LAUNCH("k_spmm");                                                             \
-        return SGB_OK;                                                                          \
+               x_ghost, ld_ghost, x_ghost ? (int32_t)n_split : (int32_t)0x7fffffff};
+    // the BatchNorm prologue and the halo block are rare operands: they share one (slower, fully general) instantiation
+#define SGB_SPMM_CASE(L, V, I)                                                                                  \
+    if (k.lpv == L && k.vec == V && k.iters == I) {                                                             \
+        if (pro || halo || c % (L * V * I) != 0) {                                                              \
+            if (st) k_spmm<L, V, I, false, true, true, true><<<grid, kSpmmThreads, 0, stream>>>(a);             \
+            else k_spmm<L, V, I, false, true, true, false><<<grid, kSpmmThreads, 0, stream>>>(a);               \
+        } else if (st) k_spmm<L, V, I, true, false, false, true><<<grid, kSpmmThreads, 0, stream>>>(a);         \
+        else k_spmm<L, V, I, true, false, false, false><<<grid, kSpmmThreads, 0, stream>>>(a);                  \
+        SGB_CHECK_LAUNCH("k_spmm");                                                                             \
+        return SGB_OK;                                                                                          \
     }
     SGB_SPMM_CASE(1, 4, 1)
     SGB_SPMM_CASE(1, 4, 2)
+#if SGB_SPMM_ITERS == 1
+    SGB_SPMM_CASE(2, 4, 1)
+    SGB_SPMM_CASE(4, 4, 1)
+    SGB_SPMM_CASE(8, 4, 1)
+    SGB_SPMM_CASE(16, 4, 1)
+    SGB_SPMM_CASE(32, 4, 1)
+#endif
     SGB_SPMM_CASE(2, 4, 2)
     SGB_SPMM_CASE(4, 4, 2)
     SGB_SPMM_CASE(8, 4, 2)
