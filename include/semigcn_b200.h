@@ -132,18 +132,25 @@ SGB_API int sgb_gather_rows(const float* x, int64_t ldx, const int32_t* idx, int
  *    `engine`: 0 = auto, 1 = fp32 CUDA-core tiles, 2 = tcgen05 3xTF32 tensor-core tiles
  *    (error-compensated: hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM).  The tensor-core
  *    engine stages the split / pre-tiled weights in `workspace` (sgb_gemm_workspace_bytes).
+ *    3 = tcgen05 2xFP16-split tiles: operands scaled by a per-tensor power of two and split into
+ *    fp16 hi + lo (22 significant bits), the same three products at the fp16 rate; bound by the HBM
+ *    stream of the activation operand.  `a_amax` / `g_amax` (optional device scalars, max |A| /
+ *    max |G|, e.g. from the amax_out of the kernel that produced the operand) save the engine its
+ *    own reduction pass over that operand; NULL = computed internally.  Accuracy is norm-relative
+ *    (elements > 2^23 below the tensor maximum lose relative precision).  engine 0 picks 3 for
+ *    real contractions, 1 for thin ones.
  * ------------------------------------------------------------------------------------ */
 SGB_API int sgb_gemm_stat_rows(int64_t m);
 SGB_API size_t sgb_gemm_workspace_bytes(int64_t m, int n, int k, int engine);
 SGB_API int sgb_gemm(int transb, const float* a, int64_t lda, const float* b, int64_t ldb,
              float* c, int64_t ldc, int64_t m, int n, int k,
              const float* a_mean, const float* a_scale, const float* a_shift, float slope,
-             const float* bias, int accumulate, float* stat_partials,
+             const float* bias, int accumulate, float* stat_partials, const float* a_amax,
              void* workspace, size_t workspace_bytes, int engine, void* stream);
 SGB_API size_t sgb_gemm_tn_workspace_bytes(int64_t m, int n, int k);
 SGB_API int sgb_gemm_tn(const float* g, int64_t ldg, const float* a, int64_t lda, float* d, int64_t ldd,
-                int64_t m, int n, int k, int accumulate, void* workspace, size_t workspace_bytes,
-                int engine, void* stream);
+                int64_t m, int n, int k, int accumulate, const float* g_amax, const float* a_amax,
+                void* workspace, size_t workspace_bytes, int engine, void* stream);
 SGB_API size_t sgb_colsum_workspace_bytes(int64_t m, int n);
 SGB_API int sgb_colsum(const float* g, int64_t ldg, int64_t m, int n, float* out, int accumulate,
                void* workspace, size_t workspace_bytes, void* stream);

@@ -38,9 +38,9 @@ SIGNATURES = {
     "sgb_gemm_stat_rows": (_i32, [_i64]),
     "sgb_gemm_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "sgb_gemm": (_i32, [_i32, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _i32,
-                        _vp, _vp, _sz, _i32, _vp]),
+                        _vp, _vp, _vp, _sz, _i32, _vp]),
     "sgb_gemm_tn_workspace_bytes": (_sz, [_i64, _i32, _i32]),
-    "sgb_gemm_tn": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _sz, _i32, _vp]),
+    "sgb_gemm_tn": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _i32, _vp]),
     "sgb_colsum_workspace_bytes": (_sz, [_i64, _i32]),
     "sgb_colsum": (_i32, [_vp, _i64, _i64, _i32, _vp, _i32, _vp, _sz, _vp]),
     "sgb_col_stat_rows": (_i32, [_i64, _i32]),

@@ -15,6 +15,11 @@ bool gemm_tn_tc_supported(int64_t m, int n, int k, int64_t ldg, int64_t lda, con
 size_t gemm_tn_tc_workspace(int64_t m, int n, int k);
 int gemm_tn_tc_launch(const float* g, int64_t ldg, const float* a, int64_t lda, float* d, int64_t ldd, int64_t m, int n, int k,
                       int accumulate, void* ws, size_t ws_bytes, cudaStream_t stream);
+size_t gemm_f16_workspace(int n, int k);
+int gemm_f16_launch(const GemmArgs& g, const float* a_amax, void* ws, size_t ws_bytes, cudaStream_t stream);
+size_t gemm_tn_f16_workspace(int64_t m, int n, int k);
+int gemm_tn_f16_launch(const float* g, int64_t ldg, const float* a, int64_t lda, const float* g_amax, const float* a_amax, float* d,
+                       int64_t ldd, int64_t m, int n, int k, int accumulate, void* ws, size_t ws_bytes, cudaStream_t stream);
 static bool tn_tc_worthwhile(int64_t m, int n, int k) { return n >= 64 && k >= 32 && m >= 4096; }
 
 // auto policy: the tensor pipe only where the transform is a real dense contraction
@@ -29,17 +34,19 @@ extern "C" size_t sgb_gemm_workspace_bytes(int64_t m, int n, int k, int engine) 
     if (m < 0 || n <= 0 || k <= 0 || engine == 1) return 0;
     if (engine == 0 && !tc_worthwhile(m, n, k)) return 0;
     if (n % 16 != 0 || k % 4 != 0) return 0;
-    return gemm_tc_workspace(n, k);
+    size_t w2 = gemm_tc_workspace(n, k), w3 = gemm_f16_workspace(n, k);
+    return engine == 2 ? w2 : engine == 3 ? w3 : (w2 > w3 ? w2 : w3);
 }
 
 extern "C" int sgb_gemm(int transb, const float* a, int64_t lda, const float* b, int64_t ldb, float* c, int64_t ldc, int64_t m,
                         int n, int k, const float* a_mean, const float* a_scale, const float* a_shift, float slope, const float* bias,
-                        int accumulate, float* stat_partials, void* workspace, size_t workspace_bytes, int engine, void* stream) {
+                        int accumulate, float* stat_partials, const float* a_amax, void* workspace, size_t workspace_bytes, int engine,
+                        void* stream) {
     SGB_CHECK_ARG(a && b && c && m >= 0 && n > 0 && k > 0, "sgb_gemm: bad argument m=%lld n=%d k=%d", (long long)m, n, k);
     SGB_CHECK_ARG(lda >= k && ldc >= n && ldb >= (transb ? k : n), "sgb_gemm: leading dimension too small");
     SGB_CHECK_ARG((a_scale == nullptr) == (a_shift == nullptr) && (a_scale == nullptr) == (a_mean == nullptr),
                   "sgb_gemm: a_mean / a_scale / a_shift must come together");
-    SGB_CHECK_ARG(engine >= 0 && engine <= 2, "sgb_gemm: bad engine %d", engine);
+    SGB_CHECK_ARG(engine >= 0 && engine <= 3, "sgb_gemm: bad engine %d", engine);
     if (m == 0) return SGB_OK;
     GemmArgs g{transb, a, lda, b, ldb, c, ldc, m, n, k, a_mean, a_scale, a_shift, slope, bias, accumulate, stat_partials};
     const bool tc_ok = gemm_tc_supported(m, n, k, lda, ldc, a, c, bias, a_scale);
@@ -50,22 +57,36 @@ extern "C" int sgb_gemm(int transb, const float* a, int64_t lda, const float* b,
         }
         return gemm_tc_launch(g, workspace, workspace_bytes, (cudaStream_t)stream);
     }
-    if (engine == 0 && tc_ok && tc_worthwhile(m, n, k) && workspace && workspace_bytes >= gemm_tc_workspace(n, k))
-        return gemm_tc_launch(g, workspace, workspace_bytes, (cudaStream_t)stream);
+    if (engine == 3) {
+        if (!tc_ok || a_scale) {
+            set_error("sgb_gemm: fp16-split engine needs n %% 16 == 0, k %% 4 == 0, 16-byte aligned operands and no A prologue (n=%d k=%d)", n, k);
+            return SGB_ENOTSUP;
+        }
+        return gemm_f16_launch(g, a_amax, workspace, workspace_bytes, (cudaStream_t)stream);
+    }
+    if (engine == 0 && tc_ok && tc_worthwhile(m, n, k) && workspace) {
+        // auto: the fp16-split tiles (HBM-bound) unless the BatchNorm prologue is fused into the A load
+        if (!a_scale && workspace_bytes >= gemm_f16_workspace(n, k))
+            return gemm_f16_launch(g, a_amax, workspace, workspace_bytes, (cudaStream_t)stream);
+        if (workspace_bytes >= gemm_tc_workspace(n, k)) return gemm_tc_launch(g, workspace, workspace_bytes, (cudaStream_t)stream);
+    }
     return gemm_simt_launch(g, (cudaStream_t)stream);
 }
 
 extern "C" size_t sgb_gemm_tn_workspace_bytes(int64_t m, int n, int k) {
     if (m < 0 || n <= 0 || k <= 0) return 0;
     size_t a = gemm_tn_simt_workspace(m, n, k), b = (n % 4 == 0 && k % 4 == 0) ? gemm_tn_tc_workspace(m, n, k) : 0;
-    return a > b ? a : b;
+    size_t c = (n % 4 == 0 && k % 4 == 0) ? gemm_tn_f16_workspace(m, n, k) : 0;
+    a = a > b ? a : b;
+    return a > c ? a : c;
 }
 
 extern "C" int sgb_gemm_tn(const float* g, int64_t ldg, const float* a, int64_t lda, float* d, int64_t ldd, int64_t m, int n, int k,
-                           int accumulate, void* workspace, size_t workspace_bytes, int engine, void* stream) {
+                           int accumulate, const float* g_amax, const float* a_amax, void* workspace, size_t workspace_bytes, int engine,
+                           void* stream) {
     SGB_CHECK_ARG(g && a && d && m >= 0 && n > 0 && k > 0, "sgb_gemm_tn: bad argument");
     SGB_CHECK_ARG(ldg >= n && lda >= k && ldd >= k, "sgb_gemm_tn: leading dimension too small");
-    SGB_CHECK_ARG(engine >= 0 && engine <= 2, "sgb_gemm_tn: bad engine %d", engine);
+    SGB_CHECK_ARG(engine >= 0 && engine <= 3, "sgb_gemm_tn: bad engine %d", engine);
     const bool tc_ok = gemm_tn_tc_supported(m, n, k, ldg, lda, g, a);
     if (engine == 2) {
         if (!tc_ok) {
@@ -73,6 +94,13 @@ extern "C" int sgb_gemm_tn(const float* g, int64_t ldg, const float* a, int64_t 
             return SGB_ENOTSUP;
         }
         return gemm_tn_tc_launch(g, ldg, a, lda, d, ldd, m, n, k, accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
+    }
+    if (engine == 3 || (engine == 0 && tc_ok && tn_tc_worthwhile(m, n, k))) {
+        if (!tc_ok) {
+            set_error("sgb_gemm_tn: fp16-split engine needs n %% 4 == 0, k %% 4 == 0 and 16-byte aligned operands");
+            return SGB_ENOTSUP;
+        }
+        return gemm_tn_f16_launch(g, ldg, a, lda, g_amax, a_amax, d, ldd, m, n, k, accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
     }
     if (engine == 0 && tc_ok && tn_tc_worthwhile(m, n, k))
         return gemm_tn_tc_launch(g, ldg, a, lda, d, ldd, m, n, k, accumulate, workspace, workspace_bytes, (cudaStream_t)stream);

@@ -1,0 +1,728 @@
+// tcgen05 tiles for the dense feature transform with a 2 x FP16 operand split (engine 3).
+//
+// Each fp32 operand is scaled by a per-tensor power of two s (exact) so that max |x s| lies in
+// [2^14, 2^15), then split   x s = hi + lo,  hi = rn_f16(x s),  lo = rn_f16(x s - hi)   (22 significant
+// bits), and the product is evaluated as   A*B ~= (A_lo*B_hi + A_hi*B_lo + A_hi*B_hi) / (s_A s_B)
+// with fp32 accumulation in TMEM.  Same three-product error compensation as the 3xTF32 engine
+// (gemm_tc.cu), but kind::f16 runs at twice the tf32 rate and every operand byte (shared memory,
+// L2 -> SM weight traffic) is halved: at these rates both kernels are bound by the HBM stream of the
+// activation operand, which is what the feature transform algorithmically has to read.
+// Accuracy contract: max |C - C_exact| <= ~4e-7 * sum_k |A||B| (norm-relative, like fp32 SIMT);
+// elements more than ~2^-23 below their tensor's maximum lose relative (not absolute) precision,
+// since fp16 has 5 exponent bits -- see DESIGN.md "engine 3".
+//
+// k_gemm_f16    C[M,N] (+)= A[M,K] * Wp^T + bias      (forward transform and dX)
+//   persistent, one CTA per SM; 8 producer warps (global -> scale/split -> K-major no-swizzle smem,
+//   conflict-free 16-byte stores), 1 lane bulk-copies the pre-split weight image (cp.async.bulk +
+//   mbarrier complete_tx), 1 lane issues tcgen05.mma.kind::f16 128 x N x 16, 4 epilogue warps
+//   (tcgen05.ld -> unscale -> bias / accumulate -> global); double-buffered TMEM accumulators.
+// k_gemm_tn_f16 D[N,K] = G[M,N]^T A[M,K]                 (weight gradient, reduction over vertices)
+//   both operands K-major with "K" = vertex: a producer thread loads 8 vertices x 4 columns
+//   (8 float4), which is exactly four 16-byte core-matrix rows after conversion -- the transposition
+//   happens in registers.  Split over vertices across CTAs, 512-vertex TMEM segments drained with
+//   round-to-nearest adds, fixed-order reduction of the per-CTA partial tiles (deterministic).
+#include "common.cuh"
+#include "umma.cuh"
+#include <cuda_fp16.h>
+
+namespace sgb {
+
+// ------------------------------------------------------------------------------------------
+// per-tensor power-of-two scale from max |x|
+// ------------------------------------------------------------------------------------------
+// s = 2^(14 - floor(log2 amax)) -> amax * s in [2^14, 2^15); amax == 0 / non-finite -> 1
+__host__ __device__ __forceinline__ void f16_scale_from_amax(float amax, float& s, float& inv) {
+    uint32_t bits;
+#ifdef __CUDA_ARCH__
+    bits = __float_as_uint(amax);
+#else
+    union { float f; uint32_t u; } cv; cv.f = amax; bits = cv.u;
+#endif
+    const int e = (int)((bits >> 23) & 0xff);
+    int se = 127 + 14 - (e - 127);
+    if (e == 0 || e == 255) se = 127;
+    if (se < 2) se = 2;
+    if (se > 252) se = 252;
+#ifdef __CUDA_ARCH__
+    s = __uint_as_float((uint32_t)se << 23);
+    inv = __uint_as_float((uint32_t)(254 - se) << 23);
+#else
+    cv.u = (uint32_t)se << 23; s = cv.f;
+    cv.u = (uint32_t)(254 - se) << 23; inv = cv.f;
+#endif
+}
+
+// max |x| over an [m, c] matrix -> atomicMax on the float bits (non-negative floats order like uints).
+// The slot must be zero before the launch.
+__global__ void __launch_bounds__(256) k_amax(const float* __restrict__ x, int64_t ldx, int64_t m, int c, uint32_t* __restrict__ slot) {
+    const int cv = c >> 2;
+    const int64_t total = m * cv;
+    float mx = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cv;
+        const int ch = (int)(i % cv) * 4;
+        const float4 v = ldg4(x + r * ldx + ch);
+        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    uint32_t b = __float_as_uint(mx);
+    b = __reduce_max_sync(0xffffffffu, b);
+    __shared__ uint32_t sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) b = max(b, sm[w]);
+        if (b) atomicMax(slot, b);
+    }
+}
+
+static int amax_launch(const float* x, int64_t ldx, int64_t m, int c, uint32_t* slot, cudaStream_t stream) {
+    SGB_CUDA(cudaMemsetAsync(slot, 0, sizeof(uint32_t), stream));
+    const int64_t total = m * (c / 4);
+    const int grid = (int)min64(ceil_div(total > 0 ? total : 1, 256 * 8), (int64_t)num_sms() * 8);
+    k_amax<<<grid, 256, 0, stream>>>(x, ldx, m, c, slot);
+    SGB_CHECK_LAUNCH("k_amax");
+    return SGB_OK;
+}
+
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x0 - f.x, x1 - f.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// ------------------------------------------------------------------------------------------
+// forward / dX kernel geometry
+// ------------------------------------------------------------------------------------------
+constexpr int kHBM = 128;                       // rows per tile == UMMA M
+constexpr int kHBK = 32;                        // K elements per pipeline stage (2 MMA k-slices of 16)
+constexpr int kHCols = kHBK / 8;                // 16-byte core-matrix columns per stage
+constexpr int kHALbo = 144;                     // bytes between K-adjacent core matrices of A (128 + 16 pad: conflict-free stores)
+constexpr int kHASbo = kHCols * kHALbo;         // bytes between M-adjacent core matrices of A
+constexpr int kHATile = (kHBM / 8) * kHASbo;    // per hi (or lo)
+constexpr int kHBLbo = 128;
+constexpr int kHBSbo = kHCols * kHBLbo;
+constexpr int kHProducerWarps = 8;
+constexpr int kHThreads = (kHProducerWarps + 2 + 4) * 32;
+constexpr int kHMaxStages = 6;
+constexpr int kHEpiLd = 36;                     // floats per row of an epilogue warp's 32 x 32 staging tile (+4: conflict-free)
+constexpr int kHEpiBytes = 4 * 32 * kHEpiLd * 4;
+static const int kHSmemBudget = 227 * 1024;
+
+__host__ __device__ constexpr int h_b_tile_bytes(int bn) { return (bn / 8) * kHBSbo; }
+__host__ __device__ constexpr int h_stage_bytes(int bn) { return 2 * kHATile + 2 * h_b_tile_bytes(bn); }
+
+struct HArgs {
+    const float* a; int64_t lda;
+    const uint8_t* wp;                // prepped weights: [n_tiles][k_chunks][hi|lo][tile image]
+    const float* wscale;              // [0] = s_W, [1] = 1 / s_W   (written by k_prep_weights_f16)
+    const float* a_amax;              // device scalar: max |A|
+    float* c; int64_t ldc;
+    int64_t m; int n; int k;
+    int bn; int n_tiles; int k_chunks; int stages;
+    const float* bias; int accumulate;
+    uint32_t tmem_cols; int acc_stride;
+};
+
+// weights -> scale, hi/lo fp16 split, zero padded, in the exact per-stage shared-memory image.
+// Small grid; every CTA first reduces max |W| itself (W is at most 1 MB and L2-resident), so one launch
+// does amax + prep and the scale never round-trips through the host.
+__global__ void __launch_bounds__(256) k_prep_weights_f16(const float* __restrict__ w, int64_t ldw, int transb, int n, int k, int bn,
+                                                          int n_tiles, int k_chunks, __half* __restrict__ wp, float* __restrict__ wscale) {
+    __shared__ float sm[8];
+    const int rows = transb ? n : k, cols = transb ? k : n;
+    float mx = 0.f;
+    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) mx = fmaxf(mx, fabsf(w[(int64_t)(i / cols) * ldw + (i % cols)]));
+    mx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mx)));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = sm[0];
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, sm[i]);
+    float s, inv;
+    f16_scale_from_amax(mx, s, inv);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { wscale[0] = s; wscale[1] = inv; }
+    const int tile_halves = h_b_tile_bytes(bn) / 2;
+    const int64_t total = (int64_t)n_tiles * k_chunks * tile_halves;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int h = (int)(i % tile_halves);
+        const int64_t blk = i / tile_halves;
+        const int q = (int)(blk % k_chunks), t = (int)(blk / k_chunks);
+        const int core_n = h / (kHBSbo / 2);
+        const int rem = h % (kHBSbo / 2);
+        const int core_k = rem / 64, in_core = rem % 64;
+        const int nl = core_n * 8 + in_core / 8, kl = core_k * 8 + in_core % 8;
+        const int gn = t * bn + nl, gk = q * kHBK + kl;
+        float v = 0.f;
+        if (gn < n && gk < k) v = transb ? w[(int64_t)gn * ldw + gk] : w[(int64_t)gk * ldw + gn];
+        v *= s;
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(hi));
+        __half* base = wp + (blk * 2) * tile_halves;
+        base[h] = hi;
+        base[tile_halves + h] = lo;
+    }
+}
+
+__global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const HArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stage_bytes = h_stage_bytes(g.bn);
+    const int b_tile_bytes = h_b_tile_bytes(g.bn);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)g.stages * stage_bytes);
+    uint64_t* empty = full + kHMaxStages;
+    uint64_t* tfull = empty + kHMaxStages;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.stages; ++s) {
+            mbar_init(&full[s], kHProducerWarps * 32 + 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tfull[b], 1);
+            mbar_init(&tempty[b], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == kHProducerWarps + 1) tmem_alloc(tmem_slot, g.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t m_tiles = (g.m + kHBM - 1) / kHBM;
+    const int64_t total_tiles = m_tiles * g.n_tiles;
+
+    if (warp < kHProducerWarps) {
+        // ================= A producers: global -> regs (scale, hi/lo fp16) -> smem =================
+        float sa, inva;
+        f16_scale_from_amax(__ldg(g.a_amax), sa, inva);
+        const int ptid = threadIdx.x;                          // 0..255
+        // stage = 128 rows x kHCols core columns (8 K elements = 2 float4 each); thread: column cq, rows r0, r0 + 64
+        const int cq = ptid % kHCols, r0 = ptid / kHCols;      // r0 in 0..63
+        constexpr int RPT = kHBM * kHCols / 256;               // row slots per thread (2)
+        constexpr int RSTEP = 256 / kHCols;                    // 64
+        const int64_t my_tiles = total_tiles > blockIdx.x ? (total_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+        const int64_t total_it = my_tiles * g.k_chunks;
+        auto issue = [&](int64_t i, float4 (&v)[RPT][2]) {
+            const int64_t tile = blockIdx.x + (i / g.k_chunks) * gridDim.x;
+            const int q = (int)(i % g.k_chunks);
+            const int64_t m0 = (tile / g.n_tiles) * kHBM;
+            const int kcol = q * kHBK + cq * 8;
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                const int64_t gm = m0 + r0 + RSTEP * r;
+                v[r][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                v[r][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < total_it && gm < g.m) {                // K % 4 == 0 guaranteed by the dispatcher
+                    if (kcol < g.k) v[r][0] = ldg4(g.a + gm * g.lda + kcol);
+                    if (kcol + 4 < g.k) v[r][1] = ldg4(g.a + gm * g.lda + kcol + 4);
+                }
+            }
+        };
+        auto process = [&](int64_t it, float4 (&v)[RPT][2]) {
+            const int s = (int)(it % g.stages);
+            const uint32_t ph = (uint32_t)((it / g.stages) & 1);
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* a_hi = smem + (size_t)s * stage_bytes;
+            uint8_t* a_lo = a_hi + kHATile;
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                const int r = r0 + RSTEP * i;
+                uint4 h, l;
+                split_f16x2(v[i][0].x * sa, v[i][0].y * sa, h.x, l.x);
+                split_f16x2(v[i][0].z * sa, v[i][0].w * sa, h.y, l.y);
+                split_f16x2(v[i][1].x * sa, v[i][1].y * sa, h.z, l.z);
+                split_f16x2(v[i][1].z * sa, v[i][1].w * sa, h.w, l.w);
+                const uint32_t off = (uint32_t)(r >> 3) * kHASbo + (uint32_t)cq * kHALbo + (uint32_t)(r & 7) * 16;
+                *reinterpret_cast<uint4*>(a_hi + off) = h;
+                *reinterpret_cast<uint4*>(a_lo + off) = l;
+            }
+            fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            mbar_arrive(&full[s]);
+        };
+        // three register buffers, loop unrolled by three: the loads of iterations it+1 and it+2 stay in flight while
+        // iteration it is converted (no register rotation -- a move out of a pending load would wait for it)
+        float4 b0[RPT][2], b1[RPT][2], b2[RPT][2];
+        issue(0, b0);
+        issue(1, b1);
+        issue(2, b2);
+        for (int64_t it = 0; it < total_it; it += 3) {
+            process(it, b0);
+            issue(it + 3, b0);
+            if (it + 1 < total_it) { process(it + 1, b1); issue(it + 4, b1); }
+            if (it + 2 < total_it) { process(it + 2, b2); issue(it + 5, b2); }
+        }
+    } else if (warp == kHProducerWarps) {
+        // ================= B copy: one bulk copy of the pre-tiled hi|lo weight image per stage =================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = (int)(tile % g.n_tiles);
+                for (int q = 0; q < g.k_chunks; ++q, ++it) {
+                    const int s = it % g.stages;
+                    const uint32_t ph = (it / g.stages) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* b_dst = smem + (size_t)s * stage_bytes + 2 * kHATile;
+                    const uint8_t* src = g.wp + ((size_t)nt * g.k_chunks + q) * 2 * b_tile_bytes;
+                    mbar_arrive_expect_tx(&full[s], 2 * b_tile_bytes);
+                    bulk_g2s(b_dst, src, 2 * b_tile_bytes, &full[s]);
+                }
+            }
+        }
+    } else if (warp == kHProducerWarps + 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            uint32_t it = 0, tcount = 0;
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+                const int nt = (int)(tile % g.n_tiles);
+                const int ncols = min(g.bn, g.n - nt * g.bn);                 // multiple of 16
+                const uint32_t idesc = make_idesc_f16(kHBM, ncols, 0, 0);
+                const int acc = tcount & 1;
+                mbar_wait(&tempty[acc], ((tcount >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.acc_stride);
+                for (int q = 0; q < g.k_chunks; ++q, ++it) {
+                    const int s = it % g.stages;
+                    const uint32_t ph = (it / g.stages) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t a_lo = a_hi + kHATile;
+                    const uint32_t b_hi = a_hi + 2 * kHATile;
+                    const uint32_t b_lo = b_hi + b_tile_bytes;
+#pragma unroll
+                    for (int j = 0; j < kHBK / 16; ++j) {
+                        const uint64_t dah = make_desc(a_hi + j * 2 * kHALbo, kHALbo, kHASbo);
+                        const uint64_t dal = make_desc(a_lo + j * 2 * kHALbo, kHALbo, kHASbo);
+                        const uint64_t dbh = make_desc(b_hi + j * 2 * kHBLbo, kHBLbo, kHBSbo);
+                        const uint64_t dbl = make_desc(b_lo + j * 2 * kHBLbo, kHBLbo, kHBSbo);
+                        // small terms first, the dominant hi*hi product last
+                        umma_f16(d_tmem, dal, dbh, idesc, (q | j) ? 1u : 0u);
+                        umma_f16(d_tmem, dah, dbl, idesc, 1u);
+                        umma_f16(d_tmem, dah, dbh, idesc, 1u);
+                    }
+                    umma_commit(&empty[s]);          // frees the smem slot when the MMAs above have read it
+                }
+                umma_commit(&tfull[acc]);            // accumulator complete
+            }
+        }
+    } else {
+        // ================= epilogue: TMEM -> registers -> unscale (+bias, +C) -> global =================
+        float sa, inva;
+        f16_scale_from_amax(__ldg(g.a_amax), sa, inva);
+        const float invw = __ldg(g.wscale + 1);
+        const int quarter = warp & 3;                // TMEM lanes 32*quarter .. +31 are accessible to this warp
+        float* stg = reinterpret_cast<float*>(smem + (size_t)g.stages * stage_bytes + 256) + quarter * 32 * kHEpiLd;
+        uint32_t tcount = 0;
+        for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+            const int nt = (int)(tile % g.n_tiles);
+            const int64_t m0 = (tile / g.n_tiles) * kHBM;
+            const int n0 = nt * g.bn;
+            const int ncols = min(g.bn, g.n - n0);
+            const int acc = tcount & 1;
+            mbar_wait(&tfull[acc], (tcount >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * g.acc_stride);
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+                float v[32];
+                tmem_ld_32x32(taddr + c0, v);        // warp-collective: lane = row, registers = 32 consecutive columns
+                // transpose through the warp's staging tile so that global stores are whole 128-byte row segments
+                // (a lane-per-row store touches 32 different lines per instruction and saturates the L1 data pipe)
+#pragma unroll
+                for (int e = 0; e < 32; e += 4)
+                    *reinterpret_cast<float4*>(stg + lane * kHEpiLd + e) =
+                        make_float4((v[e] * inva) * invw, (v[e + 1] * inva) * invw, (v[e + 2] * inva) * invw, (v[e + 3] * inva) * invw);
+                __syncwarp();
+                const int cc = (lane & 7) * 4;                   // this lane's float4 inside the 32-column chunk
+                if (c0 + cc < ncols) {                           // ncols is a multiple of 16 => whole float4 valid
+                    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (g.bias) b = ldg4(g.bias + n0 + c0 + cc);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int j = i * 4 + (lane >> 3);
+                        const int64_t gm = m0 + quarter * 32 + j;
+                        if (gm < g.m) {
+                            float4 o = *reinterpret_cast<const float4*>(stg + j * kHEpiLd + cc);
+                            float* cp = g.c + gm * g.ldc + n0 + c0 + cc;
+                            if (g.accumulate) {
+                                const float4 old = *reinterpret_cast<const float4*>(cp);
+                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                            }
+                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                            *reinterpret_cast<float4*>(cp) = o;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kHProducerWarps + 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, g.tmem_cols);
+    }
+}
+
+// per-128-row-tile column moments of C (BatchNorm partials) / fixed-order split reduction -- gemm_tc.cu
+int tile_col_stats_launch(const float* c, int64_t ldc, int64_t m, int n, float* partials, cudaStream_t stream);
+int reduce_splits_launch(const float* partial, int splits, int n, int k, float* d, int64_t ldd, int accumulate, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------
+// weight gradient:  D[n,k] = sum_m G[m,n] * A[m,k];   UMMA M = 128 rows of n, N = k-tile, K = 16 vertices
+// ------------------------------------------------------------------------------------------
+constexpr int kTBM = 128;                        // rows of D (n) per CTA
+constexpr int kTBV = 32;                         // vertices per pipeline stage
+constexpr int kTCols = kTBV / 8;                 // 16-byte core-matrix columns (8 vertices each) per stage
+constexpr int kTLbo = 128;                       // vertex-adjacent core matrices
+constexpr int kTSbo = kTCols * kTLbo + 16;       // row-adjacent core matrices (+16: spreads the transposing stores over the banks)
+constexpr int kTGTile = (kTBM / 8) * kTSbo;      // per hi (or lo)
+constexpr int kTProducerWarps = 12;              // 384 threads: one (8 vertices x 4 columns) item each per stage
+constexpr int kTDrainWarps = 4;
+constexpr int kTThreads = (kTProducerWarps + 1 + kTDrainWarps) * 32;
+constexpr int kTSegChunks = 16;                  // 512 vertices per TMEM accumulation segment (tensor-core accumulation truncates)
+
+__host__ __device__ constexpr int t_a_tile_bytes(int bk) { return (bk / 8) * kTSbo; }
+__host__ __device__ constexpr int t_stage_bytes(int bk) { return 2 * kTGTile + 2 * t_a_tile_bytes(bk); }
+
+struct TArgs {
+    const float* g; int64_t ldg;
+    const float* a; int64_t lda;
+    const float* g_amax; const float* a_amax;   // device scalars
+    float* partial;                   // [splits][n][k]
+    int64_t m; int n; int k;
+    int bk;                           // UMMA N: columns of D per CTA (multiple of 16, <= 256)
+    int k_tiles; int stages;
+    int64_t m_per_split;              // multiple of kTBV
+    uint32_t tmem_cols; int acc_stride;
+};
+
+__global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const TArgs t) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stage_bytes = t_stage_bytes(t.bk);
+    const int a_tile_bytes = t_a_tile_bytes(t.bk);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)t.stages * stage_bytes);
+    uint64_t* empty = full + kHMaxStages;
+    uint64_t* tfull = empty + kHMaxStages;      // [2]
+    uint64_t* tempty = tfull + 2;               // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < t.stages; ++s) {
+            mbar_init(&full[s], kTProducerWarps * 32);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tfull[b], 1);
+            mbar_init(&tempty[b], kTDrainWarps);
+        }
+        fence_barrier_init();
+    }
+    if (warp == kTProducerWarps) tmem_alloc(tmem_slot, t.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n0 = (blockIdx.x / t.k_tiles) * kTBM;
+    const int k0 = (blockIdx.x % t.k_tiles) * t.bk;
+    const int64_t ms = (int64_t)blockIdx.y * t.m_per_split;
+    const int64_t me = min64(t.m, ms + t.m_per_split);
+    const int chunks = me > ms ? (int)((me - ms + kTBV - 1) / kTBV) : 0;
+    const int segments = (chunks + kTSegChunks - 1) / kTSegChunks;
+    float sg, invg, sa, inva;
+    f16_scale_from_amax(__ldg(t.g_amax), sg, invg);
+    f16_scale_from_amax(__ldg(t.a_amax), sa, inva);
+
+    if (warp < kTProducerWarps) {
+        // thread item: 8 consecutive vertices (core column mg) x 4 consecutive columns (float4 index c4) of G (threads 0..127)
+        // or of A (threads 128..383); the 8 x 4 register block is four 16-byte K-major rows after conversion
+        const int tid = threadIdx.x;
+        const bool is_g = tid < 128;
+        const int idx = is_g ? tid : tid - 128;
+        const int per_mg = is_g ? 32 : 64;
+        const int mg = idx / per_mg, c4 = idx % per_mg;
+        const int col = (is_g ? n0 : k0) + c4 * 4;
+        const int lim = is_g ? t.n : min(t.k, k0 + t.bk);
+        const bool col_ok = col < lim;                                    // n, k multiples of 4: whole float4 valid
+        const float* src = (is_g ? t.g : t.a) + col;
+        const int64_t ld = is_g ? t.ldg : t.lda;
+        const float sc = is_g ? sg : sa;
+        const uint32_t tile_off = is_g ? 0u : (uint32_t)(2 * kTGTile);
+        const uint32_t lo_off = is_g ? (uint32_t)kTGTile : (uint32_t)a_tile_bytes;
+        // rows 4*c4 .. 4*c4+3 of the operand tile, core column mg
+        const uint32_t base_off = tile_off + (uint32_t)((c4 * 4) >> 3) * kTSbo + (uint32_t)mg * kTLbo + (uint32_t)((c4 * 4) & 7) * 16;
+        auto issue = [&](int it, float4 (&v)[8]) {
+            const int64_t gm0 = ms + (int64_t)it * kTBV + mg * 8;
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                v[r] = (it < chunks && col_ok && gm0 + r < me) ? ldg4(src + (gm0 + r) * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        const bool in_tile = c4 * 4 < (is_g ? kTBM : t.bk);
+        auto process = [&](int it, float4 (&v)[8]) {
+            const int s = it % t.stages;
+            const uint32_t ph = (it / t.stages) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* st = smem + (size_t)s * stage_bytes + base_off;
+            if (in_tile) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float x0 = (&v[0].x)[q], x1 = (&v[1].x)[q], x2 = (&v[2].x)[q], x3 = (&v[3].x)[q];
+                    const float x4 = (&v[4].x)[q], x5 = (&v[5].x)[q], x6 = (&v[6].x)[q], x7 = (&v[7].x)[q];
+                    uint4 h, l;
+                    split_f16x2(x0 * sc, x1 * sc, h.x, l.x);
+                    split_f16x2(x2 * sc, x3 * sc, h.y, l.y);
+                    split_f16x2(x4 * sc, x5 * sc, h.z, l.z);
+                    split_f16x2(x6 * sc, x7 * sc, h.w, l.w);
+                    *reinterpret_cast<uint4*>(st + q * 16) = h;
+                    *reinterpret_cast<uint4*>(st + lo_off + q * 16) = l;
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(&full[s]);
+        };
+        // two register buffers, loop unrolled by two: the loads of stage it+1 are in flight while stage it is converted
+        float4 v0[8], v1[8];
+        issue(0, v0);
+        issue(1, v1);
+        for (int it = 0; it < chunks; it += 2) {
+            process(it, v0);
+            issue(it + 2, v0);
+            if (it + 1 < chunks) { process(it + 1, v1); issue(it + 3, v1); }
+        }
+    } else if (warp == kTProducerWarps) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_f16(kTBM, t.bk, 0, 0);        // both operands K-major (K = vertex)
+            for (int it = 0; it < chunks; ++it) {
+                const int s = it % t.stages;
+                const uint32_t ph = (it / t.stages) & 1;
+                const int seg = it / kTSegChunks, in_seg = it % kTSegChunks;
+                const int acc = seg & 1;
+                if (in_seg == 0) {
+                    mbar_wait(&tempty[acc], ((seg >> 1) & 1) ^ 1);          // drained (passes at once for the first two segments)
+                    tc_fence_after();
+                }
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * t.acc_stride);
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t g_hi = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t g_lo = g_hi + kTGTile;
+                const uint32_t a_hi = g_lo + kTGTile;
+                const uint32_t a_lo = a_hi + a_tile_bytes;
+#pragma unroll
+                for (int j = 0; j < kTBV / 16; ++j) {
+                    const uint64_t dgh = make_desc(g_hi + j * 2 * kTLbo, kTLbo, kTSbo);
+                    const uint64_t dgl = make_desc(g_lo + j * 2 * kTLbo, kTLbo, kTSbo);
+                    const uint64_t dah = make_desc(a_hi + j * 2 * kTLbo, kTLbo, kTSbo);
+                    const uint64_t dal = make_desc(a_lo + j * 2 * kTLbo, kTLbo, kTSbo);
+                    umma_f16(d_tmem, dgl, dah, idesc, (in_seg | j) ? 1u : 0u);
+                    umma_f16(d_tmem, dgh, dal, idesc, 1u);
+                    umma_f16(d_tmem, dgh, dah, idesc, 1u);
+                }
+                umma_commit(&empty[s]);
+                if (in_seg == kTSegChunks - 1 || it == chunks - 1) umma_commit(&tfull[acc]);
+            }
+        }
+    } else {
+        // drain warps: TMEM lane quarter = warp % 4; running total lives in the CTA's partial tile (L2-resident),
+        // always updated by the same thread in the same order -> deterministic
+        const int quarter = warp & 3;
+        float* out = t.partial + (int64_t)blockIdx.y * t.n * t.k;
+        const int gn = n0 + quarter * 32 + lane;
+        const int kcols = min(t.bk, t.k - k0);
+        const bool vec_ok = (t.k % 4 == 0) && (k0 % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+        if (segments == 0) {
+            if (gn < t.n)
+                for (int c = 0; c < kcols; ++c) out[(int64_t)gn * t.k + k0 + c] = 0.f;
+        }
+        for (int seg = 0; seg < segments; ++seg) {
+            const int acc = seg & 1;
+            mbar_wait(&tfull[acc], (seg >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * t.acc_stride);
+            for (int c0 = 0; c0 < kcols; c0 += 32) {
+                float v[32];
+                tmem_ld_32x32(taddr + (uint32_t)c0, v);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] = (v[e] * invg) * inva;
+                if (gn < t.n) {
+                    float* op = out + (int64_t)gn * t.k + k0 + c0;
+                    if (vec_ok && c0 + 32 <= kcols) {
+                        float4 old[8];
+                        if (seg != 0) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) old[e] = *reinterpret_cast<const float4*>(op + 4 * e);
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float4 o = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                            if (seg != 0) { o.x += old[e].x; o.y += old[e].y; o.z += old[e].z; o.w += old[e].w; }
+                            *reinterpret_cast<float4*>(op + 4 * e) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e)
+                            if (c0 + e < kcols) op[e] = seg == 0 ? v[e] : op[e] + v[e];
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kTProducerWarps) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, t.tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct HPlan {
+    int bn, n_tiles, k_chunks, stages, acc_stride;
+    size_t smem_bytes, img_bytes;
+    uint32_t tmem_cols;
+};
+
+static HPlan h_plan(int n, int k) {
+    HPlan p;
+    p.bn = n <= 256 ? n : 256;
+    p.n_tiles = (n + p.bn - 1) / p.bn;
+    p.k_chunks = (k + kHBK - 1) / kHBK;
+    int sb = h_stage_bytes(p.bn);
+    int st = (kHSmemBudget - 256 - kHEpiBytes) / sb;
+    p.stages = st > kHMaxStages ? kHMaxStages : st;
+    p.smem_bytes = (size_t)p.stages * sb + 256 + kHEpiBytes;
+    p.img_bytes = (size_t)p.n_tiles * p.k_chunks * 2 * h_b_tile_bytes(p.bn);
+    p.acc_stride = (p.bn + 31) / 32 * 32;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * p.acc_stride)) cols <<= 1;
+    p.tmem_cols = cols;
+    return p;
+}
+
+// workspace: [0,256) header (w scale, 1/scale, internal amax slot), then the weight image
+size_t gemm_f16_workspace(int n, int k) { return h_plan(n, k).img_bytes + 512; }
+
+int gemm_f16_launch(const GemmArgs& g, const float* a_amax, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    HPlan p = h_plan(g.n, g.k);
+    if (!ws || ws_bytes < p.img_bytes + 512) {
+        set_error("sgb_gemm: fp16-split engine needs %zu bytes of workspace, got %zu", p.img_bytes + 512, ws_bytes);
+        return SGB_ENOSPC;
+    }
+    if (p.stages < 2) {
+        set_error("sgb_gemm: tile does not fit shared memory");
+        return SGB_ENOTSUP;
+    }
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    float* hdr = reinterpret_cast<float*>(base);
+    uint8_t* img = base + 256;
+    if (!a_amax) {
+        int rc = amax_launch(g.a, g.lda, g.m, g.k, reinterpret_cast<uint32_t*>(hdr + 2), stream);
+        if (rc != SGB_OK) return rc;
+        a_amax = hdr + 2;
+    }
+    k_prep_weights_f16<<<32, 256, 0, stream>>>(g.b, g.ldb, g.transb, g.n, g.k, p.bn, p.n_tiles, p.k_chunks, reinterpret_cast<__half*>(img), hdr);
+    SGB_CHECK_LAUNCH("k_prep_weights_f16");
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        SGB_CUDA(cudaFuncSetAttribute(k_gemm_f16, cudaFuncAttributeMaxDynamicSharedMemorySize, kHSmemBudget));
+        attr_set = true;
+    }
+    HArgs t{};
+    t.a = g.a; t.lda = g.lda; t.wp = img; t.wscale = hdr; t.a_amax = a_amax; t.c = g.c; t.ldc = g.ldc; t.m = g.m; t.n = g.n; t.k = g.k;
+    t.bn = p.bn; t.n_tiles = p.n_tiles; t.k_chunks = p.k_chunks; t.stages = p.stages;
+    t.bias = g.bias; t.accumulate = g.accumulate; t.tmem_cols = p.tmem_cols; t.acc_stride = p.acc_stride;
+    int64_t tiles = ceil_div(g.m, kHBM) * p.n_tiles;
+    int grid = (int)min64(tiles, num_sms());
+    k_gemm_f16<<<grid, kHThreads, p.smem_bytes, stream>>>(t);
+    SGB_CHECK_LAUNCH("k_gemm_f16");
+    if (g.stat_partials) return tile_col_stats_launch(g.c, g.ldc, g.m, g.n, g.stat_partials, stream);
+    return SGB_OK;
+}
+
+// ---- weight gradient ----
+struct TPlan {
+    int bk, k_tiles, n_tiles, stages, splits, acc_stride;
+    int64_t m_per_split;
+    size_t smem_bytes, ws_bytes;
+    uint32_t tmem_cols;
+};
+
+static TPlan t_plan(int64_t m, int n, int k) {
+    TPlan p;
+    int kpad = (k + 15) / 16 * 16;
+    p.bk = kpad <= 256 ? kpad : 256;
+    p.k_tiles = (k + p.bk - 1) / p.bk;
+    p.n_tiles = (n + kTBM - 1) / kTBM;
+    int sb = t_stage_bytes(p.bk);
+    int st = (kHSmemBudget - 256) / sb;
+    p.stages = st > kHMaxStages ? kHMaxStages : st;
+    p.smem_bytes = (size_t)p.stages * sb + 256;
+    int tiles = p.k_tiles * p.n_tiles;
+    int64_t want = num_sms() / tiles;
+    if (want < 1) want = 1;
+    int64_t maxs = ceil_div(m > 0 ? m : 1, 1024);
+    p.splits = (int)(want < maxs ? want : maxs);
+    p.m_per_split = ceil_div(ceil_div(m, p.splits), kTBV) * kTBV;
+    p.ws_bytes = (size_t)p.splits * n * k * sizeof(float) + 512;
+    p.acc_stride = (p.bk + 31) / 32 * 32;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * p.acc_stride)) cols <<= 1;
+    p.tmem_cols = cols;
+    return p;
+}
+
+size_t gemm_tn_f16_workspace(int64_t m, int n, int k) { return t_plan(m, n, k).ws_bytes; }
+
+int gemm_tn_f16_launch(const float* g, int64_t ldg, const float* a, int64_t lda, const float* g_amax, const float* a_amax, float* d,
+                       int64_t ldd, int64_t m, int n, int k, int accumulate, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    TPlan p = t_plan(m, n, k);
+    if (!ws || ws_bytes < p.ws_bytes) {
+        set_error("sgb_gemm_tn: fp16-split engine needs %zu bytes of workspace, got %zu", p.ws_bytes, ws_bytes);
+        return SGB_ENOSPC;
+    }
+    if (p.stages < 2) {
+        set_error("sgb_gemm_tn: tile does not fit shared memory");
+        return SGB_ENOTSUP;
+    }
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    float* hdr = reinterpret_cast<float*>(base);
+    float* partial = reinterpret_cast<float*>(base + 256);
+    if (!g_amax) {
+        int rc = amax_launch(g, ldg, m, n, reinterpret_cast<uint32_t*>(hdr + 0), stream);
+        if (rc != SGB_OK) return rc;
+        g_amax = hdr + 0;
+    }
+    if (!a_amax) {
+        int rc = amax_launch(a, lda, m, k, reinterpret_cast<uint32_t*>(hdr + 1), stream);
+        if (rc != SGB_OK) return rc;
+        a_amax = hdr + 1;
+    }
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        SGB_CUDA(cudaFuncSetAttribute(k_gemm_tn_f16, cudaFuncAttributeMaxDynamicSharedMemorySize, kHSmemBudget));
+        attr_set = true;
+    }
+    TArgs t{};
+    t.g = g; t.ldg = ldg; t.a = a; t.lda = lda; t.g_amax = g_amax; t.a_amax = a_amax; t.partial = partial; t.m = m; t.n = n; t.k = k;
+    t.bk = p.bk; t.k_tiles = p.k_tiles; t.stages = p.stages; t.m_per_split = p.m_per_split; t.tmem_cols = p.tmem_cols; t.acc_stride = p.acc_stride;
+    dim3 grid((unsigned)(p.n_tiles * p.k_tiles), (unsigned)p.splits);
+    k_gemm_tn_f16<<<grid, kTThreads, p.smem_bytes, stream>>>(t);
+    SGB_CHECK_LAUNCH("k_gemm_tn_f16");
+    return reduce_splits_launch(partial, p.splits, n, k, d, ldd, accumulate, stream);
+}
+
+}  // namespace sgb

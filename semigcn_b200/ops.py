@@ -151,8 +151,10 @@ def spmm(g: MeshGraph, x: Tensor, transpose: bool = False, in_affine: Affine = N
 
 
 def gemm(a: Tensor, b: Tensor, transb: bool = True, a_affine: Affine = None, bias: Optional[Tensor] = None,
-         out: Optional[Tensor] = None, accumulate: bool = False, want_stats: bool = False, engine: int = 0):
-    """C (+)= f(A) @ (B^T if transb else B) + bias."""
+         out: Optional[Tensor] = None, accumulate: bool = False, want_stats: bool = False, engine: int = 0,
+         a_amax: Optional[Tensor] = None):
+    """C (+)= f(A) @ (B^T if transb else B) + bias.  ``a_amax``: optional device scalar max|A| (from the kernel
+    that produced A) for the fp16-split tensor-core engine; None = the engine reduces it itself."""
     lib = L.load()
     require_cuda(a, b, bias)
     a, b = _f32c(a, "a"), _f32c(b, "b")
@@ -172,14 +174,15 @@ def gemm(a: Tensor, b: Tensor, transb: bool = True, a_affine: Affine = None, bia
     with torch.cuda.device(a.device):
         check(lib.sgb_gemm(1 if transb else 0, ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(c), c.stride(0), m, n, k,
                            ptr(mu), ptr(sc), ptr(sh), float(slope), ptr(bias), 1 if accumulate else 0, ptr(partials),
-                           ptr(ws), wsb, engine, stream_ptr(a.device)), "sgb_gemm")
+                           ptr(a_amax), ptr(ws), wsb, engine, stream_ptr(a.device)), "sgb_gemm")
     if sp is not None:
         sp.close()
     L.count(1)
     return (c, partials) if want_stats else c
 
 
-def gemm_tn(gmat: Tensor, a: Tensor, out: Optional[Tensor] = None, accumulate: bool = False, engine: int = 0) -> Tensor:
+def gemm_tn(gmat: Tensor, a: Tensor, out: Optional[Tensor] = None, accumulate: bool = False, engine: int = 0,
+            g_amax: Optional[Tensor] = None, a_amax: Optional[Tensor] = None) -> Tensor:
     """D[n,k] (+)= G[m,n]^T @ A[m,k]  (weight gradient)."""
     lib = L.load()
     require_cuda(gmat, a)
@@ -194,7 +197,7 @@ def gemm_tn(gmat: Tensor, a: Tensor, out: Optional[Tensor] = None, accumulate: b
     sp = _prof.span(f"gemm_tn_n{n}_k{k}", 4.0 * (m * (k + n) + k * n), 2.0 * m * n * k) if _prof.ACTIVE is not None else None
     with torch.cuda.device(a.device):
         check(lib.sgb_gemm_tn(ptr(gmat), gmat.stride(0), ptr(a), a.stride(0), ptr(d), d.stride(0), m, n, k,
-                              1 if accumulate else 0, ptr(ws), wsb, engine, stream_ptr(a.device)), "sgb_gemm_tn")
+                              1 if accumulate else 0, ptr(g_amax), ptr(a_amax), ptr(ws), wsb, engine, stream_ptr(a.device)), "sgb_gemm_tn")
     if sp is not None:
         sp.close()
     L.count(2)

@@ -279,22 +279,48 @@ TC_SHAPES = [(1000, 64, 64), (129, 16, 8), (5000, 256, 256), (4100, 512, 256), (
 
 @pytest.mark.parametrize("m,n,k", TC_SHAPES)
 @pytest.mark.parametrize("transb", [True, False])
-def test_gemm_tensor_core_engine_vs_fp64(m, n, k, transb):
-    """engine=2 (tcgen05, error-compensated 3xTF32) must hold the same fp32-level bar as the CUDA-core tiles."""
+@pytest.mark.parametrize("engine", [2, 3])
+def test_gemm_tensor_core_engine_vs_fp64(m, n, k, transb, engine):
+    """engine=2 (tcgen05, error-compensated 3xTF32) and engine=3 (tcgen05, 2xFP16 split) must hold the same
+    fp32-level bar as the CUDA-core tiles."""
     ops = _ops()
     torch.manual_seed(m + n + k)
     a = torch.randn(m, k)
     b = torch.randn(n, k) if transb else torch.randn(k, n)
     bias = torch.randn(n)
     want = a.double() @ (b.double().t() if transb else b.double()) + bias.double()
-    got, partials = ops.gemm(a.to(DEV), b.to(DEV), transb=transb, bias=bias.to(DEV), want_stats=True, engine=2)
+    got, partials = ops.gemm(a.to(DEV), b.to(DEV), transb=transb, bias=bias.to(DEV), want_stats=True, engine=engine)
     assert_close(got, want, 5e-6, "gemm tc")   # tensor-core accumulation truncates: a few e-6, bar is 1e-5
     check_moments(partials, got.double().cpu())
     c0 = torch.randn(m, n)
-    got2 = ops.gemm(a.to(DEV), b.to(DEV), transb=transb, out=c0.to(DEV).clone(), accumulate=True, engine=2)
+    got2 = ops.gemm(a.to(DEV), b.to(DEV), transb=transb, out=c0.to(DEV).clone(), accumulate=True, engine=engine)
     assert_close(got2, want - bias.double() + c0.double(), 5e-6, "accumulate")
-    again = ops.gemm(a.to(DEV), b.to(DEV), transb=transb, bias=bias.to(DEV), engine=2)
+    again = ops.gemm(a.to(DEV), b.to(DEV), transb=transb, bias=bias.to(DEV), engine=engine)
     assert torch.equal(got, again), "tensor-core path must be deterministic"
+    if engine == 3:   # a caller-supplied max|A| (any power-of-two bracket of the true one) gives the same bits
+        amax = a.abs().max().reshape(1).to(DEV)
+        assert torch.equal(got, ops.gemm(a.to(DEV), b.to(DEV), transb=transb, bias=bias.to(DEV), engine=3, a_amax=amax))
+
+
+@pytest.mark.parametrize("scale_a,scale_b", [(1e-9, 1.0), (3e4, 1e-3), (1e-20, 1e12), (1.0, 1e-30)])
+def test_gemm_f16_split_engine_scales(scale_a, scale_b):
+    """engine=3 rescales both operands by a per-tensor power of two: tiny gradients / large activations keep
+    fp32-level (norm-relative) accuracy, and elements six orders of magnitude below the maximum keep row accuracy."""
+    ops = _ops()
+    torch.manual_seed(11)
+    m, n, k = 3000, 128, 256
+    a, b = torch.randn(m, k) * scale_a, torch.randn(n, k) * scale_b
+    got = ops.gemm(a.to(DEV), b.to(DEV), engine=3)
+    assert_close(got, a.double() @ b.double().t(), 5e-6, "scaled operands")
+    rows = torch.logspace(-6, 0, m).reshape(-1, 1)
+    a2 = a * rows
+    got = ops.gemm(a2.to(DEV), b.to(DEV), engine=3)
+    want = a2.double() @ b.double().t()
+    row_err = ((got.cpu().double() - want).abs().max(1)[0] / want.abs().max(1)[0]).max().item()
+    assert row_err <= 1e-5, f"row-relative error {row_err:.2e}"
+    g = torch.randn(m, n) * scale_b
+    got = ops.gemm_tn(g.to(DEV), a.to(DEV), engine=3)
+    assert_close(got, g.double().t() @ a.double(), 5e-6, "scaled operands (tn)")
 
 
 def test_gemm_tensor_core_prologue_and_wide_dynamic_range():
@@ -317,16 +343,17 @@ def test_gemm_tensor_core_prologue_and_wide_dynamic_range():
 
 @pytest.mark.parametrize("m,n,k", [(5000, 128, 64), (4097, 64, 32), (30000, 256, 256), (2500, 132, 72), (100000, 512, 256),
                                    (70000, 256, 512), (300, 16, 4), (9000, 64, 128)])
-def test_gemm_tn_tensor_core_engine(m, n, k):
-    """Weight gradient on tcgen05 (MN-major operands, split over vertices, fixed-order reduce)."""
+@pytest.mark.parametrize("engine", [2, 3])
+def test_gemm_tn_tensor_core_engine(m, n, k, engine):
+    """Weight gradient on tcgen05 (split over vertices, fixed-order reduce): 3xTF32 and 2xFP16-split engines."""
     ops = _ops()
     torch.manual_seed(m + k)
     g, a = torch.randn(m, n), torch.randn(m, k)
     want = g.double().t() @ a.double()
-    got = ops.gemm_tn(g.to(DEV), a.to(DEV), engine=2)
+    got = ops.gemm_tn(g.to(DEV), a.to(DEV), engine=engine)
     assert_close(got, want, 5e-6, "gemm_tn tc")
-    assert torch.equal(got, ops.gemm_tn(g.to(DEV), a.to(DEV), engine=2)), "must be deterministic"
-    acc = ops.gemm_tn(g.to(DEV), a.to(DEV), out=got.clone(), accumulate=True, engine=2)
+    assert torch.equal(got, ops.gemm_tn(g.to(DEV), a.to(DEV), engine=engine)), "must be deterministic"
+    acc = ops.gemm_tn(g.to(DEV), a.to(DEV), out=got.clone(), accumulate=True, engine=engine)
     assert_close(acc, 2 * want, 5e-6, "accumulate")
 
 
