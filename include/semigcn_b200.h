@@ -100,13 +100,15 @@ SGB_API int sgb_graph_build(const int64_t* edge_index, int64_t nnz, int64_t n, i
  *    laid out [sgb_spmm_stat_rows(n, c)][3][c]; feeds sgb_bn_finalize (Chan merge).
  *    Replaces MessagePassing.propagate (index_select -> mul -> scatter_add), fwd and,
  *    called with the transpose CSR, bwd.
+ *    amax_out (optional, device float zeroed by the caller) receives max |Y| (atomicMax on the float
+ *    bits): the scale of the fp16-split GEMM engine that consumes Y (sgb_gemm a_amax), for free.
  * ------------------------------------------------------------------------------------ */
 SGB_API int sgb_spmm_stat_rows(int64_t n, int c);
 SGB_API int sgb_spmm(const int32_t* rowptr, const sgb_edge_t* edges, const float* dis, int mode,
              const float* x, int64_t ldx, int64_t n, int c,
              const float* in_mean, const float* in_scale, const float* in_shift, float slope,
              float alpha, const float* addend, int64_t ld_addend, float beta,
-             const float* bias, float* y, int64_t ldy, float* stat_partials, void* stream);
+             const float* bias, float* y, int64_t ldy, float* stat_partials, float* amax_out, void* stream);
 
 /* Vertex-partitioned variant (one mesh over several GPUs): rows [0, n) are the
  * vertices this rank owns; neighbour ids >= n_split address the halo block x_ghost (rows received
@@ -115,7 +117,7 @@ SGB_API int sgb_spmm_halo(const int32_t* rowptr, const sgb_edge_t* edges, const 
                   const float* x, int64_t ldx, int64_t n, int c, const float* x_ghost, int64_t ld_ghost, int64_t n_split,
                   const float* in_mean, const float* in_scale, const float* in_shift, float slope,
                   float alpha, const float* addend, int64_t ld_addend, float beta,
-                  const float* bias, float* y, int64_t ldy, float* stat_partials, void* stream);
+                  const float* bias, float* y, int64_t ldy, float* stat_partials, float* amax_out, void* stream);
 /* out[k, :] = x[idx[k], :] (halo pack; also MeshUnpool-style row gathers), c floats per row */
 SGB_API int sgb_gather_rows(const float* x, int64_t ldx, const int32_t* idx, int64_t count, int c, float* out, int64_t ldo, void* stream);
 
@@ -173,7 +175,7 @@ SGB_API int sgb_bn_finalize(const float* partials, int rows, int c, int64_t coun
                     float* running_mean, float* running_var,
                     float* mean, float* invstd, float* scale, float* shift, void* stream);
 SGB_API int sgb_bn_act_apply(const float* y, int64_t ldy, int64_t m, int c, const float* mean, const float* scale,
-                     const float* shift, float slope, float* z, int64_t ldz, void* stream);
+                     const float* shift, float slope, float* z, int64_t ldz, float* amax_out /* optional: max |Z| */, void* stream);
 /* partials[rows][2][c]: (sum dA, sum dA*xhat) with dA = dZ * lrelu'((Y-mean)*scale+shift) */
 SGB_API int sgb_bn_act_bwd_reduce(const float* dz, int64_t lddz, const float* y, int64_t ldy, int64_t m, int c,
                           const float* scale, const float* shift, const float* mean, const float* invstd,
@@ -184,7 +186,8 @@ SGB_API int sgb_bn_bwd_finalize(const float* partials, int rows, int c, float* s
                         float* dbeta, int accumulate, void* stream);
 SGB_API int sgb_bn_act_bwd_apply(const float* dz, int64_t lddz, const float* y, int64_t ldy, int64_t m, int c,
                          const float* scale, const float* shift, const float* mean, const float* invstd,
-                         const float* sums, float slope, int training, float* dy, int64_t lddy, void* stream);
+                         const float* sums, float slope, int training, float* dy, int64_t lddy,
+                         float* amax_out /* optional: max |dY| */, void* stream);
 
 /* ------------------------------------------------------------------------------------ *
  * 5. Step-path mesh losses as fused gather/reduce kernels (fp64 accumulation, deterministic).

@@ -31,9 +31,9 @@ SIGNATURES = {
     "sgb_graph_build": (_i32, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sgb_spmm_stat_rows": (_i32, [_i64, _i32]),
     "sgb_spmm": (_i32, [_vp, _vp, _vp, _i32, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _f32, _f32, _vp, _i64, _f32,
-                        _vp, _vp, _i64, _vp, _vp]),
+                        _vp, _vp, _i64, _vp, _vp, _vp]),
     "sgb_spmm_halo": (_i32, [_vp, _vp, _vp, _i32, _vp, _i64, _i64, _i32, _vp, _i64, _i64, _vp, _vp, _vp, _f32, _f32, _vp, _i64, _f32,
-                             _vp, _vp, _i64, _vp, _vp]),
+                             _vp, _vp, _i64, _vp, _vp, _vp]),
     "sgb_gather_rows": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
     "sgb_gemm_stat_rows": (_i32, [_i64]),
     "sgb_gemm_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
@@ -46,11 +46,11 @@ SIGNATURES = {
     "sgb_col_stat_rows": (_i32, [_i64, _i32]),
     "sgb_col_stats": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp]),
     "sgb_bn_finalize": (_i32, [_vp, _i32, _i32, _i64, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "sgb_bn_act_apply": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _f32, _vp, _i64, _vp]),
+    "sgb_bn_act_apply": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _f32, _vp, _i64, _vp, _vp]),
     "sgb_bn_act_bwd_reduce": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _f32, _vp, _vp]),
     "sgb_bn_bwd_finalize": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp]),
     "sgb_bn_act_bwd_apply": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _i32,
-                                    _vp, _i64, _vp]),
+                                    _vp, _i64, _vp, _vp]),
     "sgb_loss_partial_rows": (_i32, []),
     "sgb_incidence_build_workspace_bytes": (_sz, [_i64, _i64]),
     "sgb_incidence_build": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),

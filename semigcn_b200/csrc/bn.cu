@@ -244,73 +244,110 @@ __global__ void __launch_bounds__(1024) k_finalize(const FinArgs f) {
 }
 
 // ---- elementwise ------------------------------------------------------------------------
+// A thread keeps its VEC channels for the whole kernel (per-channel parameters live in registers, loaded once)
+// and walks rows with a grid stride: `tpr` threads cover one row chunk, 256 / tpr rows per CTA pass.
+constexpr int kEwThreads = 256;
+
+static int ew_tpr(int c, int vec) {
+    int lanes = (c + vec - 1) / vec;
+    int p = 1;
+    while (p < lanes && p < kEwThreads) p <<= 1;
+    return p;
+}
+
 template <int VEC>
-__global__ void k_bn_act_apply(const float* __restrict__ y, int64_t ldy, int64_t m, int c, const float* __restrict__ mean,
-                               const float* __restrict__ scale, const float* __restrict__ shift, float slope,
-                               float* __restrict__ z, int64_t ldz) {
-    const int cv = c / VEC;
-    const int64_t total = m * cv;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / cv;
-        const int ch = (int)(i % cv) * VEC;
-        if (VEC == 4) {
-            const float4 v = ldg4(y + r * ldy + ch), mu = ldg4(mean + ch), s = ldg4(scale + ch), b = ldg4(shift + ch);
-            float4 o;
-            o.x = bn_lrelu(v.x, mu.x, s.x, b.x, slope); o.y = bn_lrelu(v.y, mu.y, s.y, b.y, slope);
-            o.z = bn_lrelu(v.z, mu.z, s.z, b.z, slope); o.w = bn_lrelu(v.w, mu.w, s.w, b.w, slope);
-            st4(z + r * ldz + ch, o);
-        } else {
-            z[r * ldz + ch] = bn_lrelu(__ldg(y + r * ldy + ch), __ldg(mean + ch), __ldg(scale + ch), __ldg(shift + ch), slope);
+__global__ void __launch_bounds__(kEwThreads) k_bn_act_apply(const float* __restrict__ y, int64_t ldy, int64_t m, int c, const float* __restrict__ mean,
+                                                             const float* __restrict__ scale, const float* __restrict__ shift, float slope,
+                                                             float* __restrict__ z, int64_t ldz, float* __restrict__ amax, int tpr) {
+    __shared__ uint32_t s_amax[32];
+    float amx = 0.f;
+    const int cl = threadIdx.x % tpr, rl = threadIdx.x / tpr, rpp = kEwThreads / tpr;
+    for (int c0 = 0; c0 < c; c0 += tpr * VEC) {
+        const int ch = c0 + cl * VEC;
+        if (ch >= c) continue;
+        float mu[VEC], sc[VEC], sh[VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) { mu[q] = __ldg(mean + ch + q); sc[q] = __ldg(scale + ch + q); sh[q] = __ldg(shift + ch + q); }
+        for (int64_t r = (int64_t)blockIdx.x * rpp + rl; r < m; r += (int64_t)gridDim.x * rpp) {
+            if (VEC == 4) {
+                const float4 v = ldg4(y + r * ldy + ch);
+                float4 o;
+                o.x = bn_lrelu(v.x, mu[0], sc[0], sh[0], slope); o.y = bn_lrelu(v.y, mu[1], sc[1], sh[1], slope);
+                o.z = bn_lrelu(v.z, mu[2], sc[2], sh[2], slope); o.w = bn_lrelu(v.w, mu[3], sc[3], sh[3], slope);
+                st4(z + r * ldz + ch, o);
+                amx = fmaxf(amx, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+            } else {
+                const float o = bn_lrelu(__ldg(y + r * ldy + ch), mu[0], sc[0], sh[0], slope);
+                z[r * ldz + ch] = o;
+                amx = fmaxf(amx, fabsf(o));
+            }
         }
     }
+    if (amax) publish_amax(amx, s_amax, amax);
 }
 
 struct BwdArgs {
     const float* dz; int64_t lddz; const float* y; int64_t ldy; int64_t m; int c;
     const float* scale; const float* shift; const float* mean; const float* invstd; const float* sums;
-    float slope; int training; float* dy; int64_t lddy;
+    float slope; int training; float* dy; int64_t lddy; float* amax;
 };
 
 template <int VEC>
-__global__ void k_bn_act_bwd_apply(const BwdArgs a) {
-    const int cv = a.c / VEC;
-    const int64_t total = a.m * cv;
+__global__ void __launch_bounds__(kEwThreads) k_bn_act_bwd_apply(const BwdArgs a, int tpr) {
+    __shared__ uint32_t s_amax[32];
+    float amx = 0.f;
     const float inv_m = 1.0f / (float)a.m;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / cv;
-        const int ch = (int)(i % cv) * VEC;
-        float yv[VEC], dv[VEC], out[VEC];
-        if (VEC == 4) {
-            float4 t = ldg4(a.y + r * a.ldy + ch), u = ldg4(a.dz + r * a.lddz + ch);
-            yv[0] = t.x; yv[1] = t.y; yv[2] = t.z; yv[3] = t.w;
-            dv[0] = u.x; dv[1] = u.y; dv[2] = u.z; dv[3] = u.w;
-        } else {
-            yv[0] = __ldg(a.y + r * a.ldy + ch);
-            dv[0] = __ldg(a.dz + r * a.lddz + ch);
-        }
+    const int cl = threadIdx.x % tpr, rl = threadIdx.x / tpr, rpp = kEwThreads / tpr;
+    for (int c0 = 0; c0 < a.c; c0 += tpr * VEC) {
+        const int ch = c0 + cl * VEC;
+        if (ch >= a.c) continue;
+        float mu[VEC], sc[VEC], sh[VEC], is[VEC], sb[VEC], sg[VEC];
 #pragma unroll
         for (int q = 0; q < VEC; ++q) {
-            const float sc = __ldg(a.scale + ch + q), sh = __ldg(a.shift + ch + q);
-            const float ctr = yv[q] - __ldg(a.mean + ch + q);
-            const float pre = fmaf(ctr, sc, sh);
-            const float da = pre > 0.f ? dv[q] : dv[q] * a.slope;
+            mu[q] = __ldg(a.mean + ch + q); sc[q] = __ldg(a.scale + ch + q); sh[q] = __ldg(a.shift + ch + q);
+            is[q] = 0.f; sb[q] = 0.f; sg[q] = 0.f;
             if (a.training) {
-                const float xh = ctr * __ldg(a.invstd + ch + q);
-                const float sb = __ldg(a.sums + ch + q) * inv_m, sg = __ldg(a.sums + a.c + ch + q) * inv_m;
-                out[q] = sc * (da - sb - xh * sg);
-            } else {
-                out[q] = sc * da;
+                is[q] = __ldg(a.invstd + ch + q);
+                sb[q] = __ldg(a.sums + ch + q) * inv_m;
+                sg[q] = __ldg(a.sums + a.c + ch + q) * inv_m;
             }
         }
-        if (VEC == 4) st4(a.dy + r * a.lddy + ch, make_float4(out[0], out[1], out[2], out[3]));
-        else a.dy[r * a.lddy + ch] = out[0];
+        for (int64_t r = (int64_t)blockIdx.x * rpp + rl; r < a.m; r += (int64_t)gridDim.x * rpp) {
+            float yv[VEC], dv[VEC], out[VEC];
+            if (VEC == 4) {
+                float4 t = ldg4(a.y + r * a.ldy + ch), u = ldg4(a.dz + r * a.lddz + ch);
+                yv[0] = t.x; yv[1] = t.y; yv[2] = t.z; yv[3] = t.w;
+                dv[0] = u.x; dv[1] = u.y; dv[2] = u.z; dv[3] = u.w;
+            } else {
+                yv[0] = __ldg(a.y + r * a.ldy + ch);
+                dv[0] = __ldg(a.dz + r * a.lddz + ch);
+            }
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) {
+                const float ctr = yv[q] - mu[q];
+                const float pre = fmaf(ctr, sc[q], sh[q]);
+                const float da = pre > 0.f ? dv[q] : dv[q] * a.slope;
+                if (a.training) {
+                    const float xh = ctr * is[q];
+                    out[q] = sc[q] * (da - sb[q] - xh * sg[q]);
+                } else {
+                    out[q] = sc[q] * da;
+                }
+                amx = fmaxf(amx, fabsf(out[q]));
+            }
+            if (VEC == 4) st4(a.dy + r * a.lddy + ch, make_float4(out[0], out[1], out[2], out[3]));
+            else a.dy[r * a.lddy + ch] = out[0];
+        }
     }
+    if (a.amax) publish_amax(amx, s_amax, a.amax);
 }
 
-static int ew_grid(int64_t total) {
-    int64_t g = ceil_div(total > 0 ? total : 1, 256);
-    int64_t cap = (int64_t)num_sms() * 16;
-    return (int)(g < cap ? g : cap);
+static int ew_grid(int64_t m, int tpr) {
+    const int rpp = kEwThreads / tpr;
+    int64_t g = ceil_div(m > 0 ? m : 1, (int64_t)rpp * 4);   // >= 4 rows per row-lane
+    int64_t cap = (int64_t)num_sms() * 8;
+    g = g < cap ? g : cap;
+    return (int)(g < 1 ? 1 : g);
 }
 
 }  // namespace sgb
@@ -344,12 +381,13 @@ extern "C" int sgb_bn_finalize(const float* partials, int rows, int c, int64_t c
 }
 
 extern "C" int sgb_bn_act_apply(const float* y, int64_t ldy, int64_t m, int c, const float* mean, const float* scale,
-                                const float* shift, float slope, float* z, int64_t ldz, void* stream) {
+                                const float* shift, float slope, float* z, int64_t ldz, float* amax_out, void* stream) {
     SGB_CHECK_ARG(y && z && mean && scale && shift && m >= 0 && c > 0 && ldy >= c && ldz >= c, "sgb_bn_act_apply: bad argument");
     if (m == 0) return SGB_OK;
     bool vec = c % 4 == 0 && al16(y) && al16(z) && al16(mean) && al16(scale) && al16(shift) && ldy % 4 == 0 && ldz % 4 == 0;
-    if (vec) k_bn_act_apply<4><<<ew_grid(m * (c / 4)), 256, 0, (cudaStream_t)stream>>>(y, ldy, m, c, mean, scale, shift, slope, z, ldz);
-    else k_bn_act_apply<1><<<ew_grid(m * c), 256, 0, (cudaStream_t)stream>>>(y, ldy, m, c, mean, scale, shift, slope, z, ldz);
+    const int tpr = ew_tpr(c, vec ? 4 : 1);
+    if (vec) k_bn_act_apply<4><<<ew_grid(m, tpr), kEwThreads, 0, (cudaStream_t)stream>>>(y, ldy, m, c, mean, scale, shift, slope, z, ldz, amax_out, tpr);
+    else k_bn_act_apply<1><<<ew_grid(m, tpr), kEwThreads, 0, (cudaStream_t)stream>>>(y, ldy, m, c, mean, scale, shift, slope, z, ldz, amax_out, tpr);
     SGB_CHECK_LAUNCH("k_bn_act_apply");
     return SGB_OK;
 }
@@ -378,15 +416,16 @@ extern "C" int sgb_bn_bwd_finalize(const float* partials, int rows, int c, float
 
 extern "C" int sgb_bn_act_bwd_apply(const float* dz, int64_t lddz, const float* y, int64_t ldy, int64_t m, int c, const float* scale,
                                     const float* shift, const float* mean, const float* invstd, const float* sums, float slope,
-                                    int training, float* dy, int64_t lddy, void* stream) {
+                                    int training, float* dy, int64_t lddy, float* amax_out, void* stream) {
     SGB_CHECK_ARG(dz && y && dy && scale && shift && m >= 0 && c > 0 && ldy >= c && lddz >= c && lddy >= c,
                   "sgb_bn_act_bwd_apply: bad argument");
     SGB_CHECK_ARG(mean && (!training || (invstd && sums)), "sgb_bn_act_bwd_apply: mean required; training mode also needs invstd/sums");
     if (m == 0) return SGB_OK;
-    BwdArgs a{dz, lddz, y, ldy, m, c, scale, shift, mean, invstd, sums, slope, training, dy, lddy};
+    BwdArgs a{dz, lddz, y, ldy, m, c, scale, shift, mean, invstd, sums, slope, training, dy, lddy, amax_out};
     bool vec = c % 4 == 0 && al16(y) && al16(dz) && al16(dy) && ldy % 4 == 0 && lddz % 4 == 0 && lddy % 4 == 0;
-    if (vec) k_bn_act_bwd_apply<4><<<ew_grid(m * (c / 4)), 256, 0, (cudaStream_t)stream>>>(a);
-    else k_bn_act_bwd_apply<1><<<ew_grid(m * c), 256, 0, (cudaStream_t)stream>>>(a);
+    const int tpr = ew_tpr(c, vec ? 4 : 1);
+    if (vec) k_bn_act_bwd_apply<4><<<ew_grid(m, tpr), kEwThreads, 0, (cudaStream_t)stream>>>(a, tpr);
+    else k_bn_act_bwd_apply<1><<<ew_grid(m, tpr), kEwThreads, 0, (cudaStream_t)stream>>>(a, tpr);
     SGB_CHECK_LAUNCH("k_bn_act_bwd_apply");
     return SGB_OK;
 }

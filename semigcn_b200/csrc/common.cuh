@@ -80,6 +80,20 @@ __device__ __forceinline__ Moments from_shifted(float n, float p, float s1, floa
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+// max |x| of a produced tensor, published for the fp16-split GEMM engine that consumes it (sgb_gemm a_amax):
+// per-thread running maximum -> warp -> CTA -> one atomicMax on the float bits (non-negative floats order like
+// unsigned ints; max is order-independent, so the result is deterministic).  `scratch`: >= 32 uint32 of shared memory.
+__device__ __forceinline__ void publish_amax(float mx, uint32_t* scratch, float* slot) {
+    uint32_t b = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
+    const int warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if ((threadIdx.x & 31) == 0) scratch[warp] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < nw; ++w) b = max(b, scratch[w]);
+        if (b) atomicMax(reinterpret_cast<uint32_t*>(slot), b);
+    }
+}
+
 // arguments of the dense transform C (+)= f(A) op(B) + bias (see sgb_gemm)
 struct GemmArgs {
     int transb;

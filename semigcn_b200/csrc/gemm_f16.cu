@@ -133,7 +133,15 @@ __global__ void __launch_bounds__(256) k_prep_weights_f16(const float* __restric
     __shared__ float sm[8];
     const int rows = transb ? n : k, cols = transb ? k : n;
     float mx = 0.f;
-    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) mx = fmaxf(mx, fabsf(w[(int64_t)(i / cols) * ldw + (i % cols)]));
+    if (ldw == cols && (reinterpret_cast<uintptr_t>(w) & 15) == 0 && ((rows * cols) & 3) == 0) {       // dense, aligned: flat 128-bit scan
+        for (int i = threadIdx.x; i < (rows * cols) >> 2; i += blockDim.x) {
+            const float4 v = ldg4(w + 4 * i);
+            mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        }
+    } else {
+        for (int r = 0; r < rows; ++r)
+            for (int i = threadIdx.x; i < cols; i += blockDim.x) mx = fmaxf(mx, fabsf(w[(int64_t)r * ldw + i]));
+    }
     mx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mx)));
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
     __syncthreads();
@@ -634,7 +642,7 @@ int gemm_f16_launch(const GemmArgs& g, const float* a_amax, void* ws, size_t ws_
         if (rc != SGB_OK) return rc;
         a_amax = hdr + 2;
     }
-    k_prep_weights_f16<<<32, 256, 0, stream>>>(g.b, g.ldb, g.transb, g.n, g.k, p.bn, p.n_tiles, p.k_chunks, reinterpret_cast<__half*>(img), hdr);
+    k_prep_weights_f16<<<num_sms(), 256, 0, stream>>>(g.b, g.ldb, g.transb, g.n, g.k, p.bn, p.n_tiles, p.k_chunks, reinterpret_cast<__half*>(img), hdr);
     SGB_CHECK_LAUNCH("k_prep_weights_f16");
     static thread_local bool attr_set = false;
     if (!attr_set) {

@@ -77,6 +77,7 @@ struct SpmmArgs {
     const float* xg;                  // ghost rows (vertex-partitioned mode): neighbour ids >= split read xg[(id - split)]
     int64_t ldxg;
     int32_t split;                    // INT32_MAX when there are no ghost rows
+    float* amax;                      // optional: max |y| (atomicMax on the float bits; caller zeroes it)
 };
 
 // A warp owns "runs" of VPW consecutive vertices; run r of the grid goes to warp (r mod total warps), so the
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(kSpmmThreads, (VEC * ITERS >= 8) ? (STATS ? SG
         // statistics: pivot-shifted sums per thread (pivot = first value seen), see common.cuh
         float s1[ITERS][VEC], s2[ITERS][VEC], pv[ITERS][VEC];
         float nseen = 0.f;
+        float amx = 0.f;
 #pragma unroll
         for (int t = 0; t < ITERS; ++t)
 #pragma unroll
@@ -283,6 +285,10 @@ __global__ void __launch_bounds__(kSpmmThreads, (VEC * ITERS >= 8) ? (STATS ? SG
                             for (int q = 0; q < VEC; ++q) out.v[q] = __fadd_rn(out.v[q], bs.v[q]);
                         }
                         out.store(a.y + v * a.ldy + ch[t]);
+                        if (a.amax) {
+#pragma unroll
+                            for (int q = 0; q < VEC; ++q) amx = fmaxf(amx, fabsf(out.v[q]));
+                        }
                         if (STATS) {
 #pragma unroll
                             for (int q = 0; q < VEC; ++q) {
@@ -302,6 +308,11 @@ __global__ void __launch_bounds__(kSpmmThreads, (VEC * ITERS >= 8) ? (STATS ? SG
             stage_rowptr(ri + 2, buf);
         }
         cp_async_commit_wait_all();
+        if (a.amax) {
+            __syncthreads();                                  // all warps are done with their staging buffers
+            publish_amax(amx, reinterpret_cast<uint32_t*>(smem_raw), a.amax);
+            __syncthreads();
+        }
         if (STATS) {   // fixed-order block merge (Chan) -> partials[blockIdx.x][3][c] = (count, mean, M2)
             constexpr int GROUPS = kSpmmThreads / LPV;
             float* red0 = reinterpret_cast<float*>(smem_raw);
@@ -389,16 +400,16 @@ extern "C" int sgb_spmm(const int32_t* rowptr, const sgb_edge_t* edges, const fl
                         const float* x, int64_t ldx, int64_t n, int c,
                         const float* in_mean, const float* in_scale, const float* in_shift, float slope,
                         float alpha, const float* addend, int64_t ld_addend, float beta,
-                        const float* bias, float* y, int64_t ldy, float* stat_partials, void* stream_) {
+                        const float* bias, float* y, int64_t ldy, float* stat_partials, float* amax_out, void* stream_) {
     return sgb_spmm_halo(rowptr, edges, dis, mode, x, ldx, n, c, nullptr, 0, n, in_mean, in_scale, in_shift, slope, alpha, addend, ld_addend,
-                         beta, bias, y, ldy, stat_partials, stream_);
+                         beta, bias, y, ldy, stat_partials, amax_out, stream_);
 }
 
 extern "C" int sgb_spmm_halo(const int32_t* rowptr, const sgb_edge_t* edges, const float* dis, int mode,
                              const float* x, int64_t ldx, int64_t n, int c, const float* x_ghost, int64_t ld_ghost, int64_t n_split,
                              const float* in_mean, const float* in_scale, const float* in_shift, float slope,
                              float alpha, const float* addend, int64_t ld_addend, float beta,
-                             const float* bias, float* y, int64_t ldy, float* stat_partials, void* stream_) {
+                             const float* bias, float* y, int64_t ldy, float* stat_partials, float* amax_out, void* stream_) {
     using namespace sgb;
     cudaStream_t stream = (cudaStream_t)stream_;
     SGB_CHECK_ARG(n >= 0 && c > 0, "sgb_spmm: bad shape n=%lld c=%d", (long long)n, c);
@@ -426,7 +437,7 @@ extern "C" int sgb_spmm_halo(const int32_t* rowptr, const sgb_edge_t* edges, con
     const bool pro = in_scale != nullptr, st = stat_partials != nullptr, halo = x_ghost != nullptr;
     if (!pro) slope = 1.f;            // the general instantiation applies lrelu((x - 0) * 1 + 0, slope): identity
     SpmmArgs a{rowptr, reinterpret_cast<const int2*>(edges), dis, mode, x, ldx, n, c, in_mean, in_scale, in_shift, slope, alpha, addend, ld_addend, beta, bias, y, ldy, stat_partials,
-               x_ghost, ld_ghost, x_ghost ? (int32_t)n_split : (int32_t)0x7fffffff};
+               x_ghost, ld_ghost, x_ghost ? (int32_t)n_split : (int32_t)0x7fffffff, amax_out};
     // the BatchNorm prologue and the halo block are rare operands: they share one (slower, fully general) instantiation
 #define SGB_SPMM_CASE(L, V, I)                                                                                  \
     if (k.lpv == L && k.vec == V && k.iters == I) {                                                             \

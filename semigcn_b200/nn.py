@@ -131,8 +131,10 @@ class ChebConv(nn.Module):
 # fused block: conv (+ BatchNorm1d + LeakyReLU)
 # ----------------------------------------------------------------------------------------
 class _BlockCfg:
-    def __init__(self, kind: str, bn: Optional[nn.BatchNorm1d], slope: float):
+    def __init__(self, kind: str, bn: Optional[nn.BatchNorm1d], slope: float, x_amax: Optional[Tensor] = None):
         self.kind, self.bn, self.slope = kind, bn, slope
+        self.x_amax = x_amax          # in:  device scalar max|x| if the producer of x published one (ops.amax_of)
+        self.out_amax = None          # out: device scalar max|z| of the block output (set by ConvBlockFn.forward)
 
 
 class ConvBlockFn(torch.autograd.Function):
@@ -151,33 +153,43 @@ class ConvBlockFn(torch.autograd.Function):
         training = bn is not None and (bn.training or bn.running_mean is None)
         want_stats = training
         saved_ops: List[Tensor] = []
+        # device scalars max|operand| for the fp16-split GEMM engine, published by the kernels that write the operands
+        am = ops.new_amax(x.device, 4)
+        x_amax = cfg.x_amax
         if cfg.kind == "gcn":
             (w,) = weights
             cout, cin = w.shape
             agg_first = cin <= cout
             if agg_first:
-                p = ops.spmm(graph, x)
-                r = ops.gemm(p, w, transb=True, bias=bias, want_stats=want_stats)
+                p = ops.spmm(graph, x, amax_out=am[0:1])
+                r = ops.gemm(p, w, transb=True, bias=bias, want_stats=want_stats, a_amax=am[0:1])
                 saved_ops = [p]
+                ctx.op_amax = [am[0:1]]
             else:
-                h = ops.gemm(x, w, transb=True)
+                h = ops.gemm(x, w, transb=True, a_amax=x_amax)
                 r = ops.spmm(graph, h, bias=bias, want_stats=want_stats)
                 saved_ops = [x]
+                ctx.op_amax = [x_amax]
             ctx.agg_first = agg_first
         else:
             ts = [x]
+            amx = [x_amax]
             if len(weights) > 1:
-                ts.append(ops.spmm(graph, x))
+                ts.append(ops.spmm(graph, x, amax_out=am[0:1]))
+                amx.append(am[0:1])
             for k in range(2, len(weights)):
-                ts.append(ops.spmm(graph, ts[k - 1], alpha=2.0, addend=ts[k - 2], beta=-1.0))
+                slot = am[1:2] if k == 2 else ops.new_amax(x.device)
+                ts.append(ops.spmm(graph, ts[k - 1], alpha=2.0, addend=ts[k - 2], beta=-1.0, amax_out=slot))
+                amx.append(slot)
             y = None
             r = None
             for k, w in enumerate(weights):
                 last = k == len(weights) - 1
                 r = ops.gemm(ts[k], w, transb=True, bias=bias if last else None, out=y, accumulate=k > 0,
-                             want_stats=want_stats and last)
+                             want_stats=want_stats and last, a_amax=amx[k])
                 y = r[0] if isinstance(r, tuple) else r
             saved_ops = ts
+            ctx.op_amax = amx
         y, partials = r if want_stats else (r, None)
 
         ctx.graph, ctx.cfg, ctx.nw, ctx.has_bias = graph, cfg, len(weights), bias is not None
@@ -197,7 +209,8 @@ class ConvBlockFn(torch.autograd.Function):
                                                          comm=graph.comm)
         else:
             mean, invstd, scale, shift = ops.eval_affine(bn.running_mean, bn.running_var, gamma, beta, bn.eps)
-        z = ops.bn_act_apply(y, mean, scale, shift, cfg.slope)
+        z = ops.bn_act_apply(y, mean, scale, shift, cfg.slope, amax_out=am[3:4])
+        cfg.out_amax = am[3:4]
         ctx.bn_mode = 2 if training else 1
         ctx.has_affine = gamma is not None
         ctx.save_for_backward(*weights, *saved_ops, y, scale, shift, mean, invstd)
@@ -210,43 +223,54 @@ class ConvBlockFn(torch.autograd.Function):
         weights = saved[:nw]
         dgamma = dbeta = None
         dz = dz.contiguous()
+        am = ops.new_amax(dz.device, 2)
+        dy_amax = None
         if ctx.bn_mode == 0:
             saved_ops = saved[nw:]
             dy = dz
         else:
             saved_ops = saved[nw:-5]
             y, scale, shift, mean, invstd = saved[-5:]
+            dy_amax = am[0:1]
             dy, dgamma, dbeta = ops.bn_act_bwd(dz, y, scale, shift, mean, invstd, cfg.slope, ctx.bn_mode == 2,
-                                               comm=graph.comm, n_global=graph.n_global)
+                                               comm=graph.comm, n_global=graph.n_global, amax_out=dy_amax)
             if not ctx.has_affine:
                 dgamma = dbeta = None
         need_x = ctx.needs_input_grad[0]
-        db = ops.colsum(dy) if (ctx.has_bias and ctx.needs_input_grad[3]) else None
+        db = None
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            if ctx.bn_mode == 2:
+                # training-mode BatchNorm removes the batch mean, so sum_rows dY is identically zero (dY = scale *
+                # (dA - mean(dA) - xhat * mean(dA * xhat)) and sum xhat = 0): the gradient of a conv bias in front of
+                # BatchNorm is exactly 0 (the reference holds fp32 rounding noise there).  No reduction pass needed.
+                db = torch.zeros(dy.shape[1], dtype=dy.dtype, device=dy.device)
+            else:
+                db = ops.colsum(dy)
         dws: List[Optional[Tensor]] = [None] * nw
         dx = None
         if cfg.kind == "gcn":
             (w,) = weights
             if ctx.agg_first:
                 (p,) = saved_ops
-                dws[0] = ops.gemm_tn(dy, p)
+                dws[0] = ops.gemm_tn(dy, p, g_amax=dy_amax, a_amax=ctx.op_amax[0])
                 if need_x:
-                    dp = ops.gemm(dy, w, transb=False)
+                    dp = ops.gemm(dy, w, transb=False, a_amax=dy_amax)
                     dx = ops.spmm(graph, dp, transpose=True)
             else:
                 (x,) = saved_ops
-                dh = ops.spmm(graph, dy, transpose=True)
-                dws[0] = ops.gemm_tn(dh, x)
+                dh = ops.spmm(graph, dy, transpose=True, amax_out=am[1:2])
+                dws[0] = ops.gemm_tn(dh, x, g_amax=am[1:2], a_amax=ctx.op_amax[0])
                 if need_x:
-                    dx = ops.gemm(dh, w, transb=False)
+                    dx = ops.gemm(dh, w, transb=False, a_amax=am[1:2])
         else:
             ts = saved_ops
             for k in range(nw):
-                dws[k] = ops.gemm_tn(dy, ts[k])
+                dws[k] = ops.gemm_tn(dy, ts[k], g_amax=dy_amax, a_amax=ctx.op_amax[k])
             if need_x:
                 # g_k = dY W_k + a_k S^T g_(k+1) - g_(k+2),  a_k = 2 for k >= 1, 1 for k = 0
                 gs: List[Optional[Tensor]] = [None] * nw
                 for k in range(nw - 1, -1, -1):
-                    d = ops.gemm(dy, weights[k], transb=False)
+                    d = ops.gemm(dy, weights[k], transb=False, a_amax=dy_amax)
                     if k + 2 <= nw - 1:
                         d = torch.sub(d, gs[k + 2], out=d)
                     if k + 1 <= nw - 1:
@@ -321,11 +345,14 @@ class Sequential(nn.Module):
                 _check_inputs(x, edge_index, mod.in_channels)
                 if isinstance(mod, GCNConv):
                     g = ops.graph_for(edge_index, x.shape[0], MODE_GCN)
-                    out = ConvBlockFn.apply(x, g, _BlockCfg("gcn", bn, slope), mod.bias, bn.weight, bn.bias, mod.lin.weight)
+                    cfg = _BlockCfg("gcn", bn, slope, ops.amax_of(x))
+                    out = ConvBlockFn.apply(x, g, cfg, mod.bias, bn.weight, bn.bias, mod.lin.weight)
                 else:
                     g = ops.graph_for(edge_index, x.shape[0], MODE_CHEB)
-                    out = ConvBlockFn.apply(x, g, _BlockCfg("cheb", bn, slope), mod.bias, bn.weight, bn.bias,
-                                            *[l.weight for l in mod.lins])
+                    cfg = _BlockCfg("cheb", bn, slope, ops.amax_of(x))
+                    out = ConvBlockFn.apply(x, g, cfg, mod.bias, bn.weight, bn.bias, *[l.weight for l in mod.lins])
+                if cfg.out_amax is not None:
+                    setattr(out, ops.AMAX_ATTR, cfg.out_amax)      # the next block's transform reads it (same tensor object)
                 env[outs[0]] = out
                 i += consumed
                 continue

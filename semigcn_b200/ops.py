@@ -31,6 +31,20 @@ def _ws(nbytes: int, device) -> Tensor:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
+def new_amax(device, count: int = 1) -> Tensor:
+    """Zeroed device floats for the ``amax_out`` of a producing kernel; the filled slot is then handed to the
+    fp16-split GEMM engine as ``a_amax`` / ``g_amax`` (it spares the engine its own reduction pass)."""
+    return torch.zeros(count, dtype=torch.float32, device=device)
+
+
+AMAX_ATTR = "_sgb_amax"     # python attribute on an activation tensor: device scalar max|x| published by its producer
+
+
+def amax_of(t: Tensor) -> Optional[Tensor]:
+    a = getattr(t, AMAX_ATTR, None)
+    return a if (a is not None and a.device == t.device) else None
+
+
 # ----------------------------------------------------------------------------------------
 # graph: CSR by target (forward) and by source (backward) + dis, cached per edge_index
 # ----------------------------------------------------------------------------------------
@@ -117,7 +131,8 @@ def clear_graph_cache() -> None:
 # ----------------------------------------------------------------------------------------
 def spmm(g: MeshGraph, x: Tensor, transpose: bool = False, in_affine: Affine = None, alpha: float = 1.0,
          addend: Optional[Tensor] = None, beta: float = 0.0, bias: Optional[Tensor] = None,
-         want_stats: bool = False, out: Optional[Tensor] = None):
+         want_stats: bool = False, out: Optional[Tensor] = None, amax_out: Optional[Tensor] = None):
+    """``amax_out``: zero-initialised device float that receives max|y| (see ``new_amax``)."""
     lib = L.load()
     require_cuda(x, addend, bias)
     x = _f32c(x, "x")
@@ -143,7 +158,7 @@ def spmm(g: MeshGraph, x: Tensor, transpose: bool = False, in_affine: Affine = N
                                 ptr(xg), xg.stride(0) if xg is not None else 0, n,
                                 ptr(mu), ptr(sc), ptr(sh), float(slope), float(alpha), ptr(addend),
                                 addend.stride(0) if addend is not None else 0, float(beta), ptr(bias),
-                                ptr(y), y.stride(0), ptr(partials), stream_ptr(x.device)), "sgb_spmm")
+                                ptr(y), y.stride(0), ptr(partials), ptr(amax_out), stream_ptr(x.device)), "sgb_spmm")
     if sp is not None:
         sp.close()
     L.count(1)
@@ -263,7 +278,8 @@ def bn_finalize(partials: Tensor, count: int, gamma: Optional[Tensor], beta: Opt
     return st[0], st[1], st[2], st[3]
 
 
-def bn_act_apply(y: Tensor, mean: Tensor, scale: Tensor, shift: Tensor, slope: float, out: Optional[Tensor] = None) -> Tensor:
+def bn_act_apply(y: Tensor, mean: Tensor, scale: Tensor, shift: Tensor, slope: float, out: Optional[Tensor] = None,
+                 amax_out: Optional[Tensor] = None) -> Tensor:
     lib = L.load()
     y = _f32c(y, "y")
     m, c = y.shape
@@ -271,7 +287,7 @@ def bn_act_apply(y: Tensor, mean: Tensor, scale: Tensor, shift: Tensor, slope: f
     sp = _prof.span(f"bn_act_apply_c{c}", 8.0 * m * c) if _prof.ACTIVE is not None else None
     with torch.cuda.device(y.device):
         check(lib.sgb_bn_act_apply(ptr(y), y.stride(0), m, c, ptr(mean), ptr(scale), ptr(shift), float(slope), ptr(z), z.stride(0),
-                                   stream_ptr(y.device)), "sgb_bn_act_apply")
+                                   ptr(amax_out), stream_ptr(y.device)), "sgb_bn_act_apply")
     if sp is not None:
         sp.close()
     L.count(1)
@@ -279,7 +295,8 @@ def bn_act_apply(y: Tensor, mean: Tensor, scale: Tensor, shift: Tensor, slope: f
 
 
 def bn_act_bwd(dz: Tensor, y: Tensor, scale: Tensor, shift: Tensor, mean: Optional[Tensor], invstd: Optional[Tensor],
-               slope: float, training: bool, want_param_grads: bool = True, comm=None, n_global: Optional[int] = None):
+               slope: float, training: bool, want_param_grads: bool = True, comm=None, n_global: Optional[int] = None,
+               amax_out: Optional[Tensor] = None):
     """dY (and dgamma, dbeta) of Z = lrelu(BN(Y)) given dZ."""
     lib = L.load()
     dz, y = _f32c(dz, "dz"), _f32c(y, "y")
@@ -310,7 +327,7 @@ def bn_act_bwd(dz: Tensor, y: Tensor, scale: Tensor, shift: Tensor, mean: Option
                 sums = comm.all_reduce_sum(sums.clone()) * (float(m) / float(n_global))
         check(lib.sgb_bn_act_bwd_apply(ptr(dz), dz.stride(0), ptr(y), y.stride(0), m, c, ptr(scale), ptr(shift), ptr(mean),
                                        ptr(invstd), ptr(sums), float(slope), 1 if training else 0, ptr(dy), dy.stride(0),
-                                       stream_ptr(dev)), "sgb_bn_act_bwd_apply")
+                                       ptr(amax_out), stream_ptr(dev)), "sgb_bn_act_bwd_apply")
         L.count(1)
     if sp is not None:
         sp.close()

@@ -76,8 +76,10 @@ def _worker(rank, world, port, conv):
                 continue
             e = _rel(p.grad, gr)
             # BatchNorm gamma / beta gradients are column sums with heavy cancellation (sum of dA over all vertices):
-            # the reassociation across ranks shows up at 1e-3 relative; a wrong factor would be O(1)
-            tol = 2e-2 if ".module_1." in k else 2e-4
+            # the reassociation across ranks shows up at 1e-3 relative; a wrong factor would be O(1).  Weight gradients
+            # behind 7+ BatchNorm layers on a 1 002-vertex mesh carry the same fp32 noise (tools/diag_grads.py: the fp32
+            # oracle itself is 1e-3 away from the fp64 oracle there); the forward check above is the tight one.
+            tol = 2e-2 if ".module_1." in k else 5e-3
             if e / tol > worst:
                 worst, who = e / tol, f"{k} ({e:.2e})"
         assert worst <= 1.0, f"rank {rank}: parameter gradients differ at {who}"
