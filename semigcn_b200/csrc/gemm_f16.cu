@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "umma.cuh"
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace sgb {
 
@@ -98,22 +99,28 @@ __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, ui
 constexpr int kHBM = 128;                       // rows per tile == UMMA M
 constexpr int kHBK = 32;                        // K elements per pipeline stage (2 MMA k-slices of 16)
 constexpr int kHCols = kHBK / 8;                // 16-byte core-matrix columns per stage
-constexpr int kHALbo = 144;                     // bytes between K-adjacent core matrices of A (128 + 16 pad: conflict-free stores)
+constexpr int kHALbo = 160;                     // bytes between K-adjacent core matrices of A (128 + 32 pad: conflict-free 16-byte stores)
 constexpr int kHASbo = kHCols * kHALbo;         // bytes between M-adjacent core matrices of A
 constexpr int kHATile = (kHBM / 8) * kHASbo;    // per hi (or lo)
 constexpr int kHBLbo = 128;
 constexpr int kHBSbo = kHCols * kHBLbo;
-constexpr int kHProducerWarps = 8;
-constexpr int kHThreads = (kHProducerWarps + 2 + 4) * 32;
+constexpr int kHProducerWarps = 8;             // converter warps: raw fp32 (TMA) -> scaled hi/lo fp16 operand tiles
+constexpr int kHThreads = (kHProducerWarps + 2 + 4 + 1) * 32;   // converters, B copy, MMA, 4 epilogue warps, A TMA
+constexpr int kHRawBytes = kHBM * kHBK * 4;     // one raw A stage: 128 rows x 32 fp32, 128-byte rows, TMA 128B swizzle
+#ifndef SGB_F16_RAW_STAGES
+#define SGB_F16_RAW_STAGES 3
+#endif
+constexpr int kHRawStages = SGB_F16_RAW_STAGES;
 constexpr int kHMaxStages = 6;
 constexpr int kHEpiLd = 36;                     // floats per row of an epilogue warp's 32 x 32 staging tile (+4: conflict-free)
 constexpr int kHEpiBytes = 4 * 32 * kHEpiLd * 4;
 static const int kHSmemBudget = 227 * 1024;
 
 __host__ __device__ constexpr int h_b_tile_bytes(int bn) { return (bn / 8) * kHBSbo; }
-__host__ __device__ constexpr int h_stage_bytes(int bn) { return 2 * kHATile + 2 * h_b_tile_bytes(bn); }
+__host__ __device__ constexpr int h_stage_bytes(int bn) { return (2 * kHATile + 2 * h_b_tile_bytes(bn) + 1023) / 1024 * 1024; }
 
 struct HArgs {
+    CUtensorMap a_map;                // A as a [m, k] fp32 tensor, box {32, 128}, 128-byte swizzle
     const float* a; int64_t lda;
     const uint8_t* wp;                // prepped weights: [n_tiles][k_chunks][hi|lo][tile image]
     const float* wscale;              // [0] = s_W, [1] = 1 / s_W   (written by k_prep_weights_f16)
@@ -172,16 +179,21 @@ __global__ void __launch_bounds__(256) k_prep_weights_f16(const float* __restric
     }
 }
 
-__global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const HArgs g) {
+__global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant__ HArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stage_bytes = h_stage_bytes(g.bn);
     const int b_tile_bytes = h_b_tile_bytes(g.bn);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)g.stages * stage_bytes);
+    // smem: [raw ring: kHRawStages x 16 KB][operand ring: stages x stage_bytes][barriers 256 B][epilogue staging]
+    uint8_t* const raw_base = smem;
+    uint8_t* const op_base = smem + kHRawStages * kHRawBytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(op_base + (size_t)g.stages * stage_bytes);
     uint64_t* empty = full + kHMaxStages;
     uint64_t* tfull = empty + kHMaxStages;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* rfull = tempty + 2;               // raw stage landed (TMA complete_tx)
+    uint64_t* rempty = rfull + kHRawStages;     // raw stage consumed by all converter threads
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + kHRawStages);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; ++s) {
@@ -191,6 +203,10 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const HArgs g) {
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull[b], 1);
             mbar_init(&tempty[b], 4);
+        }
+        for (int s = 0; s < kHRawStages; ++s) {
+            mbar_init(&rfull[s], 1);
+            mbar_init(&rempty[s], kHProducerWarps * 32);
         }
         fence_barrier_init();
     }
@@ -204,64 +220,69 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const HArgs g) {
     const int64_t total_tiles = m_tiles * g.n_tiles;
 
     if (warp < kHProducerWarps) {
-        // ================= A producers: global -> regs (scale, hi/lo fp16) -> smem =================
+        // ================= A converters: raw fp32 stage (TMA) -> regs (scale, hi/lo fp16) -> operand stage =================
         float sa, inva;
         f16_scale_from_amax(__ldg(g.a_amax), sa, inva);
         const int ptid = threadIdx.x;                          // 0..255
-        // stage = 128 rows x kHCols core columns (8 K elements = 2 float4 each); thread: column cq, rows r0, r0 + 64
+        // stage = 128 rows x kHCols core columns (8 K elements = 32 bytes of the raw row); thread: column cq, rows r0, r0 + 64
         const int cq = ptid % kHCols, r0 = ptid / kHCols;      // r0 in 0..63
         constexpr int RPT = kHBM * kHCols / 256;               // row slots per thread (2)
         constexpr int RSTEP = 256 / kHCols;                    // 64
         const int64_t my_tiles = total_tiles > blockIdx.x ? (total_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
         const int64_t total_it = my_tiles * g.k_chunks;
-        auto issue = [&](int64_t i, float4 (&v)[RPT][2]) {
-            const int64_t tile = blockIdx.x + (i / g.k_chunks) * gridDim.x;
-            const int q = (int)(i % g.k_chunks);
-            const int64_t m0 = (tile / g.n_tiles) * kHBM;
-            const int kcol = q * kHBK + cq * 8;
+        for (int64_t it = 0; it < total_it; ++it) {
+            const int s = (int)(it % g.stages), rs = (int)(it % kHRawStages);
+            const uint32_t ph = (uint32_t)((it / g.stages) & 1), rph = (uint32_t)((it / kHRawStages) & 1);
+            mbar_wait(&rfull[rs], rph);
+            const uint8_t* raw = raw_base + (size_t)rs * kHRawBytes;
+            float4 v[RPT][2];
 #pragma unroll
-            for (int r = 0; r < RPT; ++r) {
-                const int64_t gm = m0 + r0 + RSTEP * r;
-                v[r][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-                v[r][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i < total_it && gm < g.m) {                // K % 4 == 0 guaranteed by the dispatcher
-                    if (kcol < g.k) v[r][0] = ldg4(g.a + gm * g.lda + kcol);
-                    if (kcol + 4 < g.k) v[r][1] = ldg4(g.a + gm * g.lda + kcol + 4);
-                }
+            for (int i = 0; i < RPT; ++i) {
+                const int r = r0 + RSTEP * i;
+                // 128-byte swizzle: 16-byte chunk j of row r sits at chunk position j ^ (r % 8)
+                v[i][0] = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * cq) ^ (r & 7)) << 4));
+                v[i][1] = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * cq + 1) ^ (r & 7)) << 4));
             }
-        };
-        auto process = [&](int64_t it, float4 (&v)[RPT][2]) {
-            const int s = (int)(it % g.stages);
-            const uint32_t ph = (uint32_t)((it / g.stages) & 1);
+            // convert first: the shared-memory reads must have returned before the raw slot is handed back to the TMA
+            // engine (an arrive issued right behind the loads can overtake them in the memory pipeline)
+            uint4 h[RPT], l[RPT];
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                split_f16x2(v[i][0].x * sa, v[i][0].y * sa, h[i].x, l[i].x);
+                split_f16x2(v[i][0].z * sa, v[i][0].w * sa, h[i].y, l[i].y);
+                split_f16x2(v[i][1].x * sa, v[i][1].y * sa, h[i].z, l[i].z);
+                split_f16x2(v[i][1].z * sa, v[i][1].w * sa, h[i].w, l[i].w);
+            }
+            fence_proxy_async();
+            mbar_arrive(&rempty[rs]);
             mbar_wait(&empty[s], ph ^ 1);
-            uint8_t* a_hi = smem + (size_t)s * stage_bytes;
+            uint8_t* a_hi = op_base + (size_t)s * stage_bytes;
             uint8_t* a_lo = a_hi + kHATile;
 #pragma unroll
             for (int i = 0; i < RPT; ++i) {
                 const int r = r0 + RSTEP * i;
-                uint4 h, l;
-                split_f16x2(v[i][0].x * sa, v[i][0].y * sa, h.x, l.x);
-                split_f16x2(v[i][0].z * sa, v[i][0].w * sa, h.y, l.y);
-                split_f16x2(v[i][1].x * sa, v[i][1].y * sa, h.z, l.z);
-                split_f16x2(v[i][1].z * sa, v[i][1].w * sa, h.w, l.w);
                 const uint32_t off = (uint32_t)(r >> 3) * kHASbo + (uint32_t)cq * kHALbo + (uint32_t)(r & 7) * 16;
-                *reinterpret_cast<uint4*>(a_hi + off) = h;
-                *reinterpret_cast<uint4*>(a_lo + off) = l;
+                *reinterpret_cast<uint4*>(a_hi + off) = h[i];
+                *reinterpret_cast<uint4*>(a_lo + off) = l[i];
             }
             fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
             mbar_arrive(&full[s]);
-        };
-        // three register buffers, loop unrolled by three: the loads of iterations it+1 and it+2 stay in flight while
-        // iteration it is converted (no register rotation -- a move out of a pending load would wait for it)
-        float4 b0[RPT][2], b1[RPT][2], b2[RPT][2];
-        issue(0, b0);
-        issue(1, b1);
-        issue(2, b2);
-        for (int64_t it = 0; it < total_it; it += 3) {
-            process(it, b0);
-            issue(it + 3, b0);
-            if (it + 1 < total_it) { process(it + 1, b1); issue(it + 4, b1); }
-            if (it + 2 < total_it) { process(it + 2, b2); issue(it + 5, b2); }
+        }
+    } else if (warp == kHProducerWarps + 6) {
+        // ================= A loader: one lane streams the raw A tiles (TMA 2-D, 128B swizzle, zero fill past m / k) =================
+        if (lane == 0) {
+            tma_prefetch_desc(&g.a_map);
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int64_t m0 = (tile / g.n_tiles) * kHBM;
+                for (int q = 0; q < g.k_chunks; ++q, ++it) {
+                    const int rs = it % kHRawStages;
+                    const uint32_t rph = (it / kHRawStages) & 1;
+                    mbar_wait(&rempty[rs], rph ^ 1);
+                    mbar_arrive_expect_tx(&rfull[rs], kHRawBytes);
+                    tma_load_2d(raw_base + (size_t)rs * kHRawBytes, &g.a_map, q * kHBK, (int)m0, &rfull[rs]);
+                }
+            }
         }
     } else if (warp == kHProducerWarps) {
         // ================= B copy: one bulk copy of the pre-tiled hi|lo weight image per stage =================
@@ -273,7 +294,7 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const HArgs g) {
                     const int s = it % g.stages;
                     const uint32_t ph = (it / g.stages) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
-                    uint8_t* b_dst = smem + (size_t)s * stage_bytes + 2 * kHATile;
+                    uint8_t* b_dst = op_base + (size_t)s * stage_bytes + 2 * kHATile;
                     const uint8_t* src = g.wp + ((size_t)nt * g.k_chunks + q) * 2 * b_tile_bytes;
                     mbar_arrive_expect_tx(&full[s], 2 * b_tile_bytes);
                     bulk_g2s(b_dst, src, 2 * b_tile_bytes, &full[s]);
@@ -297,7 +318,7 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const HArgs g) {
                     const uint32_t ph = (it / g.stages) & 1;
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t a_hi = smem_u32(op_base + (size_t)s * stage_bytes);
                     const uint32_t a_lo = a_hi + kHATile;
                     const uint32_t b_hi = a_hi + 2 * kHATile;
                     const uint32_t b_lo = b_hi + b_tile_bytes;
@@ -323,7 +344,7 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const HArgs g) {
         f16_scale_from_amax(__ldg(g.a_amax), sa, inva);
         const float invw = __ldg(g.wscale + 1);
         const int quarter = warp & 3;                // TMEM lanes 32*quarter .. +31 are accessible to this warp
-        float* stg = reinterpret_cast<float*>(smem + (size_t)g.stages * stage_bytes + 256) + quarter * 32 * kHEpiLd;
+        float* stg = reinterpret_cast<float*>(op_base + (size_t)g.stages * stage_bytes + 256) + quarter * 32 * kHEpiLd;
         uint32_t tcount = 0;
         for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
             const int nt = (int)(tile % g.n_tiles);
@@ -610,9 +631,10 @@ static HPlan h_plan(int n, int k) {
     p.n_tiles = (n + p.bn - 1) / p.bn;
     p.k_chunks = (k + kHBK - 1) / kHBK;
     int sb = h_stage_bytes(p.bn);
-    int st = (kHSmemBudget - 256 - kHEpiBytes) / sb;
+    int st = (kHSmemBudget - 256 - kHEpiBytes - kHRawStages * kHRawBytes - 1024) / sb;
     p.stages = st > kHMaxStages ? kHMaxStages : st;
-    p.smem_bytes = (size_t)p.stages * sb + 256 + kHEpiBytes;
+    if (const char* e = getenv("SGB_F16_STAGES")) { int v = atoi(e); if (v >= 2 && v <= p.stages) p.stages = v; }
+    p.smem_bytes = (size_t)kHRawStages * kHRawBytes + (size_t)p.stages * sb + 256 + kHEpiBytes;
     p.img_bytes = (size_t)p.n_tiles * p.k_chunks * 2 * h_b_tile_bytes(p.bn);
     p.acc_stride = (p.bn + 31) / 32 * 32;
     uint32_t cols = 32;
@@ -650,6 +672,10 @@ int gemm_f16_launch(const GemmArgs& g, const float* a_amax, void* ws, size_t ws_
         attr_set = true;
     }
     HArgs t{};
+    {
+        int rc = make_tmap_2d(&t.a_map, g.a, g.m, g.k, g.lda, kHBK, kHBM, true);
+        if (rc != SGB_OK) return rc;
+    }
     t.a = g.a; t.lda = g.lda; t.wp = img; t.wscale = hdr; t.a_amax = a_amax; t.c = g.c; t.ldc = g.ldc; t.m = g.m; t.n = g.n; t.k = g.k;
     t.bn = p.bn; t.n_tiles = p.n_tiles; t.k_chunks = p.k_chunks; t.stages = p.stages;
     t.bias = g.bias; t.accumulate = g.accumulate; t.tmem_cols = p.tmem_cols; t.acc_stride = p.acc_stride;

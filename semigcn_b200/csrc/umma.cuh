@@ -1,6 +1,7 @@
 // tcgen05 / TMEM / mbarrier / bulk-copy PTX wrappers shared by the tensor-core GEMM engines (sm_100a only).
 #pragma once
 #include "common.cuh"
+#include <cuda.h>
 
 namespace sgb {
 
@@ -125,5 +126,22 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+
+// ---- TMA (cp.async.bulk.tensor): 2-D tiled loads of row-major fp32 matrices --------------------------------
+// box = {box_cols, box_rows} elements starting at (col, row); out-of-range elements are written as zeros and the
+// mbarrier always receives the full box byte count.
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* tmap, int col, int row, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(reinterpret_cast<uint64_t>(tmap)), "r"(col), "r"(row), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+
+// host: tensor map of a row-major [rows, cols] fp32 matrix with leading dimension ld (elements); swizzle128 = the
+// 128-byte swizzle (16-byte chunk index XOR row % 8; box_cols * 4 must be 128), else a dense box image.
+int make_tmap_2d(CUtensorMap* out, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows, bool swizzle128);
 
 }  // namespace sgb
