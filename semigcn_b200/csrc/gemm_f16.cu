@@ -415,13 +415,16 @@ constexpr int kTSbo = kTCols * kTLbo + 16;       // row-adjacent core matrices (
 constexpr int kTGTile = (kTBM / 8) * kTSbo;      // per hi (or lo)
 constexpr int kTProducerWarps = 12;              // 384 threads: one (8 vertices x 4 columns) item each per stage
 constexpr int kTDrainWarps = 4;
-constexpr int kTThreads = (kTProducerWarps + 1 + kTDrainWarps) * 32;
+constexpr int kTThreads = (kTProducerWarps + 1 + kTDrainWarps + 1) * 32;   // converters, MMA, drain, TMA loader
+constexpr int kTRawStages = 2;
 constexpr int kTSegChunks = 16;                  // 512 vertices per TMEM accumulation segment (tensor-core accumulation truncates)
 
 __host__ __device__ constexpr int t_a_tile_bytes(int bk) { return (bk / 8) * kTSbo; }
 __host__ __device__ constexpr int t_stage_bytes(int bk) { return 2 * kTGTile + 2 * t_a_tile_bytes(bk); }
 
 struct TArgs {
+    CUtensorMap g_map, a_map;         // G [m, n] box {gbox, 32}; A [m, k] box {abox, 32}; dense (no swizzle) box images
+    int gbox, abox;                   // box widths in columns (multiples of 4)
     const float* g; int64_t ldg;
     const float* a; int64_t lda;
     const float* g_amax; const float* a_amax;   // device scalars
@@ -433,16 +436,23 @@ struct TArgs {
     uint32_t tmem_cols; int acc_stride;
 };
 
-__global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const TArgs t) {
+__global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const __grid_constant__ TArgs t) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stage_bytes = t_stage_bytes(t.bk);
     const int a_tile_bytes = t_a_tile_bytes(t.bk);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)t.stages * stage_bytes);
+    // smem: [raw ring: kTRawStages x (G box | A box), fp32][operand ring: stages x stage_bytes][barriers]
+    const int raw_g_bytes = kTBV * t.gbox * 4, raw_a_bytes = kTBV * t.abox * 4;
+    const int raw_bytes = (raw_g_bytes + raw_a_bytes + 127) / 128 * 128;
+    uint8_t* const raw_base = smem;
+    uint8_t* const op_base = smem + (size_t)kTRawStages * raw_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(op_base + (size_t)t.stages * stage_bytes);
     uint64_t* empty = full + kHMaxStages;
     uint64_t* tfull = empty + kHMaxStages;      // [2]
     uint64_t* tempty = tfull + 2;               // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* rfull = tempty + 2;               // [kTRawStages]
+    uint64_t* rempty = rfull + kTRawStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + kTRawStages);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < t.stages; ++s) {
@@ -452,6 +462,10 @@ __global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const TArgs t) {
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull[b], 1);
             mbar_init(&tempty[b], kTDrainWarps);
+        }
+        for (int s = 0; s < kTRawStages; ++s) {
+            mbar_init(&rfull[s], 1);
+            mbar_init(&rempty[s], kTProducerWarps * 32);
         }
         fence_barrier_init();
     }
@@ -472,60 +486,76 @@ __global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const TArgs t) {
     f16_scale_from_amax(__ldg(t.a_amax), sa, inva);
 
     if (warp < kTProducerWarps) {
-        // thread item: 8 consecutive vertices (core column mg) x 4 consecutive columns (float4 index c4) of G (threads 0..127)
-        // or of A (threads 128..383); the 8 x 4 register block is four 16-byte K-major rows after conversion
+        // converter item: 8 consecutive vertices (core column mg) x 4 consecutive columns (float4 index c4) of G
+        // (threads 0..127) or of A (threads 128..383), read from the raw fp32 stage; the 8 x 4 register block is four
+        // 16-byte K-major rows after conversion (the transposition happens in registers)
         const int tid = threadIdx.x;
         const bool is_g = tid < 128;
         const int idx = is_g ? tid : tid - 128;
         const int per_mg = is_g ? 32 : 64;
         const int mg = idx / per_mg, c4 = idx % per_mg;
-        const int col = (is_g ? n0 : k0) + c4 * 4;
-        const int lim = is_g ? t.n : min(t.k, k0 + t.bk);
-        const bool col_ok = col < lim;                                    // n, k multiples of 4: whole float4 valid
-        const float* src = (is_g ? t.g : t.a) + col;
-        const int64_t ld = is_g ? t.ldg : t.lda;
+        const int box = is_g ? t.gbox : t.abox;
+        const bool col_ok = c4 * 4 < box;                                 // inside the TMA box (zero-filled past n / k)
+        const bool in_tile = c4 * 4 < (is_g ? kTBM : t.bk);               // inside the operand tile the tensor core reads
         const float sc = is_g ? sg : sa;
+        const uint32_t raw_off = (is_g ? 0u : (uint32_t)raw_g_bytes) + (uint32_t)(mg * 8) * (uint32_t)box * 4u + (uint32_t)c4 * 16u;
         const uint32_t tile_off = is_g ? 0u : (uint32_t)(2 * kTGTile);
         const uint32_t lo_off = is_g ? (uint32_t)kTGTile : (uint32_t)a_tile_bytes;
         // rows 4*c4 .. 4*c4+3 of the operand tile, core column mg
         const uint32_t base_off = tile_off + (uint32_t)((c4 * 4) >> 3) * kTSbo + (uint32_t)mg * kTLbo + (uint32_t)((c4 * 4) & 7) * 16;
-        auto issue = [&](int it, float4 (&v)[8]) {
-            const int64_t gm0 = ms + (int64_t)it * kTBV + mg * 8;
+        for (int it = 0; it < chunks; ++it) {
+            const int s = it % t.stages, rs = it % kTRawStages;
+            const uint32_t ph = (it / t.stages) & 1, rph = (it / kTRawStages) & 1;
+            mbar_wait(&rfull[rs], rph);
+            const uint8_t* raw = raw_base + (size_t)rs * raw_bytes + raw_off;
+            uint4 h[4], l[4];
+            if (col_ok) {
+                float4 v[8];
 #pragma unroll
-            for (int r = 0; r < 8; ++r)
-                v[r] = (it < chunks && col_ok && gm0 + r < me) ? ldg4(src + (gm0 + r) * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
-        };
-        const bool in_tile = c4 * 4 < (is_g ? kTBM : t.bk);
-        auto process = [&](int it, float4 (&v)[8]) {
-            const int s = it % t.stages;
-            const uint32_t ph = (it / t.stages) & 1;
-            mbar_wait(&empty[s], ph ^ 1);
-            uint8_t* st = smem + (size_t)s * stage_bytes + base_off;
-            if (in_tile) {
+                for (int r = 0; r < 8; ++r) v[r] = *reinterpret_cast<const float4*>(raw + (size_t)r * box * 4);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float x0 = (&v[0].x)[q], x1 = (&v[1].x)[q], x2 = (&v[2].x)[q], x3 = (&v[3].x)[q];
                     const float x4 = (&v[4].x)[q], x5 = (&v[5].x)[q], x6 = (&v[6].x)[q], x7 = (&v[7].x)[q];
-                    uint4 h, l;
-                    split_f16x2(x0 * sc, x1 * sc, h.x, l.x);
-                    split_f16x2(x2 * sc, x3 * sc, h.y, l.y);
-                    split_f16x2(x4 * sc, x5 * sc, h.z, l.z);
-                    split_f16x2(x6 * sc, x7 * sc, h.w, l.w);
-                    *reinterpret_cast<uint4*>(st + q * 16) = h;
-                    *reinterpret_cast<uint4*>(st + lo_off + q * 16) = l;
+                    split_f16x2(x0 * sc, x1 * sc, h[q].x, l[q].x);
+                    split_f16x2(x2 * sc, x3 * sc, h[q].y, l[q].y);
+                    split_f16x2(x4 * sc, x5 * sc, h[q].z, l[q].z);
+                    split_f16x2(x6 * sc, x7 * sc, h[q].w, l[q].w);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { h[q] = make_uint4(0u, 0u, 0u, 0u); l[q] = make_uint4(0u, 0u, 0u, 0u); }
+            }
+            // the conversion above consumed the loaded values: only now may the raw slot go back to the TMA engine
+            fence_proxy_async();
+            mbar_arrive(&rempty[rs]);
+            mbar_wait(&empty[s], ph ^ 1);
+            if (in_tile) {
+                uint8_t* st = op_base + (size_t)s * stage_bytes + base_off;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    *reinterpret_cast<uint4*>(st + q * 16) = h[q];
+                    *reinterpret_cast<uint4*>(st + lo_off + q * 16) = l[q];
                 }
             }
             fence_proxy_async();
             mbar_arrive(&full[s]);
-        };
-        // two register buffers, loop unrolled by two: the loads of stage it+1 are in flight while stage it is converted
-        float4 v0[8], v1[8];
-        issue(0, v0);
-        issue(1, v1);
-        for (int it = 0; it < chunks; it += 2) {
-            process(it, v0);
-            issue(it + 2, v0);
-            if (it + 1 < chunks) { process(it + 1, v1); issue(it + 3, v1); }
+        }
+    } else if (warp == kTProducerWarps + 1 + kTDrainWarps) {
+        // ================= loader: one lane streams the raw G and A boxes of each 32-vertex stage (TMA 2-D, zero fill) =================
+        if (lane == 0) {
+            tma_prefetch_desc(&t.g_map);
+            tma_prefetch_desc(&t.a_map);
+            for (int it = 0; it < chunks; ++it) {
+                const int rs = it % kTRawStages;
+                const uint32_t rph = (it / kTRawStages) & 1;
+                mbar_wait(&rempty[rs], rph ^ 1);
+                mbar_arrive_expect_tx(&rfull[rs], (uint32_t)(raw_g_bytes + raw_a_bytes));
+                uint8_t* dst = raw_base + (size_t)rs * raw_bytes;
+                const int row = (int)(ms + (int64_t)it * kTBV);
+                tma_load_2d(dst, &t.g_map, n0, row, &rfull[rs]);
+                tma_load_2d(dst + raw_g_bytes, &t.a_map, k0, row, &rfull[rs]);
+            }
         }
     } else if (warp == kTProducerWarps) {
         if (lane == 0) {
@@ -542,7 +572,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const TArgs t) {
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * t.acc_stride);
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                const uint32_t g_hi = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t g_hi = smem_u32(op_base + (size_t)s * stage_bytes);
                 const uint32_t g_lo = g_hi + kTGTile;
                 const uint32_t a_hi = g_lo + kTGTile;
                 const uint32_t a_lo = a_hi + a_tile_bytes;
@@ -572,6 +602,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const TArgs t) {
             if (gn < t.n)
                 for (int c = 0; c < kcols; ++c) out[(int64_t)gn * t.k + k0 + c] = 0.f;
         }
+        float* stg = reinterpret_cast<float*>(op_base + (size_t)t.stages * stage_bytes + 256) + quarter * 32 * kHEpiLd;
         for (int seg = 0; seg < segments; ++seg) {
             const int acc = seg & 1;
             mbar_wait(&tfull[acc], (seg >> 1) & 1);
@@ -579,28 +610,40 @@ __global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const TArgs t) {
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * t.acc_stride);
             for (int c0 = 0; c0 < kcols; c0 += 32) {
                 float v[32];
-                tmem_ld_32x32(taddr + (uint32_t)c0, v);
+                tmem_ld_32x32(taddr + (uint32_t)c0, v);          // lane = row of D, registers = 32 consecutive columns
 #pragma unroll
                 for (int e = 0; e < 32; ++e) v[e] = (v[e] * invg) * inva;
-                if (gn < t.n) {
-                    float* op = out + (int64_t)gn * t.k + k0 + c0;
-                    if (vec_ok && c0 + 32 <= kcols) {
+                if (vec_ok) {
+                    // transpose through the warp's staging tile: the read-modify-write of the partial tile then moves whole
+                    // 128-byte row segments (a lane-per-row access touches 32 lines per instruction)
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(stg + lane * kHEpiLd + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                    __syncwarp();
+                    const int cc = (lane & 7) * 4;
+                    if (c0 + cc < kcols) {                       // kcols is a multiple of 4 here
+                        float* const op0 = out + (int64_t)(n0 + quarter * 32 + (lane >> 3)) * t.k + k0 + c0 + cc;
+                        const int nrows = t.n - (n0 + quarter * 32 + (lane >> 3));       // rows j = i*4 + (lane>>3) valid while 4*i < nrows
                         float4 old[8];
-                        if (seg != 0) {
+                        if (seg != 0) {                          // all eight loads in flight before the first add
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) old[e] = *reinterpret_cast<const float4*>(op + 4 * e);
+                            for (int i = 0; i < 8; ++i)
+                                old[i] = (4 * i < nrows) ? __ldcg(reinterpret_cast<const float4*>(op0 + (int64_t)(4 * i) * t.k)) : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            float4 o = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
-                            if (seg != 0) { o.x += old[e].x; o.y += old[e].y; o.z += old[e].z; o.w += old[e].w; }
-                            *reinterpret_cast<float4*>(op + 4 * e) = o;
+                        for (int i = 0; i < 8; ++i) {
+                            if (4 * i < nrows) {
+                                float4 o = *reinterpret_cast<const float4*>(stg + (i * 4 + (lane >> 3)) * kHEpiLd + cc);
+                                if (seg != 0) { o.x += old[i].x; o.y += old[i].y; o.z += old[i].z; o.w += old[i].w; }
+                                __stcg(reinterpret_cast<float4*>(op0 + (int64_t)(4 * i) * t.k), o);
+                            }
                         }
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e)
-                            if (c0 + e < kcols) op[e] = seg == 0 ? v[e] : op[e] + v[e];
                     }
+                    __syncwarp();
+                } else if (gn < t.n) {
+                    float* op = out + (int64_t)gn * t.k + k0 + c0;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (c0 + e < kcols) op[e] = seg == 0 ? v[e] : op[e] + v[e];
                 }
             }
             tc_fence_before();
@@ -689,7 +732,7 @@ int gemm_f16_launch(const GemmArgs& g, const float* a_amax, void* ws, size_t ws_
 
 // ---- weight gradient ----
 struct TPlan {
-    int bk, k_tiles, n_tiles, stages, splits, acc_stride;
+    int bk, k_tiles, n_tiles, stages, splits, acc_stride, gbox, abox;
     int64_t m_per_split;
     size_t smem_bytes, ws_bytes;
     uint32_t tmem_cols;
@@ -702,9 +745,12 @@ static TPlan t_plan(int64_t m, int n, int k) {
     p.k_tiles = (k + p.bk - 1) / p.bk;
     p.n_tiles = (n + kTBM - 1) / kTBM;
     int sb = t_stage_bytes(p.bk);
-    int st = (kHSmemBudget - 256) / sb;
-    p.stages = st > kHMaxStages ? kHMaxStages : st;
-    p.smem_bytes = (size_t)p.stages * sb + 256;
+    p.gbox = n < kTBM ? n : kTBM;
+    p.abox = k < p.bk ? k : p.bk;
+    int raw = (kTBV * (p.gbox + p.abox) * 4 + 127) / 128 * 128;
+    int st = (kHSmemBudget - 256 - kHEpiBytes - kTRawStages * raw) / sb;
+    p.stages = st > 4 ? 4 : st;
+    p.smem_bytes = (size_t)kTRawStages * raw + (size_t)p.stages * sb + 256 + kHEpiBytes;
     int tiles = p.k_tiles * p.n_tiles;
     int64_t want = num_sms() / tiles;
     if (want < 1) want = 1;
@@ -751,6 +797,12 @@ int gemm_tn_f16_launch(const float* g, int64_t ldg, const float* a, int64_t lda,
         attr_set = true;
     }
     TArgs t{};
+    {
+        int rc = make_tmap_2d(&t.g_map, g, m, n, ldg, p.gbox, kTBV, false);
+        if (rc == SGB_OK) rc = make_tmap_2d(&t.a_map, a, m, k, lda, p.abox, kTBV, false);
+        if (rc != SGB_OK) return rc;
+        t.gbox = p.gbox; t.abox = p.abox;
+    }
     t.g = g; t.ldg = ldg; t.a = a; t.lda = lda; t.g_amax = g_amax; t.a_amax = a_amax; t.partial = partial; t.m = m; t.n = n; t.k = k;
     t.bk = p.bk; t.k_tiles = p.k_tiles; t.stages = p.stages; t.m_per_split = p.m_per_split; t.tmem_cols = p.tmem_cols; t.acc_stride = p.acc_stride;
     dim3 grid((unsigned)(p.n_tiles * p.k_tiles), (unsigned)p.splits);
