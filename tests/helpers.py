@@ -39,8 +39,10 @@ def assert_bit_equal(a, b, what=""):
     assert nbad == 0, f"{what}: {nbad} of {a.numel()} elements differ bitwise (max abs diff {(a.double()-b.double()).abs().max().item():.3e})"
 
 
-def load_golden(n: int):
-    return np.load(os.path.join(GOLDEN, f"ref_mesh_n{n}.npz"))
+def load_golden(n):
+    """``n``: icosphere frequency of a reference-mesh fixture (ref_mesh_n{n}.npz) or a fixture file name."""
+    name = n if isinstance(n, str) else f"ref_mesh_n{n}.npz"
+    return np.load(os.path.join(GOLDEN, name))
 
 
 def random_graph(n: int, nnz: int, seed: int, self_loops: int = 0, duplicates: int = 0, isolated: int = 0,

@@ -276,3 +276,34 @@ def test_reference_scripts_import_surface():
     mesh = meshgen.icosphere(3)
     y = blk(torch.randn(mesh.num_vertices, 4, device=DEV), mesh.edge_index.to(DEV))
     assert y.shape == (mesh.num_vertices, 16) and torch.isfinite(y).all()
+
+
+@pytest.mark.parametrize("conv", ["chebconv", "gcnconv"])
+@pytest.mark.parametrize("skip", [False, True])
+def test_sgcn_matches_reference_networks_py_fixture(conv, skip):
+    """Drop-in network vs the fixture produced by the reference's own util/networks.py (tests/golden/make_golden_net.py):
+    same seeded initial parameters (PyG's double reset_parameters RNG consumption) and the same forward
+    output in train and eval mode within the 1e-5 bar."""
+    import numpy as np
+    from helpers import load_golden
+    from semigcn_b200.data import Data
+    from semigcn_b200.networks import SingleScaleGCN
+    gold = load_golden("ref_sgcn_n4.npz")
+    tag = f"{conv}_{'skip' if skip else 'noskip'}"
+    torch.manual_seed(int(gold["seed"]))
+    net = SingleScaleGCN("cpu", conv=conv, skip=skip)
+    sd = net.state_dict()
+    names = sorted(sd.keys())
+    assert names == [str(s) for s in gold[f"{tag}_names"]]
+    sums = np.array([[float(sd[k].double().sum()), float(sd[k].double().abs().sum())] for k in names])
+    assert np.array_equal(sums, gold[f"{tag}_sums"]), "seeded initial parameters differ from the reference"
+    net = net.to(DEV)
+    net.device = DEV
+    data = Data(z1=torch.from_numpy(gold["z1"]).to(DEV), x_pos=torch.from_numpy(gold["x_pos"]).to(DEV),
+                edge_index=torch.from_numpy(gold["edge_index"]).to(DEV))
+    net.train()
+    y = net(data, gold["dm"])                                  # np.ndarray mask, as sgcn.py passes it
+    assert_close(y, torch.from_numpy(gold[f"{tag}_train"]), REL_TOL, "train-mode forward")
+    net.eval()
+    y = net(data, torch.from_numpy(gold["dm"]))
+    assert_close(y, torch.from_numpy(gold[f"{tag}_eval"]), REL_TOL, "eval-mode forward")

@@ -182,3 +182,30 @@ def test_sgcn_oracle_runs_and_backprops():
     loss = O.mask_pos_rec_loss(out, prob["ini_vs"], prob["v_mask"])
     loss.backward()
     assert all(p.grad is not None for n_, p in net.named_parameters() if "skip" not in n_)
+
+
+# ------------------------------------------------------------------ network wiring pinned against the reference file
+@pytest.mark.parametrize("conv", ["chebconv", "gcnconv"])
+@pytest.mark.parametrize("skip", [False, True])
+def test_oracle_sgcn_matches_reference_networks_py(conv, skip):
+    """tests/golden/ref_sgcn_n4.npz was produced by running /root/reference/util/networks.py::SingleScaleGCN itself
+    (PyG symbols resolved to the oracle classes, tests/golden/make_golden_net.py): the oracle's restated network must
+    consume the RNG identically (same seeded initial state_dict) and give the same forward in train and eval mode."""
+    import numpy as np
+    gold = load_golden("ref_sgcn_n4.npz")
+    tag = f"{conv}_{'skip' if skip else 'noskip'}"
+    torch.manual_seed(int(gold["seed"]))
+    net = O.SingleScaleGCN(conv, skip=skip)
+    sd = net.state_dict()
+    names = sorted(sd.keys())
+    assert names == [str(s) for s in gold[f"{tag}_names"]]
+    sums = np.array([[float(sd[k].double().sum()), float(sd[k].double().abs().sum())] for k in names])
+    assert np.array_equal(sums, gold[f"{tag}_sums"]), "seeded initial parameters differ from the reference construction order"
+    z1, x_pos = torch.from_numpy(gold["z1"]), torch.from_numpy(gold["x_pos"])
+    ei, dm = torch.from_numpy(gold["edge_index"]), torch.from_numpy(gold["dm"])
+    net.train()
+    y = net(z1, x_pos, ei, dm)
+    assert torch.equal(y.detach(), torch.from_numpy(gold[f"{tag}_train"]))
+    net.eval()
+    y = net(z1, x_pos, ei, dm)
+    assert torch.equal(y.detach(), torch.from_numpy(gold[f"{tag}_eval"]))
