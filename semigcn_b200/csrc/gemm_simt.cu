@@ -284,6 +284,132 @@ __global__ void k_reduce_splits(const float* __restrict__ partial, int splits, i
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Thin weight gradient  D[n,k] = sum_m G[m,n] A[m,k]  with n <= 32, k <= 64 (the 4-16-32 / 32-16-3 ends of the SGCN
+// stack): a pure HBM stream of two narrow matrices.  A CTA walks a contiguous row range in 32-row stages
+// (cp.async, 3-deep); a warp takes 4 rows of a stage, every lane owns KPL columns of k and all NT rows of n
+// (G values are shared-memory broadcasts), so the whole D tile lives in registers.  Fixed-order merge of the 8
+// warps, one partial tile per CTA, then k_reduce_splits (deterministic).
+// ---------------------------------------------------------------------------------------
+constexpr int kThinRows = 32;
+constexpr int kThinStages = 3;
+constexpr int kThinThreads = 256;
+
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+template <int NT, int KPL>
+__global__ void __launch_bounds__(kThinThreads) k_gemm_tn_thin(const float* __restrict__ gmat, int64_t ldg, const float* __restrict__ amat,
+                                                               int64_t lda, int64_t m, int n, int k, int64_t rows_per_cta,
+                                                               float* __restrict__ partial) {
+    constexpr int KW = 32 * KPL;
+    __shared__ __align__(16) float Gs[kThinStages][kThinRows][NT];
+    __shared__ __align__(16) float As[kThinStages][kThinRows][KW];
+    __shared__ float red[NT][KW];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t ms = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t me = min64(m, ms + rows_per_cta);
+    const int nstages = me > ms ? (int)((me - ms + kThinRows - 1) / kThinRows) : 0;
+    const bool g_vec = (n % 4 == 0) && (ldg % 4 == 0) && ((reinterpret_cast<uintptr_t>(gmat) & 15) == 0);
+    const bool a_vec = (k % 4 == 0) && (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(amat) & 15) == 0);
+    // padding columns (>= n, >= k) are never written again: zero everything once
+    for (int i = tid; i < kThinStages * kThinRows * NT; i += kThinThreads) (&Gs[0][0][0])[i] = 0.f;
+    for (int i = tid; i < kThinStages * kThinRows * KW; i += kThinThreads) (&As[0][0][0])[i] = 0.f;
+    __syncthreads();
+
+    auto stage_load = [&](int st, int buf) {
+        if (st < nstages) {
+            const int64_t r0 = ms + (int64_t)st * kThinRows;
+            const int rows = (int)min64(kThinRows, me - r0);
+            if (g_vec) {
+                const int per = n >> 2;
+                for (int i = tid; i < kThinRows * per; i += kThinThreads) {
+                    const int r = i / per, c = (i % per) * 4;
+                    if (r < rows) cp_async_16(&Gs[buf][r][c], gmat + (r0 + r) * ldg + c);
+                    else *reinterpret_cast<float4*>(&Gs[buf][r][c]) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+                for (int i = tid; i < kThinRows * n; i += kThinThreads) {
+                    const int r = i / n, c = i % n;
+                    if (r < rows) cp_async_4(&Gs[buf][r][c], gmat + (r0 + r) * ldg + c);
+                    else Gs[buf][r][c] = 0.f;
+                }
+            }
+            if (a_vec) {
+                const int per = k >> 2;
+                for (int i = tid; i < kThinRows * per; i += kThinThreads) {
+                    const int r = i / per, c = (i % per) * 4;
+                    if (r < rows) cp_async_16(&As[buf][r][c], amat + (r0 + r) * lda + c);
+                    else *reinterpret_cast<float4*>(&As[buf][r][c]) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+                for (int i = tid; i < kThinRows * k; i += kThinThreads) {
+                    const int r = i / k, c = i % k;
+                    if (r < rows) cp_async_4(&As[buf][r][c], amat + (r0 + r) * lda + c);
+                    else As[buf][r][c] = 0.f;
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    float acc[NT][KPL];
+#pragma unroll
+    for (int i = 0; i < NT; ++i)
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) acc[i][j] = 0.f;
+
+    stage_load(0, 0);
+    stage_load(1, 1);
+    for (int st = 0; st < nstages; ++st) {
+        const int buf = st % kThinStages;
+        stage_load(st + 2, (st + 2) % kThinStages);                 // buffer (st + 2) % 3 was consumed at iteration st - 1
+        asm volatile("cp.async.wait_group 2;" ::: "memory");         // stage st has landed (two younger groups may be in flight)
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < kThinRows / 8; ++rr) {
+            const int r = warp * (kThinRows / 8) + rr;
+            float av[KPL];
+#pragma unroll
+            for (int j = 0; j < KPL; ++j) av[j] = As[buf][r][lane + 32 * j];
+#pragma unroll
+            for (int i = 0; i < NT; i += 4) {
+                const float4 gq = *reinterpret_cast<const float4*>(&Gs[buf][r][i]);   // broadcast
+                const float gg[4] = {gq.x, gq.y, gq.z, gq.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int j = 0; j < KPL; ++j) acc[i + q][j] = fmaf(gg[q], av[j], acc[i + q][j]);
+            }
+        }
+        __syncthreads();                                             // everyone is done with buf before it is refilled
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // fixed-order merge of the warps
+    for (int w = 0; w < kThinThreads / 32; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int i = 0; i < NT; ++i)
+#pragma unroll
+                for (int j = 0; j < KPL; ++j) red[i][lane + 32 * j] = (w == 0 ? 0.f : red[i][lane + 32 * j]) + acc[i][j];
+        }
+        __syncthreads();
+    }
+    float* out = partial + (int64_t)blockIdx.x * n * k;
+    for (int i = tid; i < n * k; i += kThinThreads) out[i] = red[i / k][i % k];
+}
+
+static bool tn_thin_ok(int n, int k) { return n <= 32 && k <= 64; }
+static int tn_thin_grid(int64_t m) {
+    int64_t g = ceil_div(m > 0 ? m : 1, 8 * kThinRows);
+    int64_t cap = (int64_t)num_sms() * 2;
+    return (int)(g < cap ? g : cap);
+}
+
 static int tn_splits(int64_t m, int n, int k) {
     int64_t tiles = ceil_div(n, kTnTile) * ceil_div(k, kTnTile);
     int64_t want = ceil_div((int64_t)num_sms() * 4, tiles);
@@ -294,6 +420,26 @@ static int tn_splits(int64_t m, int n, int k) {
 
 int gemm_tn_simt_launch(const float* g, int64_t ldg, const float* a, int64_t lda, float* d, int64_t ldd, int64_t m, int n, int k,
                         int accumulate, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (tn_thin_ok(n, k) && m > 0) {
+        const int grid = tn_thin_grid(m);
+        const size_t need = (size_t)grid * n * k * sizeof(float);
+        if (ws_bytes < need || !ws) {
+            set_error("sgb_gemm_tn: workspace %zu < required %zu", ws_bytes, need);
+            return SGB_ENOSPC;
+        }
+        const int64_t rpc = ceil_div(ceil_div(m, grid), kThinRows) * kThinRows;
+        const int nt = n <= 4 ? 4 : (n <= 16 ? 16 : 32), kpl = k <= 32 ? 1 : 2;
+#define SGB_THIN_CASE(NTV, KPLV)                                                                                            \
+        if (nt == NTV && kpl == KPLV) k_gemm_tn_thin<NTV, KPLV><<<grid, kThinThreads, 0, stream>>>(g, ldg, a, lda, m, n, k, rpc, (float*)ws);
+        SGB_THIN_CASE(4, 1) SGB_THIN_CASE(4, 2) SGB_THIN_CASE(16, 1) SGB_THIN_CASE(16, 2) SGB_THIN_CASE(32, 1) SGB_THIN_CASE(32, 2)
+#undef SGB_THIN_CASE
+        SGB_CHECK_LAUNCH("k_gemm_tn_thin");
+        int64_t total = (int64_t)n * k;
+        int rgrid = (int)min64(ceil_div(total, 256), (int64_t)num_sms() * 8);
+        k_reduce_splits<<<rgrid, 256, 0, stream>>>((const float*)ws, grid, n, k, d, ldd, accumulate);
+        SGB_CHECK_LAUNCH("k_reduce_splits");
+        return SGB_OK;
+    }
     int splits = tn_splits(m, n, k);
     size_t need = (size_t)splits * n * k * sizeof(float);
     if (ws_bytes < need || !ws) {
@@ -311,6 +457,10 @@ int gemm_tn_simt_launch(const float* g, int64_t ldg, const float* a, int64_t lda
     return SGB_OK;
 }
 
-size_t gemm_tn_simt_workspace(int64_t m, int n, int k) { return (size_t)tn_splits(m, n, k) * n * k * sizeof(float); }
+size_t gemm_tn_simt_workspace(int64_t m, int n, int k) {
+    size_t a = (size_t)tn_splits(m, n, k) * n * k * sizeof(float);
+    size_t b = tn_thin_ok(n, k) ? (size_t)tn_thin_grid(m) * n * k * sizeof(float) : 0;
+    return a > b ? a : b;
+}
 
 }  // namespace sgb
