@@ -43,11 +43,15 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--freq", type=int, default=316, help="icosphere frequency n (V = 10 n^2 + 2)")
+    ap.add_argument("--freq", type=int, default=0, help="icosphere frequency n (V = 10 n^2 + 2); 0 = 316 (1M vertices) for replicas, "
+                                                        "632 (4M vertices, fits one GPU) for partition")
     ap.add_argument("--conv", default="gcnconv", choices=["gcnconv", "chebconv"])
     ap.add_argument("--cpu-freq", type=int, default=0, help="icosphere frequency of the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel CUDA-event roofline pass")
+    ap.add_argument("--mode", default="replicas", choices=["replicas", "partition"],
+                    help="replicas: one independent mesh per GPU (default, configs[2]/[4]); partition: ONE mesh vertex-partitioned over the "
+                         "GPUs with per-propagation halo exchange over NCCL (configs[3], strong scaling)")
     return ap.parse_args()
 
 
@@ -333,8 +337,122 @@ def run_reference(args, rank, world):
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
+def run_partition(args, rank, world, local_rank):
+    """BASELINE.json configs[3]: ONE mesh, vertices partitioned over the ranks (contiguous ranges of the generator's
+    grid-like numbering), one halo exchange per propagation (all-to-all over NCCL), SyncBN partial all-gather,
+    weight-gradient all-reduce.  Total work is fixed as N grows -> strong scaling.  The step is forward + the masked
+    position loss (the face-normal loss needs faces across cuts; not partitioned yet) + backward + gradient sum + Adam."""
+    from semigcn_b200 import _lib, partition
+    from semigcn_b200._lib import MODE_CHEB, MODE_GCN
+    from semigcn_b200.data import Data
+    from semigcn_b200.dist import TorchComm, dist_mask_pos_rec_loss, register_partition, sync_gradients
+    from semigcn_b200.networks import SingleScaleGCN, SGCN_WIDTHS
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    _lib.load()
+    comm = TorchComm()
+    prob = make_problem(args.freq, dev, seed=314)            # the same mesh on every rank
+    mesh = prob["mesh"]
+    n, nnz = mesh.num_vertices, mesh.nnz
+    plan = partition.build_plan(mesh.edge_index, n, rank, world)
+    lo, hi = plan.lo, plan.hi
+    own = {k: prob[k][lo:hi].contiguous() for k in ("z1", "x_pos", "ini", "v_mask", "dms")}
+    halo_rows = plan.n_ghost
+    del prob, mesh
+    torch.cuda.empty_cache()
+    ei_local = register_partition(plan, comm, modes=(MODE_GCN if args.conv == "gcnconv" else MODE_CHEB,))
+    torch.manual_seed(314)
+    net = SingleScaleGCN(dev, conv=args.conv).to(dev)
+    net.comm = comm
+    opt = torch.optim.Adam(net.parameters(), lr=0.01)
+    data = Data(z1=own["z1"], x_pos=own["x_pos"], edge_index=ei_local)
+
+    def one_step(i):
+        opt.zero_grad(set_to_none=True)
+        out = net(data, own["dms"][:, i % 8:i % 8 + 1])
+        loss = dist_mask_pos_rec_loss(out, own["ini"], own["v_mask"], comm)
+        loss.backward()
+        sync_gradients(net, comm)
+        opt.step()
+        return loss
+
+    def barrier():
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = _lib.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = one_step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.LAUNCHES - launches0
+    clocks = sampler.stop()
+    loss_host = torch.empty((), dtype=torch.float64).pin_memory()
+    # e2e: this rank's slice of z1 / x_pos / mask uploaded from pinned host memory every step, loss read back
+    h = {k: own[k].cpu().pin_memory() for k in ("z1", "x_pos")}
+    h_dm = [own["dms"][:, j:j + 1].contiguous().cpu().pin_memory() for j in range(8)]
+    d_dm = torch.empty((hi - lo, 1), dtype=torch.float32, device=dev)
+
+    def e2e_step(i):
+        own["z1"].copy_(h["z1"], non_blocking=True)
+        own["x_pos"].copy_(h["x_pos"], non_blocking=True)
+        d_dm.copy_(h_dm[i % 8], non_blocking=True)
+        opt.zero_grad(set_to_none=True)
+        out = net(data, d_dm)
+        loss = dist_mask_pos_rec_loss(out, own["ini"], own["v_mask"], comm)
+        loss.backward()
+        sync_gradients(net, comm)
+        opt.step()
+        loss_host.copy_(loss.detach(), non_blocking=True)
+
+    e2e_step(0)
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+    h2d = sum(t.numel() * t.element_size() for t in (h["z1"], h["x_pos"], h_dm[0]))
+    t = torch.tensor([ms, ms_e2e, float(halo_rows), float(h2d)], dtype=torch.float64, device=dev)
+    tmax = t.clone()
+    torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+    ms, ms_e2e = float(tmax[0]), float(tmax[1])
+    if rank != 0:
+        return None
+    units = float(nnz) * N_LAYERS * args.steps
+    return {
+        "metric": METRIC, "value": units / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"SGCN ({args.conv}, 13 blocks, widths {SGCN_WIDTHS}) fwd + masked position loss + bwd + gradient all-reduce + Adam "
+                               f"on ONE icosphere n={args.freq} ({n} vertices, {nnz} directed edges) vertex-partitioned over {world} GPU(s); "
+                               "BASELINE.json configs[3] at the largest size that also fits one GPU",
+                   "vertices": n, "directed_edges": nnz, "conv_layers": N_LAYERS,
+                   "parallelism": f"vertex partition x{world}: halo all-to-all per propagation (NCCL), SyncBN partial all-gather, grad all-reduce",
+                   "halo_rows_total": int(t[2]), "halo_rows_max_per_rank": int(tmax[2]),
+                   "l2_policy": "inputs larger than L2; no explicit flush"},
+        "train_steps_per_s": args.steps / (ms / 1e3),
+        "e2e": {"value": units / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(t[3]), "d2h_bytes_per_step": 8 * world,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "clocks": clocks, "final_loss": float(loss),
+    }
+
+
 def main():
     args = parse()
+    if args.freq == 0:
+        args.freq = 632 if args.mode == "partition" else 316
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -343,13 +461,17 @@ def main():
         if line is not None:
             print(json.dumps(line), flush=True)
         return
-    if world > 1:
+    dist_on = world > 1 or args.mode == "partition"
+    if dist_on:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        os.environ.setdefault("RANK", "0")
+        os.environ.setdefault("WORLD_SIZE", "1")
         torch.distributed.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-    line = run_ours(args, rank, world, local_rank)
+    line = (run_partition if args.mode == "partition" else run_ours)(args, rank, world, local_rank)
     if line is not None:
         print(json.dumps(line), flush=True)
-    if world > 1:
+    if dist_on:
         torch.distributed.destroy_process_group()
 
 

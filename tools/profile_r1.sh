@@ -1,15 +1,24 @@
 #!/bin/bash
-# ncu passes of B200_PROFILING.md on the bench workload (1 GPU).  Outputs under gpurun_out/.
-set -x
+# One GPU call (1 GPU): parity tests, both bench arms, ncu launch list, ncu --set full of the hot kernels.
+# Outputs under gpurun_out/ (scratch); the summaries that are judged are copied into profiles/ afterwards.
+TAG=${1:-r1}
 mkdir -p gpurun_out
-# 1. launch list: every launch of OUR kernels (all named k_*) with its device time
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 700 --csv \
-    --log-file gpurun_out/launches_r1.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-profile > gpurun_out/launches_r1.stdout 2>&1
-# 2. full captures: the 256->512 forward transform (5th tensor-core GEMM launch), a 256-wide SpMM, the 256x256 weight gradient
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_gemm_tc -s 4 -c 1 -f -o gpurun_out/prof_r1_gemm_tc \
-    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-profile > /dev/null 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_spmm -s 4 -c 1 -f -o gpurun_out/prof_r1_spmm \
-    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-profile > /dev/null 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_gemm_tn_tc -s 4 -c 1 -f -o gpurun_out/prof_r1_gemm_tn_tc \
-    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-profile > /dev/null 2>&1
+# 0. parity tests through the C-ABI
+timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu_$TAG.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu_$TAG.log
+tail -3 gpurun_out/pytest_gpu_$TAG.log
+# 1. bench lines (reference arm first, as the driver does)
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err
+timeout 900 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
+cat gpurun_out/bench_$TAG.json
+timeout 600 python tools/step_breakdown.py > gpurun_out/step_breakdown_$TAG.txt 2>&1
+# 2. launch list: every launch of OUR kernels (all named k_*) with its device time
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 900 --csv \
+    --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-profile > gpurun_out/launches_$TAG.stdout 2>&1
+# 3. full captures of the widest launches of the four dominant families (one process each; -s skips the narrow early layers)
+for spec in "k_spmm:5:spmm" "k_gemm_f16:4:gemm_f16" "k_gemm_tn_f16:3:gemm_tn_f16" "k_bn_act_bwd_apply:5:bn_act_bwd"; do
+    IFS=: read kern skip name <<< "$spec"
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:^$kern -s $skip -c 1 -f -o gpurun_out/prof_${TAG}_$name \
+        python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-profile > gpurun_out/prof_${TAG}_$name.stdout 2>&1
+done
 ls -la gpurun_out/
