@@ -16,7 +16,14 @@ def timeit(fn, reps=5, warm=2):
     for _ in range(reps): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
-if 'spmm' in what:
+if what == 'spmm1':      # one width, GCN mode, for ncu captures:  bench_kernels.py spmm1 <freq> <c>
+    c = int(sys.argv[3])
+    g = ops.MeshGraph(mesh.edge_index, n, 0)
+    x = torch.randn(n, c, device=dev)
+    ms = timeit(lambda: ops.spmm(g, x))
+    print(f'spmm c={c}: {ms:.3f} ms')
+    sys.exit(0)
+if 'spmm' in what.split(','):
     for mode in (0, 1):
         g = ops.MeshGraph(mesh.edge_index, n, mode)
         for c in (4, 16, 32, 64, 128, 256, 512):
