@@ -445,7 +445,7 @@ def run_partition(args, rank, world, local_rank):
         "train_steps_per_s": args.steps / (ms / 1e3),
         "e2e": {"value": units / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(t[3]), "d2h_bytes_per_step": 8 * world,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches, "clocks": clocks, "final_loss": float(loss),
+        "gpu_launches": launches, "clocks": clocks, "final_loss": float(loss.detach()),
     }
 
 

@@ -94,7 +94,18 @@ struct SpmmArgs {
 // A warp owns "runs" of VPW consecutive vertices; run r of the grid goes to warp (r mod total warps), so the
 // co-resident warps sweep one window of X together (neighbour rows are served by L1/L2, DRAM sees X once) and the
 // warps of a CTA cover 4 adjacent runs (L1 reuse along a mesh row).
-__host__ __device__ constexpr int spmm_vpw(int) { return 32; }                          // vertices per run
+#ifndef SGB_SPMM_VPW32
+#define SGB_SPMM_VPW32 8
+#endif
+#ifndef SGB_SPMM_VPW16
+#define SGB_SPMM_VPW16 16
+#endif
+#ifndef SGB_SPMM_VPW8
+#define SGB_SPMM_VPW8 32
+#endif
+// vertices per run.  Full-warp rows (C >= 256) touch 1 KB+ per vertex: a shorter run keeps the window the grid sweeps
+// (and with it the reuse distance of a neighbour row in L2) at the size the narrower widths have.
+__host__ __device__ constexpr int spmm_vpw(int lpv) { return lpv == 32 ? SGB_SPMM_VPW32 : lpv == 16 ? SGB_SPMM_VPW16 : lpv == 8 ? SGB_SPMM_VPW8 : 32; }
 __host__ __device__ constexpr int spmm_ecap(int lpv) { return spmm_vpw(lpv) * 8; }      // staged edges per run (mean degree 6)
 __host__ __device__ constexpr int kSpmmNB(int vec, int iters) { return vec * iters >= 8 ? SGB_SPMM_NB2 : 8; }
 constexpr int kSpmmSlack = 8;                           // >= NB: a round may read up to NB - 1 slots past the staged slice
