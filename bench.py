@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--cpu-freq", type=int, default=0, help="icosphere frequency of the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel CUDA-event roofline pass")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="replay the whole train step as one CUDA graph (semigcn_b200/graphed.py): the launch-bound small-mesh regime")
     ap.add_argument("--mode", default="replicas", choices=["replicas", "partition"],
                     help="replicas: one independent mesh per GPU (default, configs[2]/[4]); partition: ONE mesh vertex-partitioned over the "
                          "GPUs with per-propagation halo exchange over NCCL (configs[3], strong scaling)")
@@ -159,10 +161,17 @@ def run_ours(args, rank, world, local_rank):
     n, nnz = mesh.num_vertices, mesh.nnz
     torch.manual_seed(314)
     net = SingleScaleGCN(dev, conv=args.conv).to(dev)
-    opt = torch.optim.Adam(net.parameters(), lr=0.01)
+    opt = torch.optim.Adam(net.parameters(), lr=0.01, capturable=args.cuda_graph)
     data = Data(z1=prob["z1"], x_pos=prob["x_pos"], edge_index=mesh.edge_index)
+    graphed = None
+    if args.cuda_graph:
+        from semigcn_b200.graphed import GraphedTrainStep
+        graphed = GraphedTrainStep(net, lambda out: step_losses(out, prob), opt, prob["z1"], prob["x_pos"], mesh.edge_index,
+                                   prob["dms"][:, 0:1].contiguous())
 
     def one_step(i, data_in, dm):
+        if graphed is not None:      # inputs (device or pinned host) are copied into the graph's static buffers, then one replay
+            return graphed(dm, None if data_in is data else data_in.z1, None if data_in is data else data_in.x_pos)
         opt.zero_grad(set_to_none=True)
         out = net(data_in, dm)
         loss = step_losses(out, prob)
@@ -194,7 +203,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---------------- per-kernel-family roofline pass (CUDA events on the launching stream)
     fam = {}
-    if not args.no_profile and rank == 0:
+    if not args.no_profile and rank == 0 and graphed is None:
         with profile.KernelProfile() as kp:
             for i in range(min(args.steps, 5)):
                 one_step(i, data, prob["dms"][:, i % 8:i % 8 + 1])
@@ -210,6 +219,10 @@ def run_ours(args, rank, world, local_rank):
     loss_host = torch.empty((), dtype=torch.float64).pin_memory()
 
     def e2e_step(i):
+        if graphed is not None:      # graph mode: the mesh (edge_index) is fixed at capture; z1 / x_pos / mask come from pinned host memory
+            loss = one_step(i, Data(z1=h["z1"], x_pos=h["x_pos"], edge_index=None), h["dms"][i % 8])
+            loss_host.copy_(loss.detach(), non_blocking=True)
+            return
         # util/networks.py:65 uploads z1 / x_pos / edge_index on every forward, :77 the mask
         d_z1.copy_(h["z1"], non_blocking=True)
         d_xp.copy_(h["x_pos"], non_blocking=True)
@@ -229,7 +242,8 @@ def run_ours(args, rank, world, local_rank):
     t1.record()
     barrier()
     ms_e2e = t0.elapsed_time(t1)
-    h2d = sum(t.numel() * t.element_size() for t in (h["z1"], h["x_pos"], h["edge_index"], h["dms"][0]))
+    h2d = sum(t.numel() * t.element_size() for t in ((h["z1"], h["x_pos"], h["dms"][0]) if graphed is not None else
+                                                       (h["z1"], h["x_pos"], h["edge_index"], h["dms"][0])))
 
     # ---------------- max over ranks
     if world > 1:
@@ -255,6 +269,10 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": launches,
         "clocks": clocks,
     }
+    if graphed is not None:
+        line["config"]["cuda_graph"] = "whole train step replayed as one CUDA graph (semigcn_b200/graphed.py); gpu_launches counted at capture"
+        line["config"]["e2e_inputs"] = "z1, x_pos, mask uploaded from pinned host memory every step into the graph's static buffers; edge_index fixed at capture"
+        line["gpu_launches"] = graphed.launches_per_replay * args.steps
     pk = peaks()
     if fam:
         groups = {}

@@ -586,12 +586,15 @@ extern "C" int sgb_spmm_halo(const int32_t* rowptr, const sgb_edge_t* edges, con
         }
         return SGB_OK;
     }
-    // the BatchNorm prologue and the halo block are rare operands: they share one (slower, fully general) instantiation
+    // the BatchNorm prologue and ragged widths are rare operands: they share one (slower, fully general) instantiation
 #define SGB_SPMM_CASE(L, V, I)                                                                                  \
     if (k.lpv == L && k.vec == V && k.iters == I) {                                                             \
-        if (pro || halo || c % (L * V * I) != 0) {                                                              \
+        if (pro || c % (L * V * I) != 0) {                                                                      \
             if (st) k_spmm<L, V, I, false, true, true, true><<<grid, kSpmmThreads, 0, stream>>>(a);             \
             else k_spmm<L, V, I, false, true, true, false><<<grid, kSpmmThreads, 0, stream>>>(a);               \
+        } else if (halo) { /* vertex-partitioned mode: the fast path plus the ghost-block select */              \
+            if (st) k_spmm<L, V, I, true, true, false, true><<<grid, kSpmmThreads, 0, stream>>>(a);             \
+            else k_spmm<L, V, I, true, true, false, false><<<grid, kSpmmThreads, 0, stream>>>(a);               \
         } else if (st) k_spmm<L, V, I, true, false, false, true><<<grid, kSpmmThreads, 0, stream>>>(a);         \
         else k_spmm<L, V, I, true, false, false, false><<<grid, kSpmmThreads, 0, stream>>>(a);                  \
         SGB_CHECK_LAUNCH("k_spmm");                                                                             \
