@@ -67,6 +67,18 @@ def peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of ``kernel`` (family_shape name) from the committed
+    ``ncu --set full`` capture summarised in profiles/ncu_traffic.json (written by tools/ncu_traffic.py); None if that
+    kernel shape has not been captured."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(p)).get(kernel)
+        return (float(d["dram_bytes"]), d.get("source")) if d else (None, None)
+    except (OSError, ValueError, KeyError):
+        return None, None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -275,6 +287,8 @@ def run_ours(args, rank, world, local_rank):
         line["gpu_launches"] = graphed.launches_per_replay * args.steps
     pk = peaks()
     if fam:
+        # families (gemm, spmm, ...) for the step breakdown; the roofline block describes the DOMINANT KERNEL = the one
+        # (family, shape) with the most time per step: its launches are identical, so "per launch" means one thing
         groups = {}
         for name, a in fam.items():
             key = name.split("_c")[0].split("_n")[0]
@@ -282,8 +296,8 @@ def run_ours(args, rank, world, local_rank):
             for k2 in ("ms", "bytes", "flops", "launches"):
                 gsum[k2] += a[k2]
         tot_ms = sum(v["ms"] for v in groups.values())
-        dom = max(groups, key=lambda k: groups[k]["ms"])
-        d = groups[dom]
+        dom = max(fam, key=lambda k: fam[k]["ms"])
+        d = fam[dom]
         gbs = d["bytes"] / (d["ms"] / 1e3) / 1e9
         tfs = d["flops"] / (d["ms"] / 1e3) / 1e12
         t_hbm, t_tc = d["bytes"] / (pk["hbm_gbs"] * 1e9), d["flops"] / (pk["bf16_tflops"] * 1e12)
@@ -291,13 +305,18 @@ def run_ours(args, rank, world, local_rank):
             roof = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"]}
         else:
             roof = {"bound": "tensor", "achieved": tfs, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": tfs / pk["bf16_tflops"]}
-        roof.update({"traffic": None, "kernel": dom, "launches_per_step": d["launches"] / prof_steps,
-                     "avg_launch_ms": d["ms"] / d["launches"], "share_of_step_kernel_time": d["ms"] / tot_ms,
-                     "peak_source": pk["source"]})
+        traffic, traffic_src = ncu_traffic(dom)
+        roof.update({"traffic": traffic, "kernel": dom, "launches_per_step": d["launches"] / prof_steps,
+                     "avg_launch_ms": d["ms"] / d["launches"], "algorithmic_bytes_per_launch": d["bytes"] / d["launches"],
+                     "share_of_step_kernel_time": d["ms"] / tot_ms,
+                     "peak_source": pk["source"], "traffic_source": traffic_src})
         line["roofline"] = roof
         line["kernel_families"] = {k: {"ms_per_step": v["ms"] / prof_steps, "GBps": v["bytes"] / (v["ms"] / 1e3) / 1e9,
                                        "TFLOPs": v["flops"] / (v["ms"] / 1e3) / 1e12, "launches_per_step": v["launches"] / prof_steps}
                                    for k, v in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])}
+        line["kernel_shapes_top"] = {k: {"ms_per_step": v["ms"] / prof_steps, "GBps": v["bytes"] / (v["ms"] / 1e3) / 1e9,
+                                         "launches_per_step": v["launches"] / prof_steps}
+                                     for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])[:8]}
         alg = algorithmic_bytes_per_step(n, nnz, SGCN_WIDTHS)
         line["step_algorithmic_GB"] = alg / 1e9
         line["step_hbm_frac"] = alg / (ms / args.steps / 1e3) / 1e9 / pk["hbm_gbs"]
