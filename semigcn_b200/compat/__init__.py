@@ -25,3 +25,18 @@ def install(force: bool = False) -> None:
             pass
     if path() not in sys.path:
         sys.path.insert(0, path())
+
+
+def patch_meshnet(meshnet_module=None) -> None:
+    """Replace the reference's ``MeshPool`` / ``MeshUnpool`` (util/meshnet.py:9-27: torch.sparse.mm plus a dense
+    [n_coarse, n_fine] row-sum on every forward) by the SpMM-kernel drop-ins of the same constructor / forward:
+
+        import util.meshnet as meshnet; compat.patch_meshnet(meshnet)      # before MGCN(...) is constructed
+
+    With no argument, patches ``util.meshnet`` if it is already imported."""
+    from semigcn_b200.nn import MeshPool, MeshUnpool
+    if meshnet_module is None:
+        meshnet_module = sys.modules.get("util.meshnet")
+        if meshnet_module is None:
+            raise RuntimeError("patch_meshnet: import util.meshnet first or pass the module")
+    meshnet_module.MeshPool, meshnet_module.MeshUnpool = MeshPool, MeshUnpool

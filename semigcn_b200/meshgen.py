@@ -225,3 +225,77 @@ def write_obj(path: str, vs: torch.Tensor, faces: torch.Tensor) -> None:
             fh.write("v %.17g %.17g %.17g\n" % (p[0], p[1], p[2]))
         for t in f:
             fh.write("f %d %d %d\n" % (t[0], t[1], t[2]))
+
+
+# ----------------------------------------------------------------------------------------
+# synthetic pooling hierarchy (stand-in for Mesh.simplification + pool_hash, util/meshnet.py:169-193)
+# ----------------------------------------------------------------------------------------
+def synth_pool_level(edge_index: torch.Tensor, n: int, ratio: float = 0.6, seed: int = 314, rounds: int = 12):
+    """One coarsening step of ``n`` vertices to ``int(n * ratio)`` clusters by contracting a matching of edges
+    (the reference contracts edges by QEM cost, util/mesh.py simplification -- out of scope; any matching exercises
+    the same MeshPool / MeshUnpool / coarse-graph code).  Returns ``(cluster_of[n] int64, n_coarse, coarse_edge_index)``;
+    ``coarse_edge_index`` follows the Mesh contract ``[unique (lo, hi) pairs || flipped]``.
+
+    Handshake matching, vectorised: every unmatched vertex proposes to its unmatched neighbour of highest random
+    priority; mutual proposals match.  Surplus pairs (beyond n - n_coarse) are dropped deterministically."""
+    dev = edge_index.device
+    n_coarse = int(n * ratio)
+    need = n - n_coarse
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    prio = torch.rand(n, generator=g).to(dev)
+    row, col = edge_index[0], edge_index[1]
+    mate = torch.full((n,), -1, dtype=torch.int64, device=dev)
+    for _ in range(rounds):
+        free = mate < 0
+        ok = free[row] & free[col]
+        if not bool(ok.any()):
+            break
+        r, c = row[ok], col[ok]
+        # best neighbour per vertex: scatter-max on (priority of neighbour), ties broken by id through the key
+        key = (prio[c] * (2 ** 20)).to(torch.int64) * n + c
+        best = torch.full((n,), -1, dtype=torch.int64, device=dev)
+        best.scatter_reduce_(0, r, key, reduce="amax", include_self=True)
+        prop = torch.where(best >= 0, best % n, torch.full_like(best, -1))
+        v = torch.arange(n, device=dev)
+        mutual = (prop >= 0) & (prop[prop.clamp(min=0)] == v) & (v < prop)
+        a, b = v[mutual], prop[mutual]
+        mate[a], mate[b] = b, a
+        if int((mate >= 0).sum()) // 2 >= need:
+            break
+    heads = torch.nonzero((mate >= 0) & (torch.arange(n, device=dev) < mate)).reshape(-1)
+    if heads.numel() > need:                       # keep exactly `need` contractions
+        drop = heads[need:]
+        mate[mate[drop]] = -1
+        mate[drop] = -1
+    rep = torch.where((mate >= 0) & (mate < torch.arange(n, device=dev)), mate, torch.arange(n, device=dev))
+    uniq, cluster = torch.unique(rep, return_inverse=True)
+    n_c = int(uniq.numel())
+    cr, cc = cluster[row], cluster[col]
+    keep = cr < cc
+    keyc = torch.unique(cr[keep] * n_c + cc[keep])
+    e = torch.stack([keyc // n_c, keyc % n_c], dim=1)
+    return cluster, n_c, edge_index_from_edges(e)
+
+
+def pool_matrices(cluster: torch.Tensor, n_coarse: int):
+    """The reference's ``pool_hash_to_mask`` / ``unpool_hash_to_mask`` (util/meshnet.py:331-341) for the (fine, coarse) pairs
+    of ``cluster``: pool [n_coarse, n_fine] and unpool [n_fine, n_coarse] sparse COO matrices of ones."""
+    n = int(cluster.numel())
+    fine = torch.arange(n, device=cluster.device)
+    ones = torch.ones(n, dtype=torch.float32, device=cluster.device)
+    pool = torch.sparse_coo_tensor(torch.stack([cluster, fine]), ones, (n_coarse, n), check_invariants=False).coalesce()
+    unpool = torch.sparse_coo_tensor(torch.stack([fine, cluster]), ones, (n, n_coarse), check_invariants=False).coalesce()
+    return pool, unpool
+
+
+def synth_pool_hierarchy(mesh: SynthMesh, levels: int = 3, ratio: float = 0.6, seed: int = 314):
+    """edge_inds[0..levels], p_hashes[0..levels-1], up_hashes[0..levels-1] as MGCN.__init__ holds them."""
+    edge_inds, p_hashes, up_hashes, sizes = [mesh.edge_index], [], [], [mesh.num_vertices]
+    for l in range(levels):
+        cluster, n_c, ei_c = synth_pool_level(edge_inds[-1], sizes[-1], ratio, seed + l)
+        pool, unpool = pool_matrices(cluster, n_c)
+        p_hashes.append(pool)
+        up_hashes.append(unpool)
+        edge_inds.append(ei_c)
+        sizes.append(n_c)
+    return {"edge_inds": edge_inds, "p_hashes": p_hashes, "up_hashes": up_hashes, "sizes": sizes}

@@ -280,6 +280,66 @@ class ConvBlockFn(torch.autograd.Function):
         return (dx, None, None, db, dgamma, dbeta, *dws)
 
 
+# ----------------------------------------------------------------------------------------
+# MeshPool / MeshUnpool (reference util/meshnet.py:9-27), on the SpMM kernel
+# ----------------------------------------------------------------------------------------
+class _SparseHashModule(nn.Module):
+    """Holds the reference's sparse "hash" matrix as a buffer of the same name (so ``state_dict`` / ``.to(device)`` behave
+    as in util/meshnet.py) and, lazily per device, the CSR pair the SpMM kernel reads."""
+
+    _buffer_name = "hash"
+
+    def __init__(self, hash_matrix: Tensor):
+        super().__init__()
+        self.register_buffer(self._buffer_name, hash_matrix)
+        self._op = None
+        self._op_key = None
+
+    def _row_scale(self, mat: Tensor) -> Optional[Tensor]:
+        return None
+
+    def _operator(self, device) -> "ops.SparseOp":
+        mat = getattr(self, self._buffer_name)
+        key = (str(device), mat._version if not mat.is_sparse else id(mat))
+        if self._op is None or self._op_key != key:
+            m = mat.to(device)
+            self._op = ops.SparseOp(m, self._row_scale(m))
+            self._op_key = key
+        return self._op
+
+    def forward(self, input: Tensor) -> Tensor:
+        require_cuda(input)
+        if input.dtype != torch.float32 or input.dim() != 2:
+            raise SgbError(f"{type(self).__name__}: expected a float32 [N, C] tensor")
+        return ops.sparse_mm(self._operator(input.device), input)
+
+
+class MeshPool(_SparseHashModule):
+    """util/meshnet.py:9-17: ``sparse.mm(pool_hash, x) / rowsum(pool_hash)`` -- the average of the fine vertices merged into
+    each coarse vertex.  The reference densifies ``pool_hash`` [n_coarse, n_fine] on every forward to get the row sums;
+    here they are folded into the CSR weights once (w = value / rowsum, so the result differs from the reference by the
+    rounding of that one division, ~1e-7 relative).  A coarse vertex with an empty row gives 0 (reference: NaN)."""
+
+    _buffer_name = "pool_hash"
+
+    def __init__(self, pool_hash: Tensor):
+        super().__init__(pool_hash)
+
+    def _row_scale(self, mat: Tensor) -> Tensor:
+        m = mat if mat.is_sparse else mat.to_sparse()
+        v_sum = torch.sparse.sum(m, dim=1).to_dense().to(torch.float32)
+        return torch.where(v_sum != 0, 1.0 / v_sum, torch.zeros_like(v_sum))
+
+
+class MeshUnpool(_SparseHashModule):
+    """util/meshnet.py:20-27: ``sparse.mm(unpool_hash, x)`` -- every fine vertex takes the row of its coarse vertex."""
+
+    _buffer_name = "unpool_hash"
+
+    def __init__(self, unpool_hash: Tensor):
+        super().__init__(unpool_hash)
+
+
 class Sequential(nn.Module):
     """torch_geometric.nn.Sequential(input_args, modules): children are registered as
     ``module_{i}``; entries are ``(module, "a, b -> c")`` or bare modules applied to the
@@ -359,6 +419,21 @@ class Sequential(nn.Module):
             vals = [env[k] for k in ins]
             if type(mod) is nn.Linear and len(vals) == 1 and vals[0].is_cuda and vals[0].dim() == 2:
                 out = ops.linear(vals[0], mod.weight, mod.bias)
+            elif (type(mod) is nn.BatchNorm1d and len(vals) == 1 and vals[0].is_cuda and vals[0].dim() == 2
+                  and vals[0].dtype == torch.float32 and len(outs) == 1):
+                # BatchNorm1d [-> LeakyReLU | ReLU] behind something that is not a conv (conv -> MeshPool -> BN -> act,
+                # util/meshnet.py:44-47,106-109): our statistics / apply / backward kernels, one autograd node
+                slope, consumed = 1.0, 1
+                if i + 1 < len(self) and self._descs[i + 1][0] == outs:
+                    act = self[i + 1]
+                    if type(act) is nn.LeakyReLU:
+                        slope, consumed = float(act.negative_slope), 2
+                    elif type(act) is nn.ReLU:
+                        slope, consumed = 0.0, 2
+                out = ops.bn_act(vals[0], mod, slope)
+                env[outs[0]] = out
+                i += consumed
+                continue
             else:
                 out = mod(*vals)
             if len(outs) == 1:

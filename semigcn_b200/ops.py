@@ -360,6 +360,86 @@ def propagate(graph: MeshGraph, x: Tensor, alpha: float = 1.0, addend: Optional[
     return PropagateFn.apply(x, graph, alpha, addend, beta)
 
 
+# ----------------------------------------------------------------------------------------
+# rectangular sparse operator (MeshPool / MeshUnpool, util/meshnet.py:9-27): y = S x on the SpMM kernel
+# ----------------------------------------------------------------------------------------
+class SparseOp:
+    """A fixed sparse matrix S [n_out, n_in] as the two CSRs the SpMM kernel consumes (forward: by row; backward: by
+    column), built once from a ``torch.sparse`` COO (or dense) tensor with plain torch ops on its device.  Entries of a
+    row are in ascending column order = the order the CPU ``torch.sparse.mm`` of the reference sums a coalesced matrix.
+    ``row_scale`` folds a per-row factor into the weights (MeshPool's division by the row sum)."""
+
+    def __init__(self, mat: Tensor, row_scale: Optional[Tensor] = None):
+        require_cuda(mat)
+        m = (mat if mat.is_sparse else mat.to_sparse()).coalesce()
+        if m.dim() != 2:
+            raise SgbError("SparseOp: expected a 2-D matrix")
+        dev = m.device
+        self.n_out, self.n_in = int(m.shape[0]), int(m.shape[1])
+        idx, val = m.indices(), m.values().to(torch.float32)
+        rows, cols = idx[0], idx[1]
+        self.nnz = int(val.numel())
+        if self.n_out >= 2 ** 31 - 1 or self.n_in >= 2 ** 31 - 1 or self.nnz >= 2 ** 31 - 1:
+            raise SgbError("SparseOp: dimensions exceed int32")
+        if row_scale is not None:
+            val = val * row_scale.to(torch.float32).reshape(-1)[rows]
+
+        def csr(r, c, v, n_r):
+            key = r * max(self.n_in, self.n_out) + c           # coalesce() already sorts (row, col); the transpose needs it
+            order = torch.argsort(key, stable=True)
+            r, c, v = r[order], c[order], v[order]
+            rowptr = torch.zeros(n_r + 1, dtype=torch.int64, device=dev)
+            rowptr[1:] = torch.cumsum(torch.bincount(r, minlength=n_r), 0)
+            edges = torch.empty((max(self.nnz, 1), 2), dtype=torch.int32, device=dev)
+            edges.zero_()
+            edges[:self.nnz, 0] = c.to(torch.int32)
+            edges[:self.nnz, 1] = v.contiguous().view(torch.int32)
+            return rowptr.to(torch.int32).contiguous(), edges.contiguous()
+
+        self.rowptr, self.edges = csr(rows, cols, val, self.n_out)
+        self.rowptr_t, self.edges_t = csr(cols, rows, val, self.n_in)
+        self._dis = torch.zeros(1, dtype=torch.float32, device=dev)    # not read in SGB_MODE_ADJ; the ABI wants a pointer
+        self.device = dev
+
+    def apply(self, x: Tensor, transpose: bool = False) -> Tensor:
+        lib = L.load()
+        require_cuda(x)
+        x = _f32c(x, "x")
+        n_in, n_out = (self.n_out, self.n_in) if transpose else (self.n_in, self.n_out)
+        if x.dim() != 2 or x.shape[0] != n_in:
+            raise SgbError(f"SparseOp: x has {tuple(x.shape)} rows/cols, expected {n_in} rows")
+        c = int(x.shape[1])
+        y = torch.empty((n_out, c), dtype=torch.float32, device=x.device)
+        rowptr, edges = (self.rowptr_t, self.edges_t) if transpose else (self.rowptr, self.edges)
+        sp = _prof.span(f"sparse_mm_c{c}", 4.0 * ((n_in + n_out) * c + 2 * self.nnz + n_out + 1), 2.0 * self.nnz * c) \
+            if _prof.ACTIVE is not None else None
+        with torch.cuda.device(x.device):
+            check(lib.sgb_spmm(ptr(rowptr), ptr(edges), ptr(self._dis), MODE_ADJ, ptr(x), x.stride(0), n_out, c,
+                               None, None, None, 0.0, 1.0, None, 0, 0.0, None, ptr(y), y.stride(0), None, None,
+                               stream_ptr(x.device)), "sgb_spmm (SparseOp)")
+        if sp is not None:
+            sp.close()
+        L.count(1)
+        return y
+
+
+class SparseMMFn(torch.autograd.Function):
+    """y = S x;  dx = S^T dy (gather over the by-column CSR: atomic-free, deterministic)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, op: SparseOp):
+        ctx.op = op
+        return op.apply(x)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        return (ctx.op.apply(dy.contiguous(), transpose=True) if ctx.needs_input_grad[0] else None), None
+
+
+def sparse_mm(op: SparseOp, x: Tensor) -> Tensor:
+    return SparseMMFn.apply(x, op)
+
+
 class LinearFn(torch.autograd.Function):
     """y = x W^T (+ b) on our GEMM tiles; dX = dY W, dW = dY^T X (split-m, fixed order), db = colsum(dY)."""
 
