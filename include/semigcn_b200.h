@@ -102,6 +102,10 @@ SGB_API int sgb_graph_build(const int64_t* edge_index, int64_t nnz, int64_t n, i
  *    called with the transpose CSR, bwd.
  *    amax_out (optional, device float zeroed by the caller) receives max |Y| (atomicMax on the float
  *    bits): the scale of the fp16-split GEMM engine that consumes Y (sgb_gemm a_amax), for free.
+ *    SGB_MODE_ADJ takes any CSR whose packed stream carries its own weights -- also a RECTANGULAR one
+ *    (n = rows of Y; column ids index rows of X, which may have any row count > max column id; dis is
+ *    not read): this is how MeshPool / MeshUnpool (reference util/meshnet.py:9-27, torch.sparse.mm of
+ *    the pool / unpool "hash" matrices) run, forward on the by-row CSR, backward on the by-column one.
  * ------------------------------------------------------------------------------------ */
 SGB_API int sgb_spmm_stat_rows(int64_t n, int c);
 SGB_API int sgb_spmm(const int32_t* rowptr, const sgb_edge_t* edges, const float* dis, int mode,

@@ -32,7 +32,7 @@ class GraphedTrainStep:
                  z1: Tensor, x_pos: Tensor, edge_index: Tensor, dm: Tensor, warmup: int = 3, accumulate: int = 1):
         """``loss_fn(out) -> scalar`` closes over its (static) targets.  ``accumulate``: optimizer steps every that many
         calls (sgcn.py:40,146 steps every 5 masks): the graph then holds forward + backward only when it is > 1."""
-        require_cuda(z1, x_pos, edge_index, dm)
+        require_cuda(z1, x_pos, dm)          # edge_index may be None for networks that hold their graphs (MGCN)
         for g in optimizer.param_groups:
             if not g.get("capturable", False) and accumulate == 1:
                 raise SgbError("GraphedTrainStep: the optimizer must be built with capturable=True")
