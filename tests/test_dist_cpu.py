@@ -83,3 +83,42 @@ def _worker(rank, world, port, freq):
 @pytest.mark.parametrize("world", [2, 3])
 def test_halo_exchange_over_gloo(world):
     mp.spawn(_worker, args=(world, _free_port(), 6), nprocs=world, join=True)
+
+
+def test_merge_moment_rows_matches_direct_statistics():
+    """SyncBN pre-reduction (semigcn_b200.ops.merge_moment_rows): folding per-tile (count, mean, M2) rows -- ragged tiles,
+    empty rows, a near-constant channel -- gives the statistics of the concatenated data."""
+    from semigcn_b200.ops import merge_moment_rows
+    g = torch.Generator().manual_seed(3)
+    c = 7
+    sizes = [128, 128, 0, 37, 1, 128, 0, 5]
+    chunks = [torch.randn(s, c, generator=g, dtype=torch.float64) * 3.0 + torch.arange(c) for s in sizes]
+    for ch in chunks:
+        if ch.shape[0]:
+            ch[:, 2] = 1000.0 + 1e-3 * ch[:, 2]          # |mean| >> std: sum / sum-of-squares forms lose this one
+    rows = []
+    for ch in chunks:
+        if ch.shape[0] == 0:
+            rows.append(torch.zeros(3, c, dtype=torch.float64))
+        else:
+            mu = ch.mean(0)
+            rows.append(torch.stack([torch.full((c,), float(ch.shape[0]), dtype=torch.float64), mu, ((ch - mu) ** 2).sum(0)]))
+    part = torch.stack(rows).to(torch.float32)
+    out = merge_moment_rows(part)
+    assert out.shape == (1, 3, c) and out.dtype == torch.float32
+    allx = torch.cat(chunks)
+    assert torch.equal(out[0, 0], torch.full((c,), float(allx.shape[0])))
+    assert torch.allclose(out[0, 1].double(), allx.mean(0), rtol=1e-6, atol=0)
+    m2 = ((allx - allx.mean(0)) ** 2).sum(0)
+    keep = torch.tensor([q != 2 for q in range(c)])
+    assert torch.allclose(out[0, 2].double()[keep], m2[keep], rtol=1e-5, atol=0)
+    # the near-constant channel: the per-row means were rounded to float32 (ulp 6e-5 at 1000, spread 3e-3) before merging
+    assert torch.allclose(out[0, 2].double()[2], m2[2], rtol=2e-3, atol=0)
+    # all-empty input stays empty (no NaN)
+    z = merge_moment_rows(torch.zeros(4, 3, c))
+    assert torch.equal(z, torch.zeros(1, 3, c))
+    # merging merged rows of two halves == merging everything (associativity, what the all-gather relies on)
+    two = torch.cat([merge_moment_rows(part[:4]), merge_moment_rows(part[4:])])
+    again = merge_moment_rows(two)
+    assert torch.allclose(again.double()[..., keep], out.double()[..., keep], rtol=1e-6, atol=0)
+    assert torch.allclose(again.double()[..., 2], out.double()[..., 2], rtol=1e-3, atol=0)     # float32 rows in between
