@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel CUDA-event roofline pass")
     ap.add_argument("--cuda-graph", action="store_true",
                     help="replay the whole train step as one CUDA graph (semigcn_b200/graphed.py): the launch-bound small-mesh regime")
+    ap.add_argument("--order", default="given", choices=["given", "morton"],
+                    help="partition mode: vertex numbering the contiguous cut is taken on (morton: Z-order renumbering, balanced halos; "
+                         "CPU-tested, not yet timed on GPUs)")
     ap.add_argument("--mode", default="replicas", choices=["replicas", "partition"],
                     help="replicas: one independent mesh per GPU (default, configs[2]/[4]); partition: ONE mesh vertex-partitioned over the "
                          "GPUs with per-propagation halo exchange over NCCL (configs[3], strong scaling)")
@@ -391,11 +394,18 @@ def run_partition(args, rank, world, local_rank):
     prob = make_problem(args.freq, dev, seed=314)            # the same mesh on every rank
     mesh = prob["mesh"]
     n, nnz = mesh.num_vertices, mesh.nnz
-    plan = partition.build_plan(mesh.edge_index, n, rank, world)
+    ei_global = mesh.edge_index
+    if args.order == "morton":
+        perm = partition.morton_order(mesh.vs)
+        ei_global, z1_, xp_, ini_, vm_, dms_ = partition.renumber(perm, mesh.edge_index, prob["z1"], prob["x_pos"], prob["ini"],
+                                                                  prob["v_mask"], prob["dms"])
+        prob.update(z1=z1_, x_pos=xp_, ini=ini_, v_mask=vm_, dms=dms_)
+        ei_global = ei_global.contiguous()
+    plan = partition.build_plan(ei_global, n, rank, world)
     lo, hi = plan.lo, plan.hi
     own = {k: prob[k][lo:hi].contiguous() for k in ("z1", "x_pos", "ini", "v_mask", "dms")}
     halo_rows = plan.n_ghost
-    del prob, mesh
+    del prob, mesh, ei_global
     torch.cuda.empty_cache()
     ei_local = register_partition(plan, comm, modes=(MODE_GCN if args.conv == "gcnconv" else MODE_CHEB,))
     torch.manual_seed(314)
@@ -477,7 +487,7 @@ def run_partition(args, rank, world, local_rank):
                                "BASELINE.json configs[3] at the largest size that also fits one GPU",
                    "vertices": n, "directed_edges": nnz, "conv_layers": N_LAYERS,
                    "parallelism": f"vertex partition x{world}: halo all-to-all per propagation (NCCL), SyncBN partial all-gather, grad all-reduce",
-                   "halo_rows_total": int(t[2]), "halo_rows_max_per_rank": int(tmax[2]),
+                   "halo_rows_total": int(t[2]), "halo_rows_max_per_rank": int(tmax[2]), "vertex_order": args.order,
                    "l2_policy": "inputs larger than L2; no explicit flush"},
         "train_steps_per_s": args.steps / (ms / 1e3),
         "e2e": {"value": units / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(t[3]), "d2h_bytes_per_step": 8 * world,

@@ -122,3 +122,31 @@ def test_merge_moment_rows_matches_direct_statistics():
     again = merge_moment_rows(two)
     assert torch.allclose(again.double()[..., keep], out.double()[..., keep], rtol=1e-6, atol=0)
     assert torch.allclose(again.double()[..., 2], out.double()[..., 2], rtol=1e-3, atol=0)     # float32 rows in between
+
+
+def test_morton_order_balances_the_cut():
+    """partition.morton_order: a permutation; renumbering keeps the graph; contiguous ranges of the new numbering give
+    every rank a similar halo (the generator's numbering gives rank 0 -- the owner of the icosahedron edge vertices --
+    several times the average), and the plans stay mutually consistent."""
+    m = meshgen.icosphere(30)
+    n, world = m.num_vertices, 8
+    perm = partition.morton_order(m.vs)
+    assert torch.equal(torch.sort(perm)[0], torch.arange(n))
+    ei2, vs2 = partition.renumber(perm, m.edge_index, m.vs)
+    assert torch.equal(vs2, m.vs[perm])
+    # same undirected graph: degrees are permuted, edge count unchanged, endpoints map back
+    assert torch.equal(torch.bincount(ei2[1], minlength=n), torch.bincount(m.edge_index[1], minlength=n)[perm])
+    assert torch.equal(perm[ei2], m.edge_index)
+    ghosts_given = [partition.build_plan(m.edge_index, n, r, world).n_ghost for r in range(world)]
+    plans = [partition.build_plan(ei2, n, r, world) for r in range(world)]
+    ghosts = [p.n_ghost for p in plans]
+    mean_g, mean_given = sum(ghosts) / world, sum(ghosts_given) / world
+    assert max(ghosts) <= 2.0 * mean_g, (ghosts, ghosts_given)
+    assert max(ghosts) < max(ghosts_given), (ghosts, ghosts_given)
+    for r, p in enumerate(plans):
+        off = 0
+        for q in range(world):
+            so = sum(plans[q].send_counts[:r])
+            sent = plans[q].send_idx[so:so + plans[q].send_counts[r]].long() + plans[q].lo
+            assert torch.equal(p.ghost_gid[off:off + p.recv_counts[q]], sent)
+            off += p.recv_counts[q]
