@@ -240,3 +240,46 @@ def mask_norm_rec_loss(pred_norm: Tensor, real_norm: Tensor, mask: Tensor) -> Te
     m = mask.to(pred_norm.device).to(real_norm.dtype).reshape(-1, 1)
     d = torch.abs(pred_norm - real_norm)
     return torch.sum(d * m) / torch.sum(m)
+
+
+def fn_bnf_detach_loss(pos: Tensor, fn: Tensor, faces: Tensor, f2f: Tensor, ltype: str = "l1mae", loop: int = 5):
+    """util/loss.py:197-253 (the ``-CAD`` regulariser, sgcn.py:133-136): bilateral filtering of the face normals over the
+    1-ring ``f2f`` (weights exp(-|dc|^2 / 2 sigma_c^2) exp(-|dn|^2 / 2 sigma_s^2) area, sigma_s = 0.3, sigma_c = mean
+    centroid distance, ``loop`` detached iterations) and the distance of ``fn`` to the filtered normals.  Returns
+    ``(loss, new_fn)`` like the reference.  Plain torch ops on the caller's device (v0: ~40 small kernels per call; the
+    fused gather kernel is a next-round row); ``faces`` / ``f2f`` are int64 tensors (``mesh.faces``,
+    ``mesh.f2f`` or ``meshgen.face_adjacency``), -1 = no neighbour."""
+    if ltype not in ("mae", "l1mae", "rmse", "l1rmse"):
+        raise SgbError(f"fn_bnf_detach_loss: unknown ltype {ltype!r}")
+    dev = fn.device
+    pos = pos.detach().to(dev)
+    faces, f2f = faces.to(dev).long(), f2f.to(dev).long()
+    fc = torch.sum(pos[faces], 1) / 3.0
+    fa = torch.linalg.cross(pos[faces[:, 1]] - pos[faces[:, 0]], pos[faces[:, 2]] - pos[faces[:, 0]])
+    fa = 0.5 * torch.sqrt(torch.sum(fa ** 2, dim=1) + 1.0e-12)
+    no_neig = 1.0 * (f2f != -1)
+    neig_fc = fc[f2f]                                  # -1 wraps to the last face exactly as the reference's indexing does
+    neig_fa = fa[f2f] * no_neig
+    fc_dist = torch.sum((neig_fc - fc.reshape(-1, 1, 3)) ** 2, dim=2)
+    sigma_c = torch.sum(torch.sqrt(fc_dist + 1.0e-12)) / (fc_dist.shape[0] * fc_dist.shape[1])
+    wc = torch.exp(-1.0 * fc_dist / (2 * (sigma_c ** 2)))
+    new_fn = fn
+    for _ in range(loop):
+        neig_fn = new_fn[f2f]
+        fn_dist = torch.sum((neig_fn - new_fn.reshape(-1, 1, 3)) ** 2, dim=2)
+        ws = torch.exp(-1.0 * fn_dist / (2 * (0.3 ** 2)))
+        w = (wc * ws * neig_fa).unsqueeze(2)
+        new_fn = torch.sum(w * neig_fn, dim=1)
+        new_fn = new_fn / (torch.sqrt(torch.sum(new_fn * new_fn, dim=1, keepdim=True) + 1.0e-12) + 1.0e-12)
+        new_fn = new_fn.detach()
+    if ltype == "mae":
+        loss = torch.sum(torch.sqrt(torch.sum((new_fn - fn) ** 2, dim=1) + 1.0e-12)) / fn.shape[0]
+    elif ltype == "l1mae":
+        loss = torch.sum(torch.sum(torch.abs(new_fn - fn), dim=1)) / fn.shape[0]
+    elif ltype == "rmse":
+        loss = torch.sqrt(torch.sum(torch.sum((new_fn - fn) ** 2, dim=1)) / fn.shape[0] + 1.0e-12)
+    else:   # "l1rmse" exactly as written in the reference (util/loss.py:246-249)
+        d = torch.sum(torch.abs(new_fn - fn), dim=1)
+        loss = torch.sum(d ** 2) / fn.shape[0]
+        loss = torch.sqrt(loss ** 2 + 1.0e-12)
+    return loss, new_fn

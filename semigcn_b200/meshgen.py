@@ -299,3 +299,27 @@ def synth_pool_hierarchy(mesh: SynthMesh, levels: int = 3, ratio: float = 0.6, s
         edge_inds.append(ei_c)
         sizes.append(n_c)
     return {"edge_inds": edge_inds, "p_hashes": p_hashes, "up_hashes": up_hashes, "sizes": sizes}
+
+
+def face_adjacency(faces: torch.Tensor) -> torch.Tensor:
+    """``f2f`` [F, 3] of the reference's ``Mesh`` (util/mesh.py:215-227): the faces sharing a side with face i, padded with
+    -1 where a side is on a boundary.  Vectorised half-edge matching; slot s holds the face across side
+    (f[s], f[(s+1)%3]) -- the reference lists the same set in its ``Counter`` insertion order, which only changes the order
+    of a 3-term sum in ``fn_bnf_detach_loss``.  Non-manifold sides (more than two faces) keep the first match."""
+    f = faces.to(torch.int64)
+    nf = int(f.shape[0])
+    nv = int(f.max().item()) + 1 if nf else 0
+    a, b = f.reshape(-1), f[:, [1, 2, 0]].reshape(-1)
+    key = torch.minimum(a, b) * nv + torch.maximum(a, b)
+    skey, order = torch.sort(key, stable=True)
+    he_face = order // 3
+    same_next = torch.zeros_like(skey, dtype=torch.bool)
+    same_next[:-1] = skey[:-1] == skey[1:]
+    same_prev = torch.zeros_like(skey, dtype=torch.bool)
+    same_prev[1:] = skey[1:] == skey[:-1]
+    mate = torch.full((3 * nf,), -1, dtype=torch.int64, device=f.device)
+    idx = torch.arange(3 * nf, device=f.device)
+    nxt = torch.where(same_next, he_face[(idx + 1).clamp(max=3 * nf - 1)], torch.full_like(idx, -1))
+    prv = torch.where(same_prev, he_face[(idx - 1).clamp(min=0)], torch.full_like(idx, -1))
+    mate[order] = torch.where(prv >= 0, prv, nxt)
+    return mate.reshape(nf, 3)

@@ -209,3 +209,36 @@ def test_oracle_sgcn_matches_reference_networks_py(conv, skip):
     net.eval()
     y = net(z1, x_pos, ei, dm)
     assert torch.equal(y.detach(), torch.from_numpy(gold[f"{tag}_eval"]))
+
+
+@pytest.mark.parametrize("n", [4, 8])
+def test_fn_bnf_detach_loss_matches_reference(n):
+    """The -CAD regulariser (util/loss.py:197-253) as torch ops (semigcn_b200.losses.fn_bnf_detach_loss; device-agnostic,
+    so the same code is checked here on CPU) against the reference's own output on the reference's own ``Mesh.f2f``,
+    and the vectorised ``f2f`` builder against the reference's (same neighbour sets; slot order is the reference's
+    Counter order there, side order here -- a reordering of a 3-term sum)."""
+    from semigcn_b200 import losses, meshgen
+    gold = load_golden(n)
+    pred = torch.from_numpy(gold["pred"])
+    faces = torch.from_numpy(gold["faces"]).long()
+    f2f_ref = torch.from_numpy(gold["f2f"]).long()
+    fn_pred = torch.from_numpy(gold["compute_fn_f32"])
+    loss, new_fn = losses.fn_bnf_detach_loss(pred, fn_pred, faces, f2f_ref, loop=5)
+    assert torch.allclose(new_fn, torch.from_numpy(gold["bnf_fn_f32"]), rtol=0, atol=1e-6)
+    assert abs(float(loss) - float(gold["loss_bnf_f32"])) <= 1e-6 * abs(float(gold["loss_bnf_f32"]))
+    f2f = meshgen.face_adjacency(faces)
+    assert f2f.shape == f2f_ref.shape
+    assert torch.equal(torch.sort(f2f, dim=1)[0], torch.sort(f2f_ref, dim=1)[0])
+    loss2, new_fn2 = losses.fn_bnf_detach_loss(pred, fn_pred, faces, f2f, loop=5)
+    assert torch.allclose(new_fn2, new_fn, rtol=0, atol=1e-6)
+    assert abs(float(loss2) - float(loss)) <= 1e-6 * abs(float(loss))
+    # a mesh with a boundary: drop some faces -> -1 slots, no crash, symmetric adjacency
+    keep = torch.ones(faces.shape[0], dtype=torch.bool)
+    keep[::7] = False
+    f_open = faces[keep]
+    adj = meshgen.face_adjacency(f_open)
+    assert int((adj == -1).sum()) > 0
+    i = torch.arange(adj.shape[0]).repeat_interleave(3)
+    j = adj.reshape(-1)
+    ok = j >= 0
+    assert bool(((adj[j[ok]] == i[ok].unsqueeze(1)).any(dim=1)).all())
