@@ -32,15 +32,7 @@ namespace sgb {
 #ifndef SGB_SPMM_ITERS
 #define SGB_SPMM_ITERS 2
 #endif
-#ifndef SGB_SPMM_RC
-#define SGB_SPMM_RC 0             // experiment (measured slower): register cache of the rows of v-1 / v
-#endif
-#ifndef SGB_SPMM_RC_MINLPV
-#define SGB_SPMM_RC_MINLPV 32
-#endif
-#ifndef SGB_SPMM_SPAN_DEFAULT
-#define SGB_SPMM_SPAN_DEFAULT 0   // span schedule off unless SGB_SPMM_SPAN is set (see span_lpv)
-#endif
+
 constexpr int kSpmmThreads = 128;                       // 4 autonomous warps per CTA
 constexpr int kSpmmWarps = kSpmmThreads / 32;
 
@@ -54,14 +46,12 @@ struct Vec<4> {
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     }
     __device__ __forceinline__ void store(float* p) const { st4(p, make_float4(v[0], v[1], v[2], v[3])); }
-    __device__ __forceinline__ void store_cs(float* p) const { __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3])); }
 };
 template <>
 struct Vec<1> {
     float v[1];
     __device__ __forceinline__ void load(const float* p) { v[0] = __ldg(p); }
     __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
-    __device__ __forceinline__ void store_cs(float* p) const { __stcs(p, v[0]); }
 };
 
 struct SpmmArgs {
@@ -109,7 +99,6 @@ __host__ __device__ constexpr int spmm_vpw(int lpv) { return lpv == 32 ? SGB_SPM
 __host__ __device__ constexpr int spmm_ecap(int lpv) { return spmm_vpw(lpv) * 8; }      // staged edges per run (mean degree 6)
 __host__ __device__ constexpr int kSpmmNB(int vec, int iters) { return vec * iters >= 8 ? SGB_SPMM_NB2 : 8; }
 constexpr int kSpmmSlack = 8;                           // >= NB: a round may read up to NB - 1 slots past the staged slice
-constexpr int kSpanWarps = 16;                          // warps per CTA of the span schedule (one CTA per SM)
 __host__ __device__ constexpr int spmm_smem_ints(int lpv, int vec, int iters, bool stats, int nw) {
     const int stage = nw * 2 * ((spmm_vpw(lpv) + 2) + 2 * (spmm_ecap(lpv) + kSpmmSlack));
     const int stat = stats ? 2 * nw * 32 * vec * iters + nw * 32 : 0;
@@ -132,24 +121,20 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 // row are issued together, branch-free -- slots past the row's degree re-read its last neighbour with weight 0
 // (acc + 0*x is exact), so the gather code is straight-line and the loads of a whole round are in flight at once.
 // FULL: c is a multiple of the pass width (every lane active, no channel predicates).
-template <int LPV, int VEC, int ITERS, bool FULL, bool HALO, bool PRO, bool STATS, int NW = kSpmmWarps, bool SPAN = false>
-__global__ void __launch_bounds__(NW * 32, NW != kSpmmWarps ? 1 : ((VEC * ITERS >= 8) ? (STATS ? SGB_SPMM_MINB2 - 1 : SGB_SPMM_MINB2) : 6)) k_spmm(const SpmmArgs a) {
+template <int LPV, int VEC, int ITERS, bool FULL, bool HALO, bool PRO, bool STATS>
+__global__ void __launch_bounds__(kSpmmThreads, (VEC * ITERS >= 8) ? (STATS ? SGB_SPMM_MINB2 - 1 : SGB_SPMM_MINB2) : 6) k_spmm(const SpmmArgs a) {
     constexpr int NB = kSpmmNB(VEC, ITERS);                 // neighbour rows in flight per round (register budget)
     constexpr int CH = LPV * VEC * ITERS;                   // channels per pass
     constexpr int SUB = 32 / LPV;                           // sub-warps (vertices in lock-step) per warp
     constexpr int VPW = spmm_vpw(LPV);
     constexpr int ECAP = spmm_ecap(LPV);
-    constexpr int THREADS = NW * 32;
-    constexpr bool RC = SGB_SPMM_RC && FULL && !HALO && !PRO && !SPAN && VEC == 4 && LPV >= SGB_SPMM_RC_MINLPV;
+    constexpr int NW = kSpmmWarps, THREADS = kSpmmThreads;
     constexpr int STAT_FLOATS = STATS ? 2 * THREADS * VEC * ITERS + THREADS : 0;
     constexpr int EBUF = ECAP + kSpmmSlack;                 // int2 slots per edge buffer
     constexpr int STAGE_INTS = NW * 2 * ((VPW + 2) + 2 * EBUF);
     constexpr int SMEM_INTS = spmm_smem_ints(LPV, VEC, ITERS, STATS, NW);
     static_assert(SMEM_INTS >= STAGE_INTS && SMEM_INTS >= STAT_FLOATS, "shared-memory sizing");
-    // 4-warp CTAs: static shared memory; the 16-warp span CTAs need > 48 KB -> dynamic
-    __shared__ __align__(16) int smem_static[NW == kSpmmWarps ? SMEM_INTS : 4];
-    extern __shared__ __align__(16) int smem_dyn[];
-    int* const smem_raw = NW == kSpmmWarps ? smem_static : smem_dyn;
+    __shared__ __align__(16) int smem_raw[SMEM_INTS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int l = lane & (LPV - 1);
     const int sub = lane / LPV;
@@ -161,24 +146,12 @@ __global__ void __launch_bounds__(NW * 32, NW != kSpmmWarps ? 1 : ((VEC * ITERS 
         return reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + (uint64_t)row * stride_b);
     };
 
-    // Run schedule: position ri of this warp is run  gw + ri * tw.
-    //   interleaved (default): run r of the grid goes to warp r mod (#warps in the grid);
-    //   SPAN: the CTA owns a contiguous span of runs and its NW warps sweep it together, so the rows of the previous /
-    //         next mesh rows (touched a few hundred vertices ago) are still in this SM's L1 when they are needed again.
+    // Run schedule: position ri of this warp is run  gw + ri * tw, i.e. run r of the grid goes to warp r mod (#warps in the
+    // grid).  (A per-SM contiguous-span schedule with channel slices was measured slower: DESIGN.md §5.2.)
     const int64_t nruns = (a.n + VPW - 1) / VPW;
-    int64_t gw, tw, rcount;
-    if (SPAN) {
-        const int64_t rpc = (nruns + gridDim.x - 1) / gridDim.x;
-        const int64_t fr = (int64_t)blockIdx.x * rpc;
-        const int64_t rc = nruns > fr ? min64(rpc, nruns - fr) : 0;
-        gw = fr + warp;
-        tw = NW;
-        rcount = rc > warp ? (rc - 1 - warp) / NW + 1 : 0;
-    } else {
-        gw = (int64_t)blockIdx.x * NW + warp;
-        tw = (int64_t)gridDim.x * NW;
-        rcount = nruns > gw ? (nruns - 1 - gw) / tw + 1 : 0;
-    }
+    const int64_t gw = (int64_t)blockIdx.x * NW + warp;
+    const int64_t tw = (int64_t)gridDim.x * NW;
+    const int64_t rcount = nruns > gw ? (nruns - 1 - gw) / tw + 1 : 0;
 
     auto stage_rowptr = [&](int64_t ri, int buf) {         // async; ri (schedule position) may be past the end
         if (ri < rcount) {
@@ -248,26 +221,19 @@ __global__ void __launch_bounds__(NW * 32, NW != kSpmmWarps ? 1 : ((VEC * ITERS 
             // rows are too long to stage)
             auto gather = [&](auto staged_tag) {
                 constexpr bool STAGED = decltype(staged_tag)::value;
-                // RC: a sub-warp walks CONSECUTIVE vertices and keeps the rows of v-1 and v in registers: on a mesh numbering
-                // where v-1 / v+1 are neighbours of v (grid-like orders) 2 of the 7 rows of a vertex are not gathered again
-                // (the row of v+1 arrives as a neighbour of v and is kept as the next self row).  Same values, same order.
-                constexpr int PER = VPW / SUB;
-                const int vi_begin = RC ? sub * PER : sub;
-                const int vi_end = RC ? min(nv, sub * PER + PER) : nv;
-                constexpr int vi_step = RC ? 1 : SUB;
-                const bool rc = RC && a.mode != SGB_MODE_ADJ;
-                Vec<VEC> prv[ITERS], xself[ITERS];
-                bool prv_ok = false, self_ok = false;
+                // The self-row registers live across the vertex loop (zeroed once, reloaded per vertex): re-zeroing them per
+                // vertex made the next vertex's address arithmetic wait on the previous vertex's loads (13-18 % slower, §5.2).
+                // (Keeping the rows of v-1 / v cached in registers to save 2 of the 7 gathers was measured slower as well.)
+                Vec<VEC> xself[ITERS];
 #pragma unroll
                 for (int t = 0; t < ITERS; ++t)
 #pragma unroll
-                    for (int q = 0; q < VEC; ++q) { prv[t].v[q] = 0.f; xself[t].v[q] = 0.f; }
+                    for (int q = 0; q < VEC; ++q) xself[t].v[q] = 0.f;
 #pragma unroll 1
-                for (int vi = vi_begin; vi < vi_end; vi += vi_step) {
+                for (int vi = sub; vi < nv; vi += SUB) {
                     const int kb = srp[vi] - e0, ke = srp[vi + 1] - e0;
                     const int64_t v = v0 + vi;
                     Vec<VEC> acc[ITERS];
-                    unsigned next_mask = 0;
                     float di = 0.f;
 #pragma unroll
                     for (int t = 0; t < ITERS; ++t)
@@ -275,30 +241,21 @@ __global__ void __launch_bounds__(NW * 32, NW != kSpmmWarps ? 1 : ((VEC * ITERS 
                         for (int q = 0; q < VEC; ++q) acc[t].v[q] = 0.f;
                     if (a.mode != SGB_MODE_ADJ) {                 // the self row rides along with the first round of gathers
                         if (a.mode == SGB_MODE_GCN) di = __ldg(a.dis + v);
-                        if (!(rc && self_ok)) {
-                            const float* xs = row_of(xl, (uint32_t)v, ldx_b);
+                        const float* xs = row_of(xl, (uint32_t)v, ldx_b);
 #pragma unroll
-                            for (int t = 0; t < ITERS; ++t)
-                                if (t == 0 || act[t]) xself[t].load(xs + t * LPV * VEC);
-                        }
+                        for (int t = 0; t < ITERS; ++t)
+                            if (t == 0 || act[t]) xself[t].load(xs + t * LPV * VEC);
                     }
 #pragma unroll 1
                     for (int r = kb; r < ke; r += NB) {
                         Vec<VEC> xv[NB][ITERS];
                         float w[NB];
                         const int left = ke - r;
-                        const bool last_round = r + NB >= ke;
 #pragma unroll
                         for (int b = 0; b < NB; ++b) {
                             // slots past the row's end: a valid (stale or next-row) vertex id with weight 0
                             const int2 ed = STAGED ? sedge[r + b] : __ldg(a.edges + e0 + min(r + b, ke - 1));
                             w[b] = (b < left) ? __int_as_float(ed.y) : 0.f;
-                            if (rc && prv_ok && ed.x == (int)v - 1) {
-#pragma unroll
-                                for (int t = 0; t < ITERS; ++t) xv[b][t] = prv[t];
-                                continue;
-                            }
-                            if (rc && last_round && ed.x == (int)v + 1) next_mask |= 1u << b;
                             // owned rows live in x, halo (ghost) rows of the partitioned mode in xg
                             const float* xr = (!HALO || ed.x < a.split) ? row_of(xl, (uint32_t)ed.x, ldx_b) : row_of(xgl, (uint32_t)(ed.x - a.split), ldxg_b);
 #pragma unroll
@@ -322,17 +279,8 @@ __global__ void __launch_bounds__(NW * 32, NW != kSpmmWarps ? 1 : ((VEC * ITERS 
                                     acc[t].v[q] = __fadd_rn(acc[t].v[q], __fmul_rn(w[b], xx));
                                 }
                         }
-                        if (rc && next_mask != 0) {   // last round: prv is dead from here on, it carries the row of v+1 to the end of this vertex
-#pragma unroll
-                            for (int b = 0; b < NB; ++b)
-                                if ((next_mask >> b) & 1u) {
-#pragma unroll
-                                    for (int t = 0; t < ITERS; ++t) prv[t] = xv[b][t];
-                                }
-                        }
                     }
                     const float wii = __fmul_rn(di, di);
-                    const bool got_next = rc && next_mask != 0;
 #pragma unroll
                     for (int t = 0; t < ITERS; ++t) {
                         if (!act[t]) continue;
@@ -365,8 +313,7 @@ __global__ void __launch_bounds__(NW * 32, NW != kSpmmWarps ? 1 : ((VEC * ITERS 
 #pragma unroll
                             for (int q = 0; q < VEC; ++q) out.v[q] = __fadd_rn(out.v[q], bs.v[q]);
                         }
-                        if (SPAN) out.store_cs(a.y + v * a.ldy + ch[t]);      // written once: keep it out of the way of the X rows
-                        else out.store(a.y + v * a.ldy + ch[t]);
+                        out.store(a.y + v * a.ldy + ch[t]);
                         if (a.amax) {
 #pragma unroll
                             for (int q = 0; q < VEC; ++q) amx = fmaxf(amx, fabsf(out.v[q]));
@@ -382,18 +329,6 @@ __global__ void __launch_bounds__(NW * 32, NW != kSpmmWarps ? 1 : ((VEC * ITERS 
                         }
                     }
                     nseen += 1.f;
-                    if (rc) {                                     // v becomes v-1; the row of v+1, if the last round gathered it, the next self row
-#pragma unroll
-                        for (int t = 0; t < ITERS; ++t)
-#pragma unroll
-                            for (int q = 0; q < VEC; ++q) {
-                                const float nx = prv[t].v[q];
-                                prv[t].v[q] = xself[t].v[q];
-                                xself[t].v[q] = nx;
-                            }
-                        prv_ok = true;
-                        self_ok = got_next;
-                    }
                 }
             };
             if (staged) gather(std::true_type{});
@@ -479,43 +414,6 @@ static int spmm_grid(int64_t n, const SpmmCfg& k, bool stats) {
     return (int)(need < cap ? need : cap);
 }
 
-// ---- span schedule (one 16-warp CTA per SM sweeping a contiguous vertex span, channels in slices of 8 * LPV) ----
-// SGB_SPMM_SPAN = 0 (off) | 4 | 8 | 16: sub-warp width of the span configuration (slice = 32 / 64 / 128 channels).
-static int span_lpv() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("SGB_SPMM_SPAN");
-        v = e ? atoi(e) : SGB_SPMM_SPAN_DEFAULT;
-        if (v != 4 && v != 8 && v != 16) v = 0;
-    }
-    return v;
-}
-static int64_t span_min_rows() {
-    static int64_t v = -1;
-    if (v < 0) {
-        const char* e = getenv("SGB_SPMM_SPAN_MIN_ROWS");
-        v = e ? atoll(e) : (int64_t)1 << 17;
-    }
-    return v;
-}
-
-template <int LPV, bool STATS>
-static cudaError_t launch_span(const SpmmArgs& a, int grid, cudaStream_t stream) {
-    auto kern = k_spmm<LPV, 4, 2, true, false, false, STATS, kSpanWarps, true>;
-    constexpr size_t smem = (size_t)spmm_smem_ints(LPV, 4, 2, STATS, kSpanWarps) * sizeof(int);
-    static bool configured = false;          // one process drives one device
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        // keep as much of the 256 KB for L1 as the staging buffers allow: the schedule lives on L1 reuse
-        int carve = (int)((smem + 1024 + 8 * 1024 - 1) * 100 / (228 * 1024)) + 1;
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve > 100 ? 100 : carve);
-        configured = true;
-    }
-    kern<<<grid, kSpanWarps * 32, smem, stream>>>(a);
-    return cudaGetLastError();
-}
-
 }  // namespace sgb
 
 extern "C" int sgb_spmm_stat_rows(int64_t n, int c) {
@@ -559,12 +457,6 @@ extern "C" int sgb_spmm_halo(const int32_t* rowptr, const sgb_edge_t* edges, con
                    (!bias || al16(bias)) && (!in_scale || (al16(in_scale) && al16(in_shift) && al16(in_mean)));
     SpmmCfg k = pick_cfg(c, aligned);
     int grid = spmm_grid(n, k, stat_partials != nullptr);
-    const int sl = span_lpv();
-    const bool span = sl > 0 && aligned && !in_scale && !x_ghost && c % (sl * 8) == 0 && n >= span_min_rows();
-    if (span) {
-        const int64_t need = ceil_div(ceil_div(n, spmm_vpw(sl)), kSpanWarps);
-        grid = (int)(need < num_sms() ? need : num_sms());
-    }
     if (stat_partials) {
         // rows the caller sized for; unused rows must read as zero
         int rows = sgb_spmm_stat_rows(n, c);
@@ -575,17 +467,6 @@ extern "C" int sgb_spmm_halo(const int32_t* rowptr, const sgb_edge_t* edges, con
     if (!pro) slope = 1.f;            // the general instantiation applies lrelu((x - 0) * 1 + 0, slope): identity
     SpmmArgs a{rowptr, reinterpret_cast<const int2*>(edges), dis, mode, x, ldx, n, c, in_mean, in_scale, in_shift, slope, alpha, addend, ld_addend, beta, bias, y, ldy, stat_partials,
                x_ghost, ld_ghost, x_ghost ? (int32_t)n_split : (int32_t)0x7fffffff, amax_out};
-    if (span) {
-        cudaError_t e = cudaSuccess;
-        if (sl == 4) e = st ? launch_span<4, true>(a, grid, stream) : launch_span<4, false>(a, grid, stream);
-        else if (sl == 8) e = st ? launch_span<8, true>(a, grid, stream) : launch_span<8, false>(a, grid, stream);
-        else e = st ? launch_span<16, true>(a, grid, stream) : launch_span<16, false>(a, grid, stream);
-        if (e != cudaSuccess) {
-            set_error("k_spmm (span): launch failed: %s", cudaGetErrorString(e));
-            return SGB_ECUDA;
-        }
-        return SGB_OK;
-    }
     // the BatchNorm prologue and ragged widths are rare operands: they share one (slower, fully general) instantiation
 #define SGB_SPMM_CASE(L, V, I)                                                                                  \
     if (k.lpv == L && k.vec == V && k.iters == I) {                                                             \
