@@ -88,3 +88,48 @@ class Data:
     def __repr__(self):
         parts = [f"{k}={list(v.shape)}" if torch.is_tensor(v) else f"{k}={type(v).__name__}" for k, v in self._store.items()]
         return "Data(" + ", ".join(parts) + ")"
+
+
+# ----------------------------------------------------------------------------------------
+# synthetic-occlusion masks (reference util/datamaker.py:110-159) without the dense N x N AdjI
+# ----------------------------------------------------------------------------------------
+_DUMMY_P = [0.014, 0.014, 0.014, 0.014, 0.014, 0.014, 0.014, 0.0014, 0.014]      # util/datamaker.py:118
+
+
+def dilate_mask(edge_index: torch.Tensor, seeds: torch.Tensor, rings: int) -> torch.Tensor:
+    """``rings`` times ``M <- (AdjI @ M > 0)`` (util/datamaker.py:127-129) on the sparse ``edge_index`` [2, 2E] instead of
+    the reference's dense-built ``mesh.AdjI`` (util/mesh.py:271-272): a vertex is marked when it or a neighbour is.
+    ``seeds`` [N, D] float (0 / 1); returns the same shape.  Plain torch ops on the tensors' device; the sums are small
+    non-negative integers, exact in float32, so ``> 0`` is the boolean semiring."""
+    row, col = edge_index[0], edge_index[1]
+    m = seeds.to(torch.float32)
+    for _ in range(int(rings)):
+        m = ((torch.zeros_like(m).index_add_(0, col, m[row]) + m) > 0).to(torch.float32)
+    return m
+
+
+def vmask_to_fmask(faces: torch.Tensor, vmask: torch.Tensor) -> torch.Tensor:
+    """util/datamaker.py:156-159: a face is kept iff none of its three vertices is masked
+    (``f2v_mat @ (1 - vmask) == 0``).  ``vmask`` [N] or [N, D] (1 = kept); returns bool [F] or float [F, D] as the
+    reference does for the single real mask / the dummy-mask matrix."""
+    f = faces.to(vmask.device).long()
+    if vmask.dim() == 1:
+        return (vmask.to(torch.float32)[f] > 0).all(dim=1)
+    keep = vmask.to(torch.float32)[f]                       # [F, 3, D]
+    return (keep > 0).all(dim=1).to(torch.float32)
+
+
+def make_dummy_mask(edge_index: torch.Tensor, faces: torch.Tensor, num_vertices: int, dm_size: int = 40, kn=(3, 4, 5), rng=None):
+    """util/datamaker.py:110-136 (without the .ply dumps): for each ring count k in ``kn``, ``dm_size`` Bernoulli(p_k) seed
+    sets grown k rings; ``vmask`` [N, dm_size * len(kn)] is 1 outside the fake holes, ``fmask`` the matching face masks.
+    The seeds are drawn with ``np.random.binomial`` in the reference's order, so the reference's ``np.random.seed`` gives
+    the reference's masks (``rng``: a ``numpy.random.RandomState``-like object; default the global numpy state)."""
+    import numpy as np
+    rng = np.random if rng is None else rng
+    dev = edge_index.device
+    cols = []
+    for k in kn:
+        mv0 = torch.from_numpy(rng.binomial(1, _DUMMY_P[k], size=[int(num_vertices), int(dm_size)])).float().to(dev)
+        cols.append(1.0 - dilate_mask(edge_index, mv0, k))
+    vmask = torch.cat(cols, dim=1)
+    return vmask, vmask_to_fmask(faces, vmask)

@@ -242,3 +242,27 @@ def test_fn_bnf_detach_loss_matches_reference(n):
     j = adj.reshape(-1)
     ok = j >= 0
     assert bool(((adj[j[ok]] == i[ok].unsqueeze(1)).any(dim=1)).all())
+
+
+def test_dummy_masks_match_reference_datamaker():
+    """semigcn_b200.data.make_dummy_mask / vmask_to_fmask / dilate_mask (sparse edge_index, no dense AdjI) against the
+    reference's own util/datamaker.py:110-159 run on its dense-built AdjI / f2v_mat (tests/golden/make_golden_masks.py):
+    identical masks under the reference's numpy seed."""
+    import numpy as np
+    from semigcn_b200 import data as sdata
+    gold = load_golden("ref_masks_n4.npz")
+    ei = torch.from_numpy(gold["edge_index"])
+    faces = torch.from_numpy(gold["faces"]).long()
+    n = int(ei.max()) + 1
+    rng = np.random.RandomState(int(gold["seed"]))
+    vmask, fmask = sdata.make_dummy_mask(ei, faces, n, dm_size=int(gold["dm_size"]), kn=[int(k) for k in gold["kn"]], rng=rng)
+    assert torch.equal(vmask, torch.from_numpy(gold["vmask_dummy"]))
+    assert torch.equal(fmask, torch.from_numpy(gold["fmask_dummy"]))
+    f_real = sdata.vmask_to_fmask(faces, torch.from_numpy(gold["v_real"]))
+    assert f_real.dtype == torch.bool and torch.equal(f_real, torch.from_numpy(gold["f_real"]))
+    # known answer: one seed grows to its k-ring (1 + 6 + 12 vertices on a degree-6 patch of the icosphere)
+    seed = torch.zeros(n, 1)
+    v = int(torch.bincount(ei[1]).argmax())           # any degree-6 vertex
+    seed[v] = 1.0
+    assert int(sdata.dilate_mask(ei, seed, 0).sum()) == 1
+    assert int(sdata.dilate_mask(ei, seed, 1).sum()) == 1 + int((ei[1] == v).sum())
