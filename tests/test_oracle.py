@@ -266,3 +266,31 @@ def test_dummy_masks_match_reference_datamaker():
     seed[v] = 1.0
     assert int(sdata.dilate_mask(ei, seed, 0).sum()) == 1
     assert int(sdata.dilate_mask(ei, seed, 1).sum()) == 1 + int((ei[1] == v).sum())
+
+
+def test_oracle_operators_match_scipy_laplacian():
+    """An anchor outside this repository for the normalisation arithmetic: scipy.sparse.csgraph.laplacian(normed=True) is
+    I - D^-1/2 A D^-1/2, so ChebConv's scaled operator (lambda_max = 2:  2 L / lambda_max - I) must equal it minus the
+    identity, and GCNConv's operator must equal the same construction on A + I with degrees deg + 1."""
+    import numpy as np
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import laplacian
+    from semigcn_b200 import meshgen
+    m = meshgen.icosphere(5)
+    n, ei = m.num_vertices, m.edge_index
+    a = sp.coo_matrix((np.ones(ei.shape[1]), (ei[1].numpy(), ei[0].numpy())), shape=(n, n)).tocsr()
+    lap = laplacian(a, normed=True)
+    cheb_ref = (lap - sp.identity(n)).toarray()
+    # oracle: edge list [edges (-w) || +1 loops || -1 loops] -> dense
+    ei_c, w_c = O.cheb_norm(ei, n, dtype=torch.float64)
+    dense = torch.zeros(n, n, dtype=torch.float64).index_put_((ei_c[1], ei_c[0]), w_c, accumulate=True).numpy()
+    assert np.abs(dense - cheb_ref).max() <= 1e-12
+    deg = np.asarray(a.sum(axis=1)).reshape(-1) + 1.0
+    dis = sp.diags(1.0 / np.sqrt(deg))
+    gcn_ref = (dis @ (a + sp.identity(n)) @ dis).toarray()
+    ei_g, w_g = O.gcn_norm(ei, n, dtype=torch.float64)
+    dense = torch.zeros(n, n, dtype=torch.float64).index_put_((ei_g[1], ei_g[0]), w_g, accumulate=True).numpy()
+    assert np.abs(dense - gcn_ref).max() <= 1e-12
+    # and the propagate step is that matrix applied to x
+    x = torch.randn(n, 5, dtype=torch.float64, generator=torch.Generator().manual_seed(2))
+    assert np.abs(O.propagate(ei_g, w_g, x).numpy() - gcn_ref @ x.numpy()).max() <= 1e-12
