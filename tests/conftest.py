@@ -20,3 +20,15 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _library_is_built():
+    """The built .so is git-ignored: a fresh checkout (or a re-created container) has none.  The tests are about the
+    product, which fails loudly without it, so the test session builds it once when nvcc is there (seconds per file;
+    cross-compiles without a GPU).  On the GPU box the .so travels with the tree and nothing is rebuilt."""
+    import shutil
+    from semigcn_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH) and (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
+        _lib.build_library(verbose=False)
+    yield
