@@ -508,6 +508,17 @@ def main():
         if line is not None:
             print(json.dumps(line), flush=True)
         return
+    from semigcn_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        # the built .so normally travels with the tree; a bare checkout builds it (nvcc, ~1 min; local rank 0 only)
+        if local_rank == 0:
+            _lib.build_library(verbose=False)
+        else:
+            for _ in range(600):
+                if os.path.exists(_lib.LIB_PATH):
+                    break
+                time.sleep(0.5)
+            time.sleep(2.0)
     dist_on = world > 1 or args.mode == "partition"
     if dist_on:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
