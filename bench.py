@@ -142,6 +142,41 @@ def algorithmic_bytes_per_step(n: int, nnz: int, widths):
     return total
 
 
+def gcnconv_layer_bench(edge_index, n: int, nnz: int, dev, pk, cin: int = 256, cout: int = 256, reps: int = 10):
+    """BASELINE.json's first metric, "GCNConv fwd+bwd edges/s & HBM GB/s fraction", on ONE drop-in layer (no BatchNorm
+    around it): forward + backward (dX, dW, db) of ``GCNConv(cin, cout)`` on the bench mesh, CUDA events, inputs >> L2.
+    Algorithmic bytes per SURVEY.md §8(d):  fwd = B_gemm_io + B_spmm,  bwd = B_spmm + N (Cin + 2 Cout) 4 + N Cin 4 + N Cout 4."""
+    from semigcn_b200.nn import GCNConv
+    torch.manual_seed(314)
+    conv = GCNConv(cin, cout).to(dev)
+    x = torch.randn(n, cin, device=dev, requires_grad=True)
+    g = torch.randn(n, cout, device=dev)
+
+    def step():
+        conv.zero_grad(set_to_none=True)
+        x.grad = None
+        conv(x, edge_index).backward(g)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    cs = min(cin, cout)
+    b_spmm = 4.0 * (2 * n * cs + (nnz + n) + (n + 1) + n)
+    b_fwd = 4.0 * (n * (cin + cout) + cin * cout) + b_spmm
+    b_bwd = b_spmm + 4.0 * n * (cin + 2 * cout) + 4.0 * n * cin + 4.0 * n * cout
+    gbs = (b_fwd + b_bwd) / (ms / 1e3) / 1e9
+    return {"layer": f"GCNConv({cin}, {cout}) forward + backward (dX, dW, db), {n} vertices, {nnz} directed edges",
+            "ms": ms, "edges_per_s": nnz / (ms / 1e3), "algorithmic_GB": (b_fwd + b_bwd) / 1e9, "GBps": gbs,
+            "hbm_frac": gbs / pk["hbm_gbs"], "reps": reps}
+
+
 def make_problem(freq: int, device, seed: int = 314):
     from semigcn_b200 import meshgen
     mesh = meshgen.icosphere(freq, device=device, dtype=torch.float64)
@@ -323,6 +358,12 @@ def run_ours(args, rank, world, local_rank):
         alg = algorithmic_bytes_per_step(n, nnz, SGCN_WIDTHS)
         line["step_algorithmic_GB"] = alg / 1e9
         line["step_hbm_frac"] = alg / (ms / args.steps / 1e3) / 1e9 / pk["hbm_gbs"]
+    if not args.no_profile and graphed is None:
+        try:            # an extra, self-contained measurement: it must never cost the bench line
+            torch.cuda.empty_cache()
+            line["gcnconv_layer"] = gcnconv_layer_bench(mesh.edge_index, n, nnz, dev, pk)
+        except Exception as exc:   # noqa: BLE001
+            line["gcnconv_layer"] = {"error": repr(exc)[:300]}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference(args, steps=2, warmup=1, freq=args.cpu_freq or 100)
     return line
