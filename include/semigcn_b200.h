@@ -79,6 +79,11 @@ SGB_API int sgb_num_sms(void);
  *    err_flag (device int32[1], zero-initialised by the call): 1 if an index was outside
  *    [0, n).
  * ------------------------------------------------------------------------------------ */
+/* out[0..1] (device uint64[2], zeroed by the call) = 128-bit content fingerprint of an int64 array, one streaming pass.
+ * The host layer keys its CSR cache on it when the caller passes a fresh device copy of the same edge_index every
+ * forward (the reference does: `data.edge_index.to(self.device)`, util/networks.py:65), so the copy costs one hash pass
+ * instead of a CSR rebuild. */
+SGB_API int sgb_fingerprint(const int64_t* values, int64_t count, uint64_t* out /* [2] */, void* stream);
 SGB_API size_t sgb_graph_build_workspace_bytes(int64_t nnz, int64_t n);
 SGB_API int sgb_graph_build(const int64_t* edge_index, int64_t nnz, int64_t n, int mode, int transpose,
                     int32_t* rowptr /* [n+1] */, int32_t* colidx /* [nnz] */, sgb_edge_t* edges /* [nnz] or NULL */,
@@ -135,6 +140,9 @@ SGB_API int sgb_gather_rows(const float* x, int64_t ldx, const int32_t* idx, int
  *    sgb_gemm_tn:    D[n,k] (+)= G[m,n]^T * A[m,k]   (weight gradient; split over m with a
  *                    fixed-order two-stage reduction -> deterministic).
  *    sgb_colsum:     out[n] (+)= sum_m G[m,n]        (bias gradient).
+ *    stat_partials rows: every engine writes per-CTA (not per-tile) moments, at most
+ *    sgb_gemm_stat_rows(m) = 4 * min(ceil(m/128), #SMs) rows, and zero-fills the rows it does not use
+ *    (count 0 rows drop out of the merge) -- the finalisation cost no longer grows with m.
  *    `engine`: 0 = auto, 1 = fp32 CUDA-core tiles, 2 = tcgen05 3xTF32 tensor-core tiles
  *    (error-compensated: hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM).  The tensor-core
  *    engine stages the split / pre-tiled weights in `workspace` (sgb_gemm_workspace_bytes).
@@ -159,7 +167,12 @@ SGB_API int sgb_gemm_tn(const float* g, int64_t ldg, const float* a, int64_t lda
                 void* workspace, size_t workspace_bytes, int engine, void* stream);
 SGB_API size_t sgb_colsum_workspace_bytes(int64_t m, int n);
 SGB_API int sgb_colsum(const float* g, int64_t ldg, int64_t m, int n, float* out, int accumulate,
+               float* amax_out /* optional: max |G| from the same pass (feeds g_amax / a_amax of the GEMMs that read G next) */,
                void* workspace, size_t workspace_bytes, void* stream);
+/* amax_out[0] = max |X| over an [m, c] matrix (one streaming pass; c % 4 == 0, 16-byte aligned rows): the per-tensor
+ * scale of the fp16-split engine for an operand that none of our kernels produced (e.g. the upstream gradient of a bare
+ * GCNConv), computed ONCE and shared by every GEMM that reads the operand. */
+SGB_API int sgb_amax(const float* x, int64_t ldx, int64_t m, int c, float* amax_out, void* stream);
 
 /* ------------------------------------------------------------------------------------ *
  * 4. BatchNorm1d (batch statistics over all vertices) + LeakyReLU, forward and backward.
@@ -178,6 +191,9 @@ SGB_API int sgb_bn_finalize(const float* partials, int rows, int c, int64_t coun
                     const float* gamma, const float* beta, float eps, float momentum,
                     float* running_mean, float* running_var,
                     float* mean, float* invstd, float* scale, float* shift, void* stream);
+/* merged[3][c] = Chan merge (fp64) of partials[rows][3][c]: ONE (count, mean, M2) row.  Vertex-partitioned SyncBN
+ * all-gathers this row per rank (a rank-invariant 12*c bytes) instead of the raw per-CTA rows. */
+SGB_API int sgb_moments_merge(const float* partials, int rows, int c, float* merged /* [3][c] */, void* stream);
 SGB_API int sgb_bn_act_apply(const float* y, int64_t ldy, int64_t m, int c, const float* mean, const float* scale,
                      const float* shift, float slope, float* z, int64_t ldz, float* amax_out /* optional: max |Z| */, void* stream);
 /* partials[rows][2][c]: (sum dA, sum dA*xhat) with dA = dZ * lrelu'((Y-mean)*scale+shift) */

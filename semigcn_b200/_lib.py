@@ -27,6 +27,7 @@ SIGNATURES = {
     "sgb_version": (_i32, []),
     "sgb_last_error": (C.c_char_p, []),
     "sgb_num_sms": (_i32, []),
+    "sgb_fingerprint": (_i32, [_vp, _i64, _vp, _vp]),
     "sgb_graph_build_workspace_bytes": (_sz, [_i64, _i64]),
     "sgb_graph_build": (_i32, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sgb_spmm_stat_rows": (_i32, [_i64, _i32]),
@@ -42,7 +43,9 @@ SIGNATURES = {
     "sgb_gemm_tn_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "sgb_gemm_tn": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _i32, _vp]),
     "sgb_colsum_workspace_bytes": (_sz, [_i64, _i32]),
-    "sgb_colsum": (_i32, [_vp, _i64, _i64, _i32, _vp, _i32, _vp, _sz, _vp]),
+    "sgb_colsum": (_i32, [_vp, _i64, _i64, _i32, _vp, _i32, _vp, _vp, _sz, _vp]),
+    "sgb_amax": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp]),
+    "sgb_moments_merge": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "sgb_col_stat_rows": (_i32, [_i64, _i32]),
     "sgb_col_stats": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp]),
     "sgb_bn_finalize": (_i32, [_vp, _i32, _i32, _i64, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

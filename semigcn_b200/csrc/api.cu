@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "umma.cuh"
 #include <string.h>
+#include <atomic>
 
 namespace sgb {
 
@@ -26,6 +27,19 @@ int num_sms() {
         cached_sms = v;
     }
     return cached_sms;
+}
+
+// Opt a kernel into > 48 KB of dynamic shared memory.  The attribute is per (function, device): `done_mask` (one static
+// per kernel at the call site) remembers the devices it has been set on, so a process that moves from cuda:0 to cuda:1
+// sets it again there, and the steady state costs one cudaGetDevice.
+int smem_optin(const void* func, int bytes, std::atomic<uint64_t>* done_mask) {
+    int dev = 0;
+    SGB_CUDA(cudaGetDevice(&dev));
+    const uint64_t bit = dev < 64 ? (uint64_t)1 << dev : 0;
+    if (bit && (done_mask->load(std::memory_order_relaxed) & bit)) return SGB_OK;
+    SGB_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    if (bit) done_mask->fetch_or(bit, std::memory_order_relaxed);
+    return SGB_OK;
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)

@@ -22,6 +22,7 @@ struct ColArgs {
     const float* scale; const float* shift; const float* mean; const float* invstd;
     float slope;
     float* partials;                    // STATS: [gridDim.x][3][c] (count, mean, M2); others: [gridDim.x][2][c] sums
+    float* amax;                        // SUM only, optional: receives max |y| (atomicMax on the float bits; zeroed by the launcher)
 };
 
 // One thread owns VEC channels of one row-lane; rows are grid-strided; fixed-order smem
@@ -30,6 +31,7 @@ template <int OP, int VEC>
 __global__ void __launch_bounds__(kColThreads) k_col_reduce(const ColArgs a, int tpr /* threads per row, pow2 <= 256 */) {
     __shared__ float red[2][kColThreads * VEC];
     __shared__ float redn[kColThreads];
+    float amx = 0.f;
     const int cl = threadIdx.x % tpr;
     const int rl = threadIdx.x / tpr;
     const int rows_per_pass = kColThreads / tpr;
@@ -68,6 +70,7 @@ __global__ void __launch_bounds__(kColThreads) k_col_reduce(const ColArgs a, int
                         s2[q] += (double)yv[q] * (double)yv[q];
                     } else if (OP == COL_SUM) {
                         s1[q] += (double)yv[q];
+                        amx = fmaxf(amx, fabsf(yv[q]));
                     } else {
                         const float ctr = yv[q] - mu[q];
                         const float pre = fmaf(ctr, sc[q], sh[q]);
@@ -123,6 +126,7 @@ __global__ void __launch_bounds__(kColThreads) k_col_reduce(const ColArgs a, int
         }
         __syncthreads();
     }
+    if (OP == COL_SUM && a.amax) publish_amax(amx, reinterpret_cast<uint32_t*>(redn), a.amax);
 }
 
 static int col_tpr(int c, int vec) {
@@ -173,7 +177,7 @@ struct FinArgs {
     float* running_mean; float* running_var;
     float* mean; float* invstd; float* scale; float* shift;   // BN forward outputs
     float* sums; float* dgamma; float* dbeta; int accumulate; // BN backward / colsum outputs
-    int kind;                                                  // 0 = BN fwd, 1 = BN bwd sums, 2 = column sum
+    int kind;                                                  // 0 = BN fwd, 1 = BN bwd sums, 2 = column sum, 3 = merge moment rows -> sums[3][c]
 };
 
 __global__ void __launch_bounds__(1024) k_finalize(const FinArgs f) {
@@ -181,16 +185,28 @@ __global__ void __launch_bounds__(1024) k_finalize(const FinArgs f) {
     const int ch = blockIdx.x * 32 + threadIdx.x;
     double s1 = 0.0, s2 = 0.0, s3 = 0.0;
     if (ch < f.c) {
-        if (f.kind == 0) {       // (count, mean, M2) rows: Chan merge in fp64, fixed order
+        if (f.kind == 0 || f.kind == 3) {
+            // (count, mean, M2) rows.  Per row lane: division-free sums around a pivot (the mean of the lane's first
+            // non-empty row), S0 = sum n, S1 = sum n (mean - p), S2 = sum M2 + n (mean - p)^2, in fp64 -- then one Chan
+            // merge per lane below.  (A Chan merge per row costs two fp64 divisions per row and serialises them.)
+            double p = 0.0;
+            bool have = false;
             for (int r = threadIdx.y; r < f.rows; r += 32) {
                 const double nb = (double)__ldg(f.partials + ((int64_t)r * 3 + 0) * f.c + ch);
                 if (nb == 0.0) continue;
                 const double mb = (double)__ldg(f.partials + ((int64_t)r * 3 + 1) * f.c + ch);
                 const double qb = (double)__ldg(f.partials + ((int64_t)r * 3 + 2) * f.c + ch);
-                const double nt = s1 + nb, d = mb - s2;
-                s3 += qb + d * d * s1 * nb / nt;
-                s2 += d * nb / nt;
-                s1 = nt;
+                if (!have) { p = mb; have = true; }
+                const double d = mb - p;
+                s1 += nb;
+                s2 = fma(nb, d, s2);
+                s3 += fma(nb * d, d, qb);
+            }
+            if (have) {           // -> (n, mean, M2) of this lane's rows
+                const double dm = s2 / s1;
+                s3 -= s2 * dm;
+                if (s3 < 0.0) s3 = 0.0;
+                s2 = p + dm;
             }
         } else {
             for (int r = threadIdx.y; r < f.rows; r += 32) {
@@ -204,7 +220,7 @@ __global__ void __launch_bounds__(1024) k_finalize(const FinArgs f) {
     r3[threadIdx.y][threadIdx.x] = s3;
     __syncthreads();
     if (threadIdx.y == 0 && ch < f.c) {
-        if (f.kind == 0) {
+        if (f.kind == 0 || f.kind == 3) {
             double n = 0.0, mean = 0.0, m2 = 0.0;
             for (int r = 0; r < 32; ++r) {
                 const double nb = r1[r][threadIdx.x];
@@ -213,6 +229,12 @@ __global__ void __launch_bounds__(1024) k_finalize(const FinArgs f) {
                 m2 += r3[r][threadIdx.x] + d * d * n * nb / nt;
                 mean += d * nb / nt;
                 n = nt;
+            }
+            if (f.kind == 3) {       // merged row only (SyncBN: one row per rank goes into the all-gather)
+                f.sums[ch] = (float)n;
+                f.sums[f.c + ch] = (float)mean;
+                f.sums[2 * f.c + ch] = (float)m2;
+                return;
             }
             double var = n > 0.0 ? m2 / n : 0.0;
             if (var < 0.0) var = 0.0;
@@ -380,6 +402,15 @@ extern "C" int sgb_bn_finalize(const float* partials, int rows, int c, int64_t c
     return SGB_OK;
 }
 
+extern "C" int sgb_moments_merge(const float* partials, int rows, int c, float* merged, void* stream) {
+    SGB_CHECK_ARG(partials && rows > 0 && c > 0 && merged, "sgb_moments_merge: bad argument");
+    FinArgs f{};
+    f.partials = partials; f.rows = rows; f.c = c; f.sums = merged; f.kind = 3;
+    k_finalize<<<(c + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(f);
+    SGB_CHECK_LAUNCH("k_finalize");
+    return SGB_OK;
+}
+
 extern "C" int sgb_bn_act_apply(const float* y, int64_t ldy, int64_t m, int c, const float* mean, const float* scale,
                                 const float* shift, float slope, float* z, int64_t ldz, float* amax_out, void* stream) {
     SGB_CHECK_ARG(y && z && mean && scale && shift && m >= 0 && c > 0 && ldy >= c && ldz >= c, "sgb_bn_act_apply: bad argument");
@@ -435,7 +466,7 @@ extern "C" size_t sgb_colsum_workspace_bytes(int64_t m, int n) {
     return (size_t)col_rows(m, n) * 2 * n * sizeof(float);
 }
 
-extern "C" int sgb_colsum(const float* g, int64_t ldg, int64_t m, int n, float* out, int accumulate, void* workspace,
+extern "C" int sgb_colsum(const float* g, int64_t ldg, int64_t m, int n, float* out, int accumulate, float* amax_out, void* workspace,
                           size_t workspace_bytes, void* stream) {
     SGB_CHECK_ARG(g && out && m >= 0 && n > 0 && ldg >= n, "sgb_colsum: bad argument");
     size_t need = sgb_colsum_workspace_bytes(m, n);
@@ -444,7 +475,8 @@ extern "C" int sgb_colsum(const float* g, int64_t ldg, int64_t m, int n, float* 
         return SGB_ENOSPC;
     }
     ColArgs a{};
-    a.y = g; a.ldy = ldg; a.m = m; a.c = n; a.partials = (float*)workspace;
+    a.y = g; a.ldy = ldg; a.m = m; a.c = n; a.partials = (float*)workspace; a.amax = amax_out;
+    if (amax_out) SGB_CUDA(cudaMemsetAsync(amax_out, 0, sizeof(float), (cudaStream_t)stream));
     int rc = col_launch<COL_SUM>(a, al16(g) && ldg % 4 == 0, (cudaStream_t)stream);
     if (rc != SGB_OK) return rc;
     FinArgs f{};

@@ -4,12 +4,14 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <atomic>
 #include "../../include/semigcn_b200.h"
 
 namespace sgb {
 
 void set_error(const char* fmt, ...);   // thread-local message (api.cu)
 int num_sms();                           // cached per process (api.cu)
+int smem_optin(const void* func, int bytes, std::atomic<uint64_t>* done_mask);   // dynamic shared memory opt-in, once per device (api.cu)
 
 #define SGB_CHECK_ARG(cond, ...)                 \
     do {                                         \
@@ -93,6 +95,10 @@ __device__ __forceinline__ void publish_amax(float mx, uint32_t* scratch, float*
         if (b) atomicMax(reinterpret_cast<uint32_t*>(slot), b);
     }
 }
+
+// rows of the BatchNorm-partials buffer of sgb_gemm (every engine writes at most this many (count, mean, M2) rows and
+// zero-fills the rest): 4 * min(ceil(m / 128), #SMs) -- gemm.cu
+int gemm_stat_rows(int64_t m);
 
 // arguments of the dense transform C (+)= f(A) op(B) + bias (see sgb_gemm)
 struct GemmArgs {

@@ -28,7 +28,15 @@ static bool tc_worthwhile(int64_t m, int n, int k) { return n >= 64 && k >= 32 &
 
 using namespace sgb;
 
-extern "C" int sgb_gemm_stat_rows(int64_t m) { return m <= 0 ? 0 : (int)ceil_div(m, 128); }
+namespace sgb {
+int gemm_stat_rows(int64_t m) {
+    if (m <= 0) return 0;
+    const int64_t tiles = ceil_div(m, 128);
+    return 4 * (int)(tiles < num_sms() ? tiles : num_sms());
+}
+}  // namespace sgb
+
+extern "C" int sgb_gemm_stat_rows(int64_t m) { return gemm_stat_rows(m); }
 
 extern "C" size_t sgb_gemm_workspace_bytes(int64_t m, int n, int k, int engine) {
     if (m < 0 || n <= 0 || k <= 0 || engine == 1) return 0;

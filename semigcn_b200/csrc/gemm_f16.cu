@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) k_amax(const float* __restrict__ x, int64
     }
 }
 
-static int amax_launch(const float* x, int64_t ldx, int64_t m, int c, uint32_t* slot, cudaStream_t stream) {
+int amax_launch(const float* x, int64_t ldx, int64_t m, int c, uint32_t* slot, cudaStream_t stream) {
     SGB_CUDA(cudaMemsetAsync(slot, 0, sizeof(uint32_t), stream));
     const int64_t total = m * (c / 4);
     const int grid = (int)min64(ceil_div(total > 0 ? total : 1, 256 * 8), (int64_t)num_sms() * 8);
@@ -129,6 +129,7 @@ struct HArgs {
     int64_t m; int n; int k;
     int bn; int n_tiles; int k_chunks; int stages;
     const float* bias; int accumulate;
+    float* stat_partials;             // optional BatchNorm partials of C: [4 * gridDim.x / n_tiles][3][n] (count, mean, M2), one row per epilogue warp
     uint32_t tmem_cols; int acc_stride;
 };
 
@@ -339,12 +340,24 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
             }
         }
     } else {
-        // ================= epilogue: TMEM -> registers -> unscale (+bias, +C) -> global =================
+        // ================= epilogue: TMEM -> registers -> unscale (+bias, +C) -> global (+ BatchNorm moments) =================
         float sa, inva;
         f16_scale_from_amax(__ldg(g.a_amax), sa, inva);
         const float invw = __ldg(g.wscale + 1);
         const int quarter = warp & 3;                // TMEM lanes 32*quarter .. +31 are accessible to this warp
         float* stg = reinterpret_cast<float*>(op_base + (size_t)g.stages * stage_bytes + 256) + quarter * 32 * kHEpiLd;
+        const int grp = lane >> 3;                   // row group of the transposed read-back: rows grp, grp + 4, ...
+        const int cc = (lane & 7) * 4;               // this lane's float4 inside a 32-column chunk
+        const bool stats = g.stat_partials != nullptr;
+        // Running column moments (count, mean, M2) of every row this warp has stored, Chan-merged one 32-row block at a
+        // time while the block is still in registers (no second pass over C).  gridDim.x is a multiple of n_tiles, so a
+        // CTA only ever sees one n-tile: the count is the same for all of its columns.  Chunk u of the n-tile is owned
+        // by the lanes of row group u % 4 (slot u / 4): 16 registers of state instead of 64.
+        float st_mean[2][4], st_m2[2][4], st_n = 0.f;
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { st_mean[sl][q] = 0.f; st_m2[sl][q] = 0.f; }
         uint32_t tcount = 0;
         for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
             const int nt = (int)(tile % g.n_tiles);
@@ -355,41 +368,104 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
             mbar_wait(&tfull[acc], (tcount >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * g.acc_stride);
-            for (int c0 = 0; c0 < ncols; c0 += 32) {
-                float v[32];
-                tmem_ld_32x32(taddr + c0, v);        // warp-collective: lane = row, registers = 32 consecutive columns
-                // transpose through the warp's staging tile so that global stores are whole 128-byte row segments
-                // (a lane-per-row store touches 32 different lines per instruction and saturates the L1 data pipe)
+            const int64_t rows_left = g.m - (m0 + quarter * 32);
+            const int nvalid = rows_left >= 32 ? 32 : (rows_left > 0 ? (int)rows_left : 0);   // rows of this warp's block inside C
+            const float nb = (float)nvalid;
+            const float inv_nb = nvalid ? 1.f / nb : 0.f;
+            const float wgt = nvalid ? nb / (st_n + nb) : 0.f;                                // Chan weight of the new block
 #pragma unroll
-                for (int e = 0; e < 32; e += 4)
-                    *reinterpret_cast<float4*>(stg + lane * kHEpiLd + e) =
-                        make_float4((v[e] * inva) * invw, (v[e + 1] * inva) * invw, (v[e + 2] * inva) * invw, (v[e + 3] * inva) * invw);
-                __syncwarp();
-                const int cc = (lane & 7) * 4;                   // this lane's float4 inside the 32-column chunk
-                if (c0 + cc < ncols) {                           // ncols is a multiple of 16 => whole float4 valid
-                    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (g.bias) b = ldg4(g.bias + n0 + c0 + cc);
+            for (int u = 0; u < 8; ++u) {            // bn <= 256: at most eight 32-column chunks (unrolled: the moment registers are indexed statically)
+                const int c0 = u * 32;
+                if (c0 < ncols) {
+                    float v[32];
+                    tmem_ld_32x32(taddr + c0, v);        // warp-collective: lane = row, registers = 32 consecutive columns
+                    // transpose through the warp's staging tile so that global stores are whole 128-byte row segments
+                    // (a lane-per-row store touches 32 different lines per instruction and saturates the L1 data pipe)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int j = i * 4 + (lane >> 3);
-                        const int64_t gm = m0 + quarter * 32 + j;
-                        if (gm < g.m) {
-                            float4 o = *reinterpret_cast<const float4*>(stg + j * kHEpiLd + cc);
-                            float* cp = g.c + gm * g.ldc + n0 + c0 + cc;
-                            if (g.accumulate) {
-                                const float4 old = *reinterpret_cast<const float4*>(cp);
-                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                    for (int e = 0; e < 32; e += 4)
+                        *reinterpret_cast<float4*>(stg + lane * kHEpiLd + e) =
+                            make_float4((v[e] * inva) * invw, (v[e + 1] * inva) * invw, (v[e + 2] * inva) * invw, (v[e + 3] * inva) * invw);
+                    __syncwarp();
+                    const bool col_ok = c0 + cc < ncols;             // ncols is a multiple of 16 => whole float4 valid
+                    float4 o[8];
+                    if (col_ok) {
+                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (g.bias) b = ldg4(g.bias + n0 + c0 + cc);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int j = i * 4 + grp;
+                            o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (j < nvalid) {
+                                o[i] = *reinterpret_cast<const float4*>(stg + j * kHEpiLd + cc);
+                                float* cp = g.c + (m0 + quarter * 32 + j) * g.ldc + n0 + c0 + cc;
+                                if (g.accumulate) {
+                                    const float4 old = *reinterpret_cast<const float4*>(cp);
+                                    o[i].x += old.x; o[i].y += old.y; o[i].z += old.z; o[i].w += old.w;
+                                }
+                                o[i].x += b.x; o[i].y += b.y; o[i].z += b.z; o[i].w += b.w;
+                                *reinterpret_cast<float4*>(cp) = o[i];
                             }
-                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                            *reinterpret_cast<float4*>(cp) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (stats && nvalid) {
+                        // block mean, then centred second moment (two passes over registers: no cancellation), each reduced
+                        // over the four row groups with two butterfly steps (lanes l, l^8, l^16, l^24 hold the same columns)
+                        float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { s[0] += o[i].x; s[1] += o[i].y; s[2] += o[i].z; s[3] += o[i].w; }   // invalid rows are zeros
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            s[q] += __shfl_xor_sync(0xffffffffu, s[q], 8);
+                            s[q] += __shfl_xor_sync(0xffffffffu, s[q], 16);
+                            s[q] *= inv_nb;                                  // block mean
+                        }
+                        float d2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (i * 4 + grp < nvalid) {
+                                const float dx = o[i].x - s[0], dy = o[i].y - s[1], dz = o[i].z - s[2], dw = o[i].w - s[3];
+                                d2[0] = fmaf(dx, dx, d2[0]); d2[1] = fmaf(dy, dy, d2[1]); d2[2] = fmaf(dz, dz, d2[2]); d2[3] = fmaf(dw, dw, d2[3]);
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            d2[q] += __shfl_xor_sync(0xffffffffu, d2[q], 8);
+                            d2[q] += __shfl_xor_sync(0xffffffffu, d2[q], 16);
+                        }
+                        if (grp == (u & 3)) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float delta = s[q] - st_mean[u >> 2][q];
+                                st_mean[u >> 2][q] = fmaf(delta, wgt, st_mean[u >> 2][q]);
+                                st_m2[u >> 2][q] += d2[q] + delta * delta * st_n * wgt;
+                            }
                         }
                     }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
+            st_n += nb;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+        if (stats) {
+            const int nt = (int)(blockIdx.x % g.n_tiles);
+            const int n0 = nt * g.bn;
+            const int ncols = min(g.bn, g.n - n0);
+            float* row = g.stat_partials + ((int64_t)(blockIdx.x / g.n_tiles) * 4 + quarter) * 3 * g.n;
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl) {
+                const int c0 = (sl * 4 + grp) * 32;
+                if (c0 + cc < ncols) {
+                    st4(row + 0 * (int64_t)g.n + n0 + c0 + cc, make_float4(st_n, st_n, st_n, st_n));
+                    st4(row + 1 * (int64_t)g.n + n0 + c0 + cc, make_float4(st_mean[sl][0], st_mean[sl][1], st_mean[sl][2], st_mean[sl][3]));
+                    st4(row + 2 * (int64_t)g.n + n0 + c0 + cc, make_float4(st_m2[sl][0], st_m2[sl][1], st_m2[sl][2], st_m2[sl][3]));
+                }
+            }
         }
     }
     tc_fence_before();
@@ -400,8 +476,7 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
     }
 }
 
-// per-128-row-tile column moments of C (BatchNorm partials) / fixed-order split reduction -- gemm_tc.cu
-int tile_col_stats_launch(const float* c, int64_t ldc, int64_t m, int n, float* partials, cudaStream_t stream);
+// fixed-order split reduction -- gemm_tc.cu
 int reduce_splits_launch(const float* partial, int splits, int n, int k, float* d, int64_t ldd, int accumulate, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------
@@ -709,10 +784,10 @@ int gemm_f16_launch(const GemmArgs& g, const float* a_amax, void* ws, size_t ws_
     }
     k_prep_weights_f16<<<num_sms(), 256, 0, stream>>>(g.b, g.ldb, g.transb, g.n, g.k, p.bn, p.n_tiles, p.k_chunks, reinterpret_cast<__half*>(img), hdr);
     SGB_CHECK_LAUNCH("k_prep_weights_f16");
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        SGB_CUDA(cudaFuncSetAttribute(k_gemm_f16, cudaFuncAttributeMaxDynamicSharedMemorySize, kHSmemBudget));
-        attr_set = true;
+    {
+        static std::atomic<uint64_t> optin{0};
+        int rc = smem_optin(reinterpret_cast<const void*>(k_gemm_f16), kHSmemBudget, &optin);
+        if (rc != SGB_OK) return rc;
     }
     HArgs t{};
     {
@@ -721,12 +796,22 @@ int gemm_f16_launch(const GemmArgs& g, const float* a_amax, void* ws, size_t ws_
     }
     t.a = g.a; t.lda = g.lda; t.wp = img; t.wscale = hdr; t.a_amax = a_amax; t.c = g.c; t.ldc = g.ldc; t.m = g.m; t.n = g.n; t.k = g.k;
     t.bn = p.bn; t.n_tiles = p.n_tiles; t.k_chunks = p.k_chunks; t.stages = p.stages;
-    t.bias = g.bias; t.accumulate = g.accumulate; t.tmem_cols = p.tmem_cols; t.acc_stride = p.acc_stride;
-    int64_t tiles = ceil_div(g.m, kHBM) * p.n_tiles;
-    int grid = (int)min64(tiles, num_sms());
+    t.bias = g.bias; t.accumulate = g.accumulate; t.stat_partials = g.stat_partials; t.tmem_cols = p.tmem_cols; t.acc_stride = p.acc_stride;
+    // grid = (m-tile groups) x n_tiles, a multiple of n_tiles: CTA b always works on n-tile b % n_tiles (its BatchNorm
+    // moments then cover one fixed column range) and on the m-tiles b / n_tiles, + groups, ...
+    const int64_t m_tiles = ceil_div(g.m, kHBM);
+    int groups = num_sms() / p.n_tiles;
+    if (groups < 1) groups = 1;
+    if (groups > m_tiles) groups = (int)m_tiles;
+    const int grid = groups * p.n_tiles;
+    if (g.stat_partials) {
+        SGB_CHECK_ARG((reinterpret_cast<uintptr_t>(g.stat_partials) & 15) == 0, "sgb_gemm: stat_partials must be 16-byte aligned");
+        const int rows = gemm_stat_rows(g.m), written = 4 * groups;       // one row per epilogue warp; the rest of the caller's rows are empty
+        if (rows > written)
+            SGB_CUDA(cudaMemsetAsync(g.stat_partials + (size_t)written * 3 * g.n, 0, (size_t)(rows - written) * 3 * g.n * sizeof(float), stream));
+    }
     k_gemm_f16<<<grid, kHThreads, p.smem_bytes, stream>>>(t);
     SGB_CHECK_LAUNCH("k_gemm_f16");
-    if (g.stat_partials) return tile_col_stats_launch(g.c, g.ldc, g.m, g.n, g.stat_partials, stream);
     return SGB_OK;
 }
 
@@ -791,10 +876,10 @@ int gemm_tn_f16_launch(const float* g, int64_t ldg, const float* a, int64_t lda,
         if (rc != SGB_OK) return rc;
         a_amax = hdr + 1;
     }
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        SGB_CUDA(cudaFuncSetAttribute(k_gemm_tn_f16, cudaFuncAttributeMaxDynamicSharedMemorySize, kHSmemBudget));
-        attr_set = true;
+    {
+        static std::atomic<uint64_t> optin{0};
+        int rc = smem_optin(reinterpret_cast<const void*>(k_gemm_tn_f16), kHSmemBudget, &optin);
+        if (rc != SGB_OK) return rc;
     }
     TArgs t{};
     {
@@ -812,3 +897,9 @@ int gemm_tn_f16_launch(const float* g, int64_t ldg, const float* a, int64_t lda,
 }
 
 }  // namespace sgb
+
+extern "C" int sgb_amax(const float* x, int64_t ldx, int64_t m, int c, float* amax_out, void* stream) {
+    SGB_CHECK_ARG(x && amax_out && m >= 0 && c > 0 && ldx >= c, "sgb_amax: bad argument");
+    SGB_CHECK_ARG(c % 4 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "sgb_amax: needs c %% 4 == 0 and 16-byte aligned rows");
+    return sgb::amax_launch(x, ldx, m, c, reinterpret_cast<uint32_t*>(amax_out), (cudaStream_t)stream);
+}

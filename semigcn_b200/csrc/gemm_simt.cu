@@ -23,12 +23,19 @@ __global__ void __launch_bounds__(kGemmThreads) k_gemm_simt(const GemmArgs g) {
     float (*Bs)[BN + 4] = reinterpret_cast<float (*)[BN + 4]>(smem_ab + BK * (BM + 4));
     const int tid = threadIdx.x;
     const int tx = tid % 16, ty = tid / 16;
-    const int64_t m0 = (int64_t)blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
     const bool pro = g.a_scale != nullptr;
     const bool a_vec = (g.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.a) & 15) == 0);
     const bool b_vec = (g.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.b) & 15) == 0);
 
+    // persistent over the 128-row tiles blockIdx.x, + gridDim.x, ...: the BatchNorm moments of all of a CTA's tiles are
+    // Chan-merged in registers, so the partials buffer holds gridDim.x <= gemm_stat_rows(m) rows however large m is
+    Moments run[TN];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) run[j] = Moments{0.f, 0.f, 0.f};
+    const int64_t m_tiles = (g.m + BM - 1) / BM;
+    for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+    const int64_t m0 = mt * BM;
     float acc[TM][TN];
 #pragma unroll
     for (int i = 0; i < TM; ++i)
@@ -155,6 +162,9 @@ __global__ void __launch_bounds__(kGemmThreads) k_gemm_simt(const GemmArgs g) {
             mo[j] = Moments{cnt, mean, m2};
         }
     }
+#pragma unroll
+    for (int j = 0; j < TN; ++j) run[j] = merge(run[j], mo[j]);
+    }   // m-tile loop
     if (g.stat_partials) {
         __syncthreads();
         __shared__ float red[3 * 16 * BN];   // 3 planes of [16 ty][BN]
@@ -163,9 +173,9 @@ __global__ void __launch_bounds__(kGemmThreads) k_gemm_simt(const GemmArgs g) {
         float* r2 = r1 + 16 * BN;
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-            r0[ty * BN + tx + 16 * j] = mo[j].n;
-            r1[ty * BN + tx + 16 * j] = mo[j].mean;
-            r2[ty * BN + tx + 16 * j] = mo[j].m2;
+            r0[ty * BN + tx + 16 * j] = run[j].n;
+            r1[ty * BN + tx + 16 * j] = run[j].mean;
+            r2[ty * BN + tx + 16 * j] = run[j].m2;
         }
         __syncthreads();
         for (int cl = tid; cl < BN; cl += kGemmThreads) {
@@ -183,7 +193,11 @@ __global__ void __launch_bounds__(kGemmThreads) k_gemm_simt(const GemmArgs g) {
 
 int gemm_simt_launch(const GemmArgs& g, cudaStream_t stream) {
     int bn = g.n <= 16 ? 16 : g.n <= 32 ? 32 : g.n <= 64 ? 64 : 128;
-    dim3 grid((unsigned)ceil_div(g.m, kGemmBM), (unsigned)ceil_div(g.n, bn));
+    const int rows = gemm_stat_rows(g.m);
+    const int gx = (int)min64(ceil_div(g.m, kGemmBM), rows);
+    dim3 grid((unsigned)gx, (unsigned)ceil_div(g.n, bn));
+    if (g.stat_partials && rows > gx)
+        SGB_CUDA(cudaMemsetAsync(g.stat_partials + (size_t)gx * 3 * g.n, 0, (size_t)(rows - gx) * 3 * g.n * sizeof(float), stream));
     switch (bn) {
         case 16: k_gemm_simt<16><<<grid, kGemmThreads, 0, stream>>>(g); break;
         case 32: k_gemm_simt<32><<<grid, kGemmThreads, 0, stream>>>(g); break;

@@ -276,22 +276,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const TcArgs g) {
     }
 }
 
-// per-128-row-tile column moments of C (BatchNorm partials: count, mean, M2) when the tensor-core path produced C
+// column moments of C (BatchNorm partials: count, mean, M2) when the 3xTF32 path produced C: CTA b walks the 128-row
+// tiles b, b + gridDim.x, ... and Chan-merges them, so the partials buffer holds gridDim.x <= gemm_stat_rows(m) rows
 __global__ void __launch_bounds__(256) k_tile_col_stats(const float* __restrict__ c, int64_t ldc, int64_t m, int n, float* __restrict__ partials) {
-    const int64_t m0 = (int64_t)blockIdx.x * kTcBM;
-    const int rows = (int)min64(kTcBM, m - m0);
+    const int64_t m_tiles = (m + kTcBM - 1) / kTcBM;
     for (int col = threadIdx.x; col < n; col += blockDim.x) {
-        const float p = c[m0 * ldc + col];            // pivot: first row of the tile
-        float s1 = 0.f, s2 = 0.f;
-        for (int r = 0; r < rows; ++r) {
-            const float d = c[(m0 + r) * ldc + col] - p;
-            s1 += d;
-            s2 = fmaf(d, d, s2);
+        Moments run{0.f, 0.f, 0.f};
+        for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+            const int64_t m0 = tile * kTcBM;
+            const int rows = (int)min64(kTcBM, m - m0);
+            const float p = c[m0 * ldc + col];            // pivot: first row of the tile
+            float s1 = 0.f, s2 = 0.f;
+            for (int r = 0; r < rows; ++r) {
+                const float d = c[(m0 + r) * ldc + col] - p;
+                s1 += d;
+                s2 = fmaf(d, d, s2);
+            }
+            run = merge(run, from_shifted((float)rows, p, s1, s2));
         }
-        const Moments mo = from_shifted((float)rows, p, s1, s2);
-        partials[((int64_t)blockIdx.x * 3 + 0) * n + col] = mo.n;
-        partials[((int64_t)blockIdx.x * 3 + 1) * n + col] = mo.mean;
-        partials[((int64_t)blockIdx.x * 3 + 2) * n + col] = mo.m2;
+        partials[((int64_t)blockIdx.x * 3 + 0) * n + col] = run.n;
+        partials[((int64_t)blockIdx.x * 3 + 1) * n + col] = run.mean;
+        partials[((int64_t)blockIdx.x * 3 + 2) * n + col] = run.m2;
     }
 }
 
@@ -528,7 +533,10 @@ __global__ void k_reduce_splits_tc(const float* __restrict__ partial, int splits
 // host side
 // ------------------------------------------------------------------------------------------
 int tile_col_stats_launch(const float* c, int64_t ldc, int64_t m, int n, float* partials, cudaStream_t stream) {
-    k_tile_col_stats<<<(unsigned)ceil_div(m, kTcBM), 256, 0, stream>>>(c, ldc, m, n, partials);
+    const int rows = gemm_stat_rows(m);
+    const int grid = (int)min64(ceil_div(m, kTcBM), rows);
+    if (rows > grid) SGB_CUDA(cudaMemsetAsync(partials + (size_t)grid * 3 * n, 0, (size_t)(rows - grid) * 3 * n * sizeof(float), stream));
+    k_tile_col_stats<<<grid, 256, 0, stream>>>(c, ldc, m, n, partials);
     SGB_CHECK_LAUNCH("k_tile_col_stats");
     return SGB_OK;
 }
@@ -592,10 +600,10 @@ int gemm_tc_launch(const GemmArgs& g, void* ws, size_t ws_bytes, cudaStream_t st
         k_prep_weights<<<grid, 256, 0, stream>>>(g.b, g.ldb, g.transb, g.n, g.k, p.bn, p.n_tiles, p.k_chunks, wp);
         SGB_CHECK_LAUNCH("k_prep_weights");
     }
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        SGB_CUDA(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-        attr_set = true;
+    {
+        static std::atomic<uint64_t> optin{0};
+        int rc = smem_optin(reinterpret_cast<const void*>(k_gemm_tc), kSmemBudget, &optin);
+        if (rc != SGB_OK) return rc;
     }
     TcArgs t{};
     t.a = g.a; t.lda = g.lda; t.wp = wp; t.c = g.c; t.ldc = g.ldc; t.m = g.m; t.n = g.n; t.k = g.k;
@@ -606,10 +614,7 @@ int gemm_tc_launch(const GemmArgs& g, void* ws, size_t ws_bytes, cudaStream_t st
     int grid = (int)min64(tiles, num_sms());
     k_gemm_tc<<<grid, kTcThreads, p.smem_bytes, stream>>>(t);
     SGB_CHECK_LAUNCH("k_gemm_tc");
-    if (g.stat_partials) {
-        k_tile_col_stats<<<(unsigned)ceil_div(g.m, kTcBM), 256, 0, stream>>>(g.c, g.ldc, g.m, g.n, g.stat_partials);
-        SGB_CHECK_LAUNCH("k_tile_col_stats");
-    }
+    if (g.stat_partials) return tile_col_stats_launch(g.c, g.ldc, g.m, g.n, g.stat_partials, stream);
     return SGB_OK;
 }
 
@@ -663,10 +668,10 @@ int gemm_tn_tc_launch(const float* g, int64_t ldg, const float* a, int64_t lda, 
         set_error("sgb_gemm_tn: tile does not fit shared memory");
         return SGB_ENOTSUP;
     }
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        SGB_CUDA(cudaFuncSetAttribute(k_gemm_tn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-        attr_set = true;
+    {
+        static std::atomic<uint64_t> optin{0};
+        int rc = smem_optin(reinterpret_cast<const void*>(k_gemm_tn_tc), kSmemBudget, &optin);
+        if (rc != SGB_OK) return rc;
     }
     TnArgs t{};
     t.g = g; t.ldg = ldg; t.a = a; t.lda = lda; t.partial = (float*)ws; t.m = m; t.n = n; t.k = k;

@@ -201,7 +201,42 @@ static BuildWs carve(void* ws, int64_t nnz, int64_t n) {
     return w;
 }
 
+// 128-bit content fingerprint of an int64 array: two position-dependent multiplicative hashes summed with wrapping
+// unsigned adds (commutative -> order-free, deterministic).  Keys the host-side CSR cache when the caller hands over a
+// fresh copy of the same edge_index every forward (util/networks.py:65 `.to(device)` of a CPU tensor).
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+__global__ void __launch_bounds__(256) k_fingerprint(const int64_t* __restrict__ v, int64_t count, unsigned long long* __restrict__ out) {
+    unsigned long long h0 = 0, h1 = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long x = (unsigned long long)v[i];
+        h0 += mix64(x + 0x9e3779b97f4a7c15ULL * (unsigned long long)(i + 1));
+        h1 += mix64((x ^ 0xd6e8feb86659fd93ULL) * 0xbf58476d1ce4e5b9ULL + (unsigned long long)i);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        h0 += __shfl_xor_sync(0xffffffffu, h0, o);
+        h1 += __shfl_xor_sync(0xffffffffu, h1, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out, h0);
+        atomicAdd(out + 1, h1);
+    }
+}
+
 }  // namespace sgb
+
+extern "C" int sgb_fingerprint(const int64_t* values, int64_t count, uint64_t* out, void* stream) {
+    SGB_CHECK_ARG(values && out && count >= 0, "sgb_fingerprint: bad argument");
+    SGB_CUDA(cudaMemsetAsync(out, 0, 2 * sizeof(uint64_t), (cudaStream_t)stream));
+    if (count == 0) return SGB_OK;
+    const int grid = (int)sgb::min64(sgb::ceil_div(count, 256 * 8), (int64_t)sgb::num_sms() * 8);
+    sgb::k_fingerprint<<<grid, 256, 0, (cudaStream_t)stream>>>(values, count, reinterpret_cast<unsigned long long*>(out));
+    SGB_CHECK_LAUNCH("k_fingerprint");
+    return SGB_OK;
+}
 
 extern "C" size_t sgb_graph_build_workspace_bytes(int64_t nnz, int64_t n) {
     if (nnz < 0 || n < 0) return 0;

@@ -124,7 +124,7 @@ def register_partition(plan: PartitionPlan, comm, modes=(L.MODE_GCN, L.MODE_CHEB
     for mode in modes:
         g = PartitionedGraph(plan, comm, mode)
         key = (ei.data_ptr(), tuple(ei.shape), ei._version, str(ei.device), mode, plan.n_own)
-        ops._GRAPH_CACHE[key] = (g, ei)
+        ops._GRAPH_CACHE[key] = (g, ei, 0)
     ops._GRAPH_CACHE_PINNED.update(k for k in ops._GRAPH_CACHE if k[0] == ei.data_ptr())
     return ei
 

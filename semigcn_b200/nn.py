@@ -238,7 +238,19 @@ class ConvBlockFn(torch.autograd.Function):
                 dgamma = dbeta = None
         need_x = ctx.needs_input_grad[0]
         db = None
-        if ctx.has_bias and ctx.needs_input_grad[3]:
+        want_db = ctx.has_bias and ctx.needs_input_grad[3]
+        # a bare conv (no BatchNorm behind it) receives a dY none of our kernels produced: its max |dY| (the scale of the
+        # fp16-split GEMMs) is reduced ONCE -- in the bias-gradient pass when there is one -- and shared by the dW and
+        # dX GEMMs, instead of each GEMM running its own reduction pass over dY
+        dy_used_by_gemm = cfg.kind != "gcn" or ctx.agg_first
+        if dy_amax is None and dy_used_by_gemm:
+            if want_db and ctx.bn_mode != 2:
+                dy_amax = am[0:1]
+                db = ops.colsum(dy, amax_out=dy_amax)
+                want_db = False
+            elif ops.tensor_core_likely(dy.shape[0], weights[0].shape[1], dy.shape[1]):
+                dy_amax = ops.amax(dy)
+        if want_db:
             if ctx.bn_mode == 2:
                 # training-mode BatchNorm removes the batch mean, so sum_rows dY is identically zero (dY = scale *
                 # (dA - mean(dA) - xhat * mean(dA * xhat)) and sum xhat = 0): the gradient of a conv bias in front of
@@ -412,7 +424,7 @@ class Sequential(nn.Module):
                     cfg = _BlockCfg("cheb", bn, slope, ops.amax_of(x))
                     out = ConvBlockFn.apply(x, g, cfg, mod.bias, bn.weight, bn.bias, *[l.weight for l in mod.lins])
                 if cfg.out_amax is not None:
-                    setattr(out, ops.AMAX_ATTR, cfg.out_amax)      # the next block's transform reads it (same tensor object)
+                    ops.tag_amax(out, cfg.out_amax)      # the next block's transform reads it (same tensor object, same version)
                 env[outs[0]] = out
                 i += consumed
                 continue

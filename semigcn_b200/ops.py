@@ -4,6 +4,7 @@ here is ours (libsemigcn_b200.so).  No CPU path: CPU tensors raise.
 """
 from __future__ import annotations
 
+import os
 from collections import OrderedDict
 from typing import Optional, Tuple
 
@@ -37,12 +38,23 @@ def new_amax(device, count: int = 1) -> Tensor:
     return torch.zeros(count, dtype=torch.float32, device=device)
 
 
-AMAX_ATTR = "_sgb_amax"     # python attribute on an activation tensor: device scalar max|x| published by its producer
+AMAX_ATTR = "_sgb_amax"     # python attribute on an activation tensor: (device scalar max|x| published by its producer, tensor version)
+
+
+def tag_amax(t: Tensor, amax_slot: Tensor) -> None:
+    """Attach the producer's max|t| to the tensor object, together with the tensor's version counter: any in-place edit
+    between two blocks (``x *= k``, ``x.add_(skip)``, an in-place activation in user code) bumps ``_version`` and makes the
+    tag stale -- ``amax_of`` then returns None and the GEMM engine reduces max|x| itself (a stale, too small maximum
+    would overflow the fp16 split silently)."""
+    setattr(t, AMAX_ATTR, (amax_slot, t._version))
 
 
 def amax_of(t: Tensor) -> Optional[Tensor]:
-    a = getattr(t, AMAX_ATTR, None)
-    return a if (a is not None and a.device == t.device) else None
+    tag = getattr(t, AMAX_ATTR, None)
+    if tag is None:
+        return None
+    a, version = tag
+    return a if (a.device == t.device and version == t._version) else None
 
 
 # ----------------------------------------------------------------------------------------
@@ -97,33 +109,67 @@ class MeshGraph:
         return e[:, 1].view(torch.float32)
 
 
-_GRAPH_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_GRAPH_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()   # key -> (graph, edge_index kept alive, bytes)
 _GRAPH_CACHE_PINNED: set = set()         # partitioned operators registered by dist.register_partition: never evicted
-_GRAPH_CACHE_MAX = 16
+_GRAPH_CACHE_MAX_BYTES = int(float(os.environ.get("SGB_GRAPH_CACHE_MB", "4096")) * 2 ** 20)
+_GRAPH_BY_CONTENT: dict = {}             # (fingerprint, shape, device, mode, N) -> pointer key of the entry that holds the graph
+
+
+def _graph_bytes(g: "MeshGraph", edge_index: Tensor) -> int:
+    per_dir = 4 * (g.n + 1) + 4 * max(g.nnz, 1) + 8 * max(g.nnz, 1)
+    return 2 * per_dir + 4 * g.n + edge_index.numel() * edge_index.element_size()
+
+
+def _fingerprint(edge_index: Tensor) -> tuple:
+    lib = L.load()
+    ei = edge_index.contiguous()
+    out = torch.empty(2, dtype=torch.int64, device=ei.device)
+    with torch.cuda.device(ei.device):
+        check(lib.sgb_fingerprint(ptr(ei), ei.numel(), ptr(out), stream_ptr(ei.device)), "sgb_fingerprint")
+    L.count(1)
+    return tuple(out.tolist())          # one host sync, only on a pointer miss
+
+
+def _evict() -> None:
+    total = sum(v[2] for v in _GRAPH_CACHE.values())
+    while total > _GRAPH_CACHE_MAX_BYTES and len(_GRAPH_CACHE) > 1:
+        victim = next((k for k in _GRAPH_CACHE if k not in _GRAPH_CACHE_PINNED), None)
+        if victim is None or victim == next(reversed(_GRAPH_CACHE)):
+            break
+        total -= _GRAPH_CACHE[victim][2]
+        del _GRAPH_CACHE[victim]
+        for ck in [ck for ck, pk in _GRAPH_BY_CONTENT.items() if pk == victim]:
+            del _GRAPH_BY_CONTENT[ck]
 
 
 def graph_for(edge_index: Tensor, num_nodes: int, mode: int) -> MeshGraph:
-    """Cache keyed on (storage pointer, shape, version counter, device, mode, N) -- the
-    reference passes the same ``edge_index`` to every conv of every forward
-    (util/networks.py:65,86) and never mutates it."""
+    """Two-level cache.  Fast path: (storage pointer, shape, version counter, device, mode, N) -- the reference passes the
+    same ``edge_index`` to every conv of a forward (util/networks.py:86) and never mutates it.  On a pointer miss the
+    CONTENT decides (128-bit fingerprint, one hash pass + one host sync): ``data.edge_index.to(self.device)`` of a CPU
+    dataset (util/networks.py:65) makes a fresh device tensor every forward, which must not mean a CSR rebuild per step
+    nor a cache that fills with stale copies.  Bounded by bytes (``SGB_GRAPH_CACHE_MB``, default 4 GiB), LRU."""
+    require_cuda(edge_index)
     key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, str(edge_index.device), mode, int(num_nodes))
     hit = _GRAPH_CACHE.get(key)
     if hit is not None:
         _GRAPH_CACHE.move_to_end(key)
         return hit[0]
+    ckey = (_fingerprint(edge_index), tuple(edge_index.shape), str(edge_index.device), mode, int(num_nodes))
+    pkey = _GRAPH_BY_CONTENT.get(ckey)
+    if pkey is not None and pkey in _GRAPH_CACHE:
+        _GRAPH_CACHE.move_to_end(pkey)
+        return _GRAPH_CACHE[pkey][0]
     g = MeshGraph(edge_index, num_nodes, mode)
-    _GRAPH_CACHE[key] = (g, edge_index)      # keep the tensor alive so the pointer cannot be recycled
-    while len(_GRAPH_CACHE) > _GRAPH_CACHE_MAX + len(_GRAPH_CACHE_PINNED):
-        victim = next((k for k in _GRAPH_CACHE if k not in _GRAPH_CACHE_PINNED), None)
-        if victim is None:
-            break
-        del _GRAPH_CACHE[victim]
+    _GRAPH_CACHE[key] = (g, edge_index, _graph_bytes(g, edge_index))      # keep the tensor alive so the pointer cannot be recycled
+    _GRAPH_BY_CONTENT[ckey] = key
+    _evict()
     return g
 
 
 def clear_graph_cache() -> None:
     _GRAPH_CACHE.clear()
     _GRAPH_CACHE_PINNED.clear()
+    _GRAPH_BY_CONTENT.clear()
 
 
 # ----------------------------------------------------------------------------------------
@@ -219,7 +265,8 @@ def gemm_tn(gmat: Tensor, a: Tensor, out: Optional[Tensor] = None, accumulate: b
     return d
 
 
-def colsum(gmat: Tensor, out: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
+def colsum(gmat: Tensor, out: Optional[Tensor] = None, accumulate: bool = False, amax_out: Optional[Tensor] = None) -> Tensor:
+    """Column sums (bias gradient); ``amax_out`` (device float) additionally receives max|G| from the same pass."""
     lib = L.load()
     require_cuda(gmat)
     gmat = _f32c(gmat, "g")
@@ -229,12 +276,34 @@ def colsum(gmat: Tensor, out: Optional[Tensor] = None, accumulate: bool = False)
     ws = _ws(wsb, gmat.device)
     sp = _prof.span(f"colsum_c{n}", 4.0 * m * n) if _prof.ACTIVE is not None else None
     with torch.cuda.device(gmat.device):
-        check(lib.sgb_colsum(ptr(gmat), gmat.stride(0), m, n, ptr(o), 1 if accumulate else 0, ptr(ws), wsb,
+        check(lib.sgb_colsum(ptr(gmat), gmat.stride(0), m, n, ptr(o), 1 if accumulate else 0, ptr(amax_out), ptr(ws), wsb,
                              stream_ptr(gmat.device)), "sgb_colsum")
     if sp is not None:
         sp.close()
     L.count(2)
     return o
+
+
+def tensor_core_likely(m: int, cin: int, cout: int) -> bool:
+    """Mirror of the engine policy in csrc/gemm.cu (tc_worthwhile / tn_tc_worthwhile): will the dX GEMM [m, cout] x
+    [cout, cin] or the dW GEMM of a layer go to the fp16-split tensor-core engine (which wants max|operand|)?"""
+    return m >= 2048 and min(cin, cout) >= 32 and max(cin, cout) >= 64
+
+
+def amax(x: Tensor) -> Optional[Tensor]:
+    """Device scalar max|x| in one streaming pass, or None when the layout is not the vectorised one (the GEMM engine then
+    reduces it itself).  Used once per operand that none of our kernels produced, then shared by all its consumers."""
+    lib = L.load()
+    require_cuda(x)
+    x = _f32c(x, "x")
+    m, c = x.shape
+    if c % 4 != 0 or x.stride(0) % 4 != 0 or x.data_ptr() % 16 != 0:
+        return None
+    out = torch.empty(1, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.sgb_amax(ptr(x), x.stride(0), m, c, ptr(out), stream_ptr(x.device)), "sgb_amax")
+    L.count(1)
+    return out
 
 
 def col_stats(y: Tensor) -> Tensor:
@@ -264,7 +333,17 @@ def gather_rows(x: Tensor, idx: Tensor, out: Optional[Tensor] = None) -> Tensor:
 def merge_moment_rows(partials: Tensor) -> Tensor:
     """[rows, 3, c] (count, mean, M2) partial rows -> one merged [1, 3, c] float32 row (plain torch ops on the tensor's
     device, float64 inside).  n = sum n_r, mean = sum n_r mean_r / n, M2 = sum (M2_r + n_r (mean_r - mean)^2): the
-    many-way form of Chan's pairwise merge; rows with count 0 drop out."""
+    many-way form of Chan's pairwise merge; rows with count 0 drop out.  CUDA tensors go through ``sgb_moments_merge``
+    (one launch, fp64 inside); the torch form below serves CPU tensors (gloo tests of the host logic)."""
+    if partials.is_cuda:
+        lib = L.load()
+        partials = partials.contiguous()
+        rows, _, c = partials.shape
+        out = torch.empty((1, 3, c), dtype=torch.float32, device=partials.device)
+        with torch.cuda.device(partials.device):
+            check(lib.sgb_moments_merge(ptr(partials), rows, c, ptr(out), stream_ptr(partials.device)), "sgb_moments_merge")
+        L.count(1)
+        return out
     p = partials.to(torch.float64)
     n_r, mean_r, m2_r = p[:, 0, :], p[:, 1, :], p[:, 2, :]
     n = n_r.sum(dim=0)
@@ -279,15 +358,11 @@ def bn_finalize(partials: Tensor, count: int, gamma: Optional[Tensor], beta: Opt
                 momentum: float, running_mean: Optional[Tensor], running_var: Optional[Tensor], comm=None):
     lib = L.load()
     if comm is not None:
-        # SyncBN: each rank first folds its own (count, mean, M2) rows into ONE row (a GEMM-produced layer has one row
-        # per 128-vertex tile: 15 k rows = 48 MB at 2 M vertices x 256 channels -- far too much to all-gather per layer),
-        # then every rank merges the same `world` rows in the same order -> identical statistics everywhere
-        # (opt-in, `comm.prereduce_bn = True`: with it on, tests/test_gpu_dist.py[3-chebconv] moved outside its gradient
-        # tolerance in the one run this round's GPU budget allowed -- a LeakyReLU kink flip or a defect, not yet told apart --
-        # so the default stays the validated path: all ranks merge all rows in the same order)
-        if getattr(comm, "prereduce_bn", False):
-            partials = merge_moment_rows(partials)
-        partials = comm.all_gather_cat(partials.contiguous())
+        # SyncBN: each rank folds its own (count, mean, M2) rows into ONE row (sgb_moments_merge), the ranks all-gather
+        # those rows -- 12*c bytes per rank, the same on every rank whatever its vertex count or the kernel that produced
+        # the layer -- and every rank merges the same `world` rows in the same order: identical statistics everywhere.
+        # (All-gathering the raw rows needs equal row counts on all ranks, which uneven vertex ranges do not give.)
+        partials = comm.all_gather_cat(merge_moment_rows(partials).contiguous())
     rows, _, c = partials.shape
     dev = partials.device
     st = torch.empty((4, c), dtype=torch.float32, device=dev)     # mean, invstd, scale, shift

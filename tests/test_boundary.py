@@ -44,7 +44,8 @@ def test_size_queries_need_no_gpu():
     from semigcn_b200 import _lib as L
     lib = L.load()
     assert lib.sgb_graph_build_workspace_bytes(6000, 1000) > 6000 * 4
-    assert lib.sgb_gemm_stat_rows(1000) == 8
+    assert lib.sgb_gemm_stat_rows(1000) == 4 * 8          # one row per epilogue warp and m-tile group, capped at 4 x #SMs
+    assert lib.sgb_gemm_stat_rows(10 ** 6) <= 4 * 1024    # no longer grows with m (a GPU-less process assumes 148 SMs)
     assert lib.sgb_gemm_tn_workspace_bytes(100000, 256, 256) >= 256 * 256 * 4
 
 

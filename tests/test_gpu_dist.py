@@ -24,7 +24,7 @@ def _rel(a, b):
     return (a.double() - b.double()).abs().max().item() / max(b.double().abs().max().item(), 1e-30)
 
 
-def _worker(rank, world, port, conv):
+def _worker(rank, world, port, conv, slope=0.01, ranges=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     import torch.distributed as dist
@@ -45,6 +45,9 @@ def _worker(rank, world, port, conv):
         target, vmask = prob["ini_vs"].to(dev), prob["v_mask"].to(dev)
         torch.manual_seed(314)
         net = SingleScaleGCN(dev, conv=conv).to(dev)
+        for mod in net.modules():
+            if isinstance(mod, torch.nn.LeakyReLU):
+                mod.negative_slope = slope
         # ---- unpartitioned reference on this process
         out_ref = net(Data(z1=z1, x_pos=x_pos, edge_index=ei), dm)
         loss_ref = losses.mask_pos_rec_loss(out_ref, target, vmask)
@@ -52,7 +55,7 @@ def _worker(rank, world, port, conv):
         grads_ref = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
         net.zero_grad(set_to_none=True)
         # ---- partitioned
-        plan = partition.build_plan(ei, n, rank, world)
+        plan = partition.build_plan(ei, n, rank, world, ranges=ranges)
         ei_local = register_partition(plan, comm)
         net.comm = comm
         lo, hi = plan.lo, plan.hi
@@ -80,8 +83,14 @@ def _worker(rank, world, port, conv):
             # behind 7+ BatchNorm layers on a 1 002-vertex mesh carry the same fp32 noise (tools/diag_grads.py: the fp32
             # oracle itself is 1e-3 away from the fp64 oracle there); the forward check above is the tight one.
             tol = 2e-2 if ".module_1." in k else 5e-3
+            if slope == 1.0:
+                # every LeakyReLU is the identity: the network is smooth, no pre-activation can land on the other side of a
+                # kink, and what is left is the reassociation of the BatchNorm sums across ranks -> an order tighter
+                tol = 2e-3 if ".module_1." in k else 5e-4
             if e / tol > worst:
                 worst, who = e / tol, f"{k} ({e:.2e})"
+        if rank == 0:
+            print(f"world {world} {conv} slope {slope}: output {e_out:.2e}; worst parameter-gradient error / tolerance {worst:.3f} at {who}")
         assert worst <= 1.0, f"rank {rank}: parameter gradients differ at {who}"
     finally:
         dist.destroy_process_group()
@@ -91,3 +100,18 @@ def _worker(rank, world, port, conv):
 @pytest.mark.parametrize("world", [2, 3])
 def test_partitioned_sgcn_equals_single_gpu(world, conv):
     mp.spawn(_worker, args=(world, _free_port(), conv), nprocs=world, join=True)
+
+
+@pytest.mark.parametrize("conv", ["gcnconv", "chebconv"])
+def test_partitioned_sgcn_smooth_network_is_strict(conv):
+    """Triage of round 1's open question (SyncBN with one pre-merged moment row per rank moved [3-chebconv] outside its
+    gradient tolerance: kink flip or defect?): with LeakyReLU slope 1 the network has no kinks, so the partitioned
+    gradients must match an order of magnitude tighter.  They do => the round-1 deviation was a kink flip."""
+    mp.spawn(_worker, args=(3, _free_port(), conv, 1.0), nprocs=3, join=True)
+
+
+@pytest.mark.parametrize("world,ranges", [(2, [(0, 385), (385, 1002)]), (3, [(0, 130), (130, 700), (700, 1002)])])
+def test_partitioned_sgcn_uneven_ranges(world, ranges):
+    """Uneven vertex ranges straddling the 128-row tile boundary: the ranks' kernels produce different numbers of
+    BatchNorm partial rows; SyncBN gathers ONE merged row per rank, so the payload is rank-invariant."""
+    mp.spawn(_worker, args=(world, _free_port(), "gcnconv", 0.01, ranges), nprocs=world, join=True)
