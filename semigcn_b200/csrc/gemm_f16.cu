@@ -104,16 +104,21 @@ constexpr int kHASbo = kHCols * kHALbo;         // bytes between M-adjacent core
 constexpr int kHATile = (kHBM / 8) * kHASbo;    // per hi (or lo)
 constexpr int kHBLbo = 128;
 constexpr int kHBSbo = kHCols * kHBLbo;
-constexpr int kHProducerWarps = 8;             // converter warps: raw fp32 (TMA) -> scaled hi/lo fp16 operand tiles
-constexpr int kHThreads = (kHProducerWarps + 2 + 4 + 1) * 32;   // converters, B copy, MMA, 4 epilogue warps, A TMA
+constexpr int kHConvWarps = 4;                  // warps 0..3: converters, raw fp32 (TMA) -> scaled hi/lo fp16 operand tiles
+constexpr int kHEpiWarps = 8;                   // warps 4..11: epilogue; TMEM lane quarter = warp % 4, two warps per quarter (even / odd 32-column chunks)
+constexpr int kHWarpB = kHConvWarps + kHEpiWarps;      // B copy
+constexpr int kHWarpMma = kHWarpB + 1;                 // MMA issuer, TMEM owner
+constexpr int kHWarpLoad = kHWarpB + 2;                // A TMA loader
+constexpr int kHThreads = (kHWarpLoad + 1) * 32;       // 480
 constexpr int kHRawBytes = kHBM * kHBK * 4;     // one raw A stage: 128 rows x 32 fp32, 128-byte rows, TMA 128B swizzle
 #ifndef SGB_F16_RAW_STAGES
-#define SGB_F16_RAW_STAGES 3
+#define SGB_F16_RAW_STAGES 2
 #endif
 constexpr int kHRawStages = SGB_F16_RAW_STAGES;
 constexpr int kHMaxStages = 6;
 constexpr int kHEpiLd = 36;                     // floats per row of an epilogue warp's 32 x 32 staging tile (+4: conflict-free)
-constexpr int kHEpiBytes = 4 * 32 * kHEpiLd * 4;
+constexpr int kHEpiBytes = kHEpiWarps * 32 * kHEpiLd * 4;
+constexpr int kTEpiBytes = 4 * 32 * kHEpiLd * 4;      // the weight-gradient kernel has four drain warps
 static const int kHSmemBudget = 227 * 1024;
 
 __host__ __device__ constexpr int h_b_tile_bytes(int bn) { return (bn / 8) * kHBSbo; }
@@ -180,12 +185,93 @@ __global__ void __launch_bounds__(256) k_prep_weights_f16(const float* __restric
     }
 }
 
+// One 32-column chunk of an epilogue warp's 32-row block: TMEM -> registers -> unscale -> transpose through the warp's
+// staging tile -> (+C) + bias -> coalesced 128-byte row-segment stores, and (optionally) the chunk's column moments.
+// FULL: all 32 rows of the block and all 32 columns of the chunk are inside C (no per-row / per-column predicates).
+template <bool FULL>
+__device__ __forceinline__ void h_epi_chunk(const HArgs& g, uint32_t taddr, float* __restrict__ stg, float* __restrict__ cp /* row grp, column cc of the chunk */,
+                                            const float* __restrict__ bias_p, int lane, int grp, int cc, int nvalid, bool col_ok, float sc1, float sc2,
+                                            bool stats, float inv_nb, float (&blk_mean)[4], float (&blk_m2)[4]) {
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias_p && (FULL || col_ok)) b = ldg4(bias_p);      // issued first: its latency hides behind the TMEM load
+    float v[32];
+    tmem_ld_32x32(taddr, v);                 // warp-collective: lane = row, registers = 32 consecutive columns
+    if (sc2 == 1.f) {                        // 1 / (s_A s_W) is one exact power-of-two factor in all but extreme-range cases
+#pragma unroll
+        for (int e = 0; e < 32; e += 4)
+            *reinterpret_cast<float4*>(stg + lane * kHEpiLd + e) = make_float4(v[e] * sc1, v[e + 1] * sc1, v[e + 2] * sc1, v[e + 3] * sc1);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 32; e += 4)
+            *reinterpret_cast<float4*>(stg + lane * kHEpiLd + e) =
+                make_float4((v[e] * sc1) * sc2, (v[e + 1] * sc1) * sc2, (v[e + 2] * sc1) * sc2, (v[e + 3] * sc1) * sc2);
+    }
+    __syncwarp();
+    // read back transposed: lane -> rows grp, grp + 4, ..., 16 bytes at column cc: a store instruction then writes four whole
+    // 128-byte row segments (a lane-per-row store touches 32 different lines per instruction and saturates the L1 data pipe)
+    const int64_t ld4 = 4 * g.ldc;
+    float4 o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const bool on = FULL || (col_ok && i * 4 + grp < nvalid);
+        o[i] = on ? *reinterpret_cast<const float4*>(stg + (i * 4 + grp) * kHEpiLd + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (g.accumulate) {                      // all eight loads in flight before the first add
+        float4 old[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const bool on = FULL || (col_ok && i * 4 + grp < nvalid);
+            old[i] = on ? *reinterpret_cast<const float4*>(cp + i * ld4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { o[i].x += old[i].x; o[i].y += old[i].y; o[i].z += old[i].z; o[i].w += old[i].w; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const bool on = FULL || (col_ok && i * 4 + grp < nvalid);
+        if (on) {
+            o[i].x += b.x; o[i].y += b.y; o[i].z += b.z; o[i].w += b.w;
+            *reinterpret_cast<float4*>(cp + i * ld4) = o[i];
+        }
+    }
+    if (stats) {
+        // block mean, then centred second moment (two passes over registers: no cancellation), each reduced over the four
+        // row groups with two butterfly steps (lanes l, l^8, l^16, l^24 hold the same columns); rows / columns outside C are zeros
+        float sm[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sm[0] += o[i].x; sm[1] += o[i].y; sm[2] += o[i].z; sm[3] += o[i].w; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            sm[q] += __shfl_xor_sync(0xffffffffu, sm[q], 8);
+            sm[q] += __shfl_xor_sync(0xffffffffu, sm[q], 16);
+            sm[q] *= inv_nb;
+        }
+        float d2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (FULL || i * 4 + grp < nvalid) {
+                const float dx = o[i].x - sm[0], dy = o[i].y - sm[1], dz = o[i].z - sm[2], dw = o[i].w - sm[3];
+                d2[0] = fmaf(dx, dx, d2[0]); d2[1] = fmaf(dy, dy, d2[1]); d2[2] = fmaf(dz, dz, d2[2]); d2[3] = fmaf(dw, dw, d2[3]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            d2[q] += __shfl_xor_sync(0xffffffffu, d2[q], 8);
+            d2[q] += __shfl_xor_sync(0xffffffffu, d2[q], 16);
+            blk_mean[q] = sm[q];
+            blk_m2[q] = d2[q];
+        }
+    }
+    __syncwarp();                            // the staging tile is free for the next chunk
+}
+
 __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant__ HArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stage_bytes = h_stage_bytes(g.bn);
     const int b_tile_bytes = h_b_tile_bytes(g.bn);
-    // smem: [raw ring: kHRawStages x 16 KB][operand ring: stages x stage_bytes][barriers 256 B][epilogue staging]
+    const uint32_t stages = (uint32_t)g.stages;
+    // smem: [raw ring: kHRawStages x 16 KB][operand ring: stages x stage_bytes][barriers 256 B][epilogue staging: 8 x 4.5 KB]
     uint8_t* const raw_base = smem;
     uint8_t* const op_base = smem + kHRawStages * kHRawBytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(op_base + (size_t)g.stages * stage_bytes);
@@ -198,20 +284,20 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; ++s) {
-            mbar_init(&full[s], kHProducerWarps * 32 + 1);
+            mbar_init(&full[s], kHConvWarps * 32 + 1);
             mbar_init(&empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull[b], 1);
-            mbar_init(&tempty[b], 4);
+            mbar_init(&tempty[b], kHEpiWarps);
         }
         for (int s = 0; s < kHRawStages; ++s) {
             mbar_init(&rfull[s], 1);
-            mbar_init(&rempty[s], kHProducerWarps * 32);
+            mbar_init(&rempty[s], kHConvWarps * 32);
         }
         fence_barrier_init();
     }
-    if (warp == kHProducerWarps + 1) tmem_alloc(tmem_slot, g.tmem_cols);
+    if (warp == kHWarpMma) tmem_alloc(tmem_slot, g.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -219,21 +305,23 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
 
     const int64_t m_tiles = (g.m + kHBM - 1) / kHBM;
     const int64_t total_tiles = m_tiles * g.n_tiles;
+    // tiles blockIdx.x, + gridDim.x, ...; gridDim.x is a multiple of n_tiles, so the n-tile of a CTA never changes.
+    // All ring positions / phases below are carried incrementally (no per-iteration division by a runtime stage count).
+    const uint32_t my_tiles = total_tiles > blockIdx.x ? (uint32_t)((total_tiles - 1 - blockIdx.x) / gridDim.x + 1) : 0u;
+    const uint32_t k_chunks = (uint32_t)g.k_chunks;
 
-    if (warp < kHProducerWarps) {
+    if (warp < kHConvWarps) {
         // ================= A converters: raw fp32 stage (TMA) -> regs (scale, hi/lo fp16) -> operand stage =================
         float sa, inva;
         f16_scale_from_amax(__ldg(g.a_amax), sa, inva);
-        const int ptid = threadIdx.x;                          // 0..255
-        // stage = 128 rows x kHCols core columns (8 K elements = 32 bytes of the raw row); thread: column cq, rows r0, r0 + 64
-        const int cq = ptid % kHCols, r0 = ptid / kHCols;      // r0 in 0..63
-        constexpr int RPT = kHBM * kHCols / 256;               // row slots per thread (2)
-        constexpr int RSTEP = 256 / kHCols;                    // 64
-        const int64_t my_tiles = total_tiles > blockIdx.x ? (total_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-        const int64_t total_it = my_tiles * g.k_chunks;
-        for (int64_t it = 0; it < total_it; ++it) {
-            const int s = (int)(it % g.stages), rs = (int)(it % kHRawStages);
-            const uint32_t ph = (uint32_t)((it / g.stages) & 1), rph = (uint32_t)((it / kHRawStages) & 1);
+        // stage = 128 rows x kHCols core columns (8 K elements = 32 bytes of the raw row); thread: column cq, rows r0 + 32 i
+        const int cq = threadIdx.x & (kHCols - 1), r0 = threadIdx.x >> 2;      // r0 in 0..31
+        static_assert(kHCols == 4, "converter thread mapping assumes 4 core columns per stage");
+        constexpr int RPT = kHBM * kHCols / (kHConvWarps * 32);              // row slots per thread (4)
+        constexpr int RSTEP = kHConvWarps * 32 / kHCols;                       // 32
+        const uint32_t total_it = my_tiles * k_chunks;
+        uint32_t s = 0, ph = 0, rs = 0, rph = 0;
+        for (uint32_t it = 0; it < total_it; ++it) {
             mbar_wait(&rfull[rs], rph);
             const uint8_t* raw = raw_base + (size_t)rs * kHRawBytes;
             float4 v[RPT][2];
@@ -268,55 +356,54 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
             }
             fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
             mbar_arrive(&full[s]);
+            if (++s == stages) { s = 0; ph ^= 1; }
+            if (++rs == (uint32_t)kHRawStages) { rs = 0; rph ^= 1; }
         }
-    } else if (warp == kHProducerWarps + 6) {
+    } else if (warp == kHWarpLoad) {
         // ================= A loader: one lane streams the raw A tiles (TMA 2-D, 128B swizzle, zero fill past m / k) =================
         if (lane == 0) {
             tma_prefetch_desc(&g.a_map);
-            uint32_t it = 0;
-            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int64_t m0 = (tile / g.n_tiles) * kHBM;
-                for (int q = 0; q < g.k_chunks; ++q, ++it) {
-                    const int rs = it % kHRawStages;
-                    const uint32_t rph = (it / kHRawStages) & 1;
+            uint32_t rs = 0, rph = 0;
+            int64_t tile = blockIdx.x;
+            for (uint32_t t = 0; t < my_tiles; ++t, tile += gridDim.x) {
+                const int m0 = (int)((tile / g.n_tiles) * kHBM);
+                for (uint32_t q = 0; q < k_chunks; ++q) {
                     mbar_wait(&rempty[rs], rph ^ 1);
                     mbar_arrive_expect_tx(&rfull[rs], kHRawBytes);
-                    tma_load_2d(raw_base + (size_t)rs * kHRawBytes, &g.a_map, q * kHBK, (int)m0, &rfull[rs]);
+                    tma_load_2d(raw_base + (size_t)rs * kHRawBytes, &g.a_map, (int)(q * kHBK), m0, &rfull[rs]);
+                    if (++rs == (uint32_t)kHRawStages) { rs = 0; rph ^= 1; }
                 }
             }
         }
-    } else if (warp == kHProducerWarps) {
+    } else if (warp == kHWarpB) {
         // ================= B copy: one bulk copy of the pre-tiled hi|lo weight image per stage =================
         if (lane == 0) {
-            uint32_t it = 0;
-            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = (int)(tile % g.n_tiles);
-                for (int q = 0; q < g.k_chunks; ++q, ++it) {
-                    const int s = it % g.stages;
-                    const uint32_t ph = (it / g.stages) & 1;
+            const int nt = (int)(blockIdx.x % g.n_tiles);
+            const uint8_t* src0 = g.wp + (size_t)nt * g.k_chunks * 2 * b_tile_bytes;
+            uint32_t s = 0, ph = 0;
+            for (uint32_t t = 0; t < my_tiles; ++t) {
+                for (uint32_t q = 0; q < k_chunks; ++q) {
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* b_dst = op_base + (size_t)s * stage_bytes + 2 * kHATile;
-                    const uint8_t* src = g.wp + ((size_t)nt * g.k_chunks + q) * 2 * b_tile_bytes;
                     mbar_arrive_expect_tx(&full[s], 2 * b_tile_bytes);
-                    bulk_g2s(b_dst, src, 2 * b_tile_bytes, &full[s]);
+                    bulk_g2s(b_dst, src0 + (size_t)q * 2 * b_tile_bytes, 2 * b_tile_bytes, &full[s]);
+                    if (++s == stages) { s = 0; ph ^= 1; }
                 }
             }
         }
-    } else if (warp == kHProducerWarps + 1) {
+    } else if (warp == kHWarpMma) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            uint32_t it = 0, tcount = 0;
-            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-                const int nt = (int)(tile % g.n_tiles);
-                const int ncols = min(g.bn, g.n - nt * g.bn);                 // multiple of 16
-                const uint32_t idesc = make_idesc_f16(kHBM, ncols, 0, 0);
-                const int acc = tcount & 1;
+            const int nt = (int)(blockIdx.x % g.n_tiles);
+            const int ncols = min(g.bn, g.n - nt * g.bn);                     // multiple of 16
+            const uint32_t idesc = make_idesc_f16(kHBM, ncols, 0, 0);
+            uint32_t s = 0, ph = 0;
+            for (uint32_t tcount = 0; tcount < my_tiles; ++tcount) {
+                const uint32_t acc = tcount & 1;
                 mbar_wait(&tempty[acc], ((tcount >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.acc_stride);
-                for (int q = 0; q < g.k_chunks; ++q, ++it) {
-                    const int s = it % g.stages;
-                    const uint32_t ph = (it / g.stages) & 1;
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)g.acc_stride;
+                for (uint32_t q = 0; q < k_chunks; ++q) {
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(op_base + (size_t)s * stage_bytes);
@@ -330,121 +417,72 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
                         const uint64_t dbh = make_desc(b_hi + j * 2 * kHBLbo, kHBLbo, kHBSbo);
                         const uint64_t dbl = make_desc(b_lo + j * 2 * kHBLbo, kHBLbo, kHBSbo);
                         // small terms first, the dominant hi*hi product last
-                        umma_f16(d_tmem, dal, dbh, idesc, (q | j) ? 1u : 0u);
+                        umma_f16(d_tmem, dal, dbh, idesc, (q | (uint32_t)j) ? 1u : 0u);
                         umma_f16(d_tmem, dah, dbl, idesc, 1u);
                         umma_f16(d_tmem, dah, dbh, idesc, 1u);
                     }
                     umma_commit(&empty[s]);          // frees the smem slot when the MMAs above have read it
+                    if (++s == stages) { s = 0; ph ^= 1; }
                 }
                 umma_commit(&tfull[acc]);            // accumulator complete
             }
         }
     } else {
-        // ================= epilogue: TMEM -> registers -> unscale (+bias, +C) -> global (+ BatchNorm moments) =================
+        // ================= epilogue (8 warps): TMEM -> registers -> unscale (+bias, +C) -> global (+ BatchNorm moments) =================
+        // The epilogue of a 128 x 256 tile is a long dependent chain per warp (TMEM load -> staging -> read back -> store);
+        // with four warps it took ~20 k cycles per tile and bounded every K <= 256 shape (ncu, profiles/r2_*): two warps per
+        // TMEM lane quarter, each taking every other 32-column chunk, halve it.
         float sa, inva;
         f16_scale_from_amax(__ldg(g.a_amax), sa, inva);
         const float invw = __ldg(g.wscale + 1);
+        float sc1 = inva * invw, sc2 = 1.f;
+        if (!(fabsf(sc1) >= 1.1754944e-38f && fabsf(sc1) <= 3.4028235e38f)) { sc1 = inva; sc2 = invw; }   // product out of range: two exact factors
+        const int ew = warp - kHConvWarps;           // 0..7
         const int quarter = warp & 3;                // TMEM lanes 32*quarter .. +31 are accessible to this warp
-        float* stg = reinterpret_cast<float*>(op_base + (size_t)g.stages * stage_bytes + 256) + quarter * 32 * kHEpiLd;
+        const int half = ew >> 2;                    // chunks half, half + 2, half + 4, half + 6 of the n-tile
+        float* stg = reinterpret_cast<float*>(op_base + (size_t)g.stages * stage_bytes + 256) + ew * 32 * kHEpiLd;
         const int grp = lane >> 3;                   // row group of the transposed read-back: rows grp, grp + 4, ...
         const int cc = (lane & 7) * 4;               // this lane's float4 inside a 32-column chunk
         const bool stats = g.stat_partials != nullptr;
+        const int nt = (int)(blockIdx.x % g.n_tiles);
+        const int n0 = nt * g.bn;
+        const int ncols = min(g.bn, g.n - n0);
         // Running column moments (count, mean, M2) of every row this warp has stored, Chan-merged one 32-row block at a
-        // time while the block is still in registers (no second pass over C).  gridDim.x is a multiple of n_tiles, so a
-        // CTA only ever sees one n-tile: the count is the same for all of its columns.  Chunk u of the n-tile is owned
-        // by the lanes of row group u % 4 (slot u / 4): 16 registers of state instead of 64.
-        float st_mean[2][4], st_m2[2][4], st_n = 0.f;
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { st_mean[sl][q] = 0.f; st_m2[sl][q] = 0.f; }
-        uint32_t tcount = 0;
-        for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-            const int nt = (int)(tile % g.n_tiles);
+        // time while the block is still in registers (no second pass over C).  A CTA only ever sees one n-tile, so the
+        // count is the same for all of its columns.  Of the warp's four chunks, chunk t is owned by the lanes of row group t.
+        float st_mean[4] = {0.f, 0.f, 0.f, 0.f}, st_m2[4] = {0.f, 0.f, 0.f, 0.f}, st_n = 0.f;
+        int64_t tile = blockIdx.x;
+        for (uint32_t tcount = 0; tcount < my_tiles; ++tcount, tile += gridDim.x) {
             const int64_t m0 = (tile / g.n_tiles) * kHBM;
-            const int n0 = nt * g.bn;
-            const int ncols = min(g.bn, g.n - n0);
-            const int acc = tcount & 1;
+            const uint32_t acc = tcount & 1;
             mbar_wait(&tfull[acc], (tcount >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * g.acc_stride);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)g.acc_stride;
             const int64_t rows_left = g.m - (m0 + quarter * 32);
             const int nvalid = rows_left >= 32 ? 32 : (rows_left > 0 ? (int)rows_left : 0);   // rows of this warp's block inside C
             const float nb = (float)nvalid;
             const float inv_nb = nvalid ? 1.f / nb : 0.f;
             const float wgt = nvalid ? nb / (st_n + nb) : 0.f;                                // Chan weight of the new block
+            float* crow = g.c + (m0 + quarter * 32 + grp) * g.ldc + n0 + cc;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {            // bn <= 256: at most eight 32-column chunks (unrolled: the moment registers are indexed statically)
-                const int c0 = u * 32;
+            for (int t = 0; t < 4; ++t) {            // unrolled: the moment registers are indexed statically
+                const int c0 = (2 * t + half) * 32;
                 if (c0 < ncols) {
-                    float v[32];
-                    tmem_ld_32x32(taddr + c0, v);        // warp-collective: lane = row, registers = 32 consecutive columns
-                    // transpose through the warp's staging tile so that global stores are whole 128-byte row segments
-                    // (a lane-per-row store touches 32 different lines per instruction and saturates the L1 data pipe)
-#pragma unroll
-                    for (int e = 0; e < 32; e += 4)
-                        *reinterpret_cast<float4*>(stg + lane * kHEpiLd + e) =
-                            make_float4((v[e] * inva) * invw, (v[e + 1] * inva) * invw, (v[e + 2] * inva) * invw, (v[e + 3] * inva) * invw);
-                    __syncwarp();
+                    float bm[4], bq[4];
                     const bool col_ok = c0 + cc < ncols;             // ncols is a multiple of 16 => whole float4 valid
-                    float4 o[8];
-                    if (col_ok) {
-                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (g.bias) b = ldg4(g.bias + n0 + c0 + cc);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int j = i * 4 + grp;
-                            o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (j < nvalid) {
-                                o[i] = *reinterpret_cast<const float4*>(stg + j * kHEpiLd + cc);
-                                float* cp = g.c + (m0 + quarter * 32 + j) * g.ldc + n0 + c0 + cc;
-                                if (g.accumulate) {
-                                    const float4 old = *reinterpret_cast<const float4*>(cp);
-                                    o[i].x += old.x; o[i].y += old.y; o[i].z += old.z; o[i].w += old.w;
-                                }
-                                o[i].x += b.x; o[i].y += b.y; o[i].z += b.z; o[i].w += b.w;
-                                *reinterpret_cast<float4*>(cp) = o[i];
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    if (stats && nvalid) {
-                        // block mean, then centred second moment (two passes over registers: no cancellation), each reduced
-                        // over the four row groups with two butterfly steps (lanes l, l^8, l^16, l^24 hold the same columns)
-                        float s[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) { s[0] += o[i].x; s[1] += o[i].y; s[2] += o[i].z; s[3] += o[i].w; }   // invalid rows are zeros
+                    const float* bias_p = g.bias ? g.bias + n0 + c0 + cc : nullptr;
+                    if (nvalid == 32 && c0 + 32 <= ncols)
+                        h_epi_chunk<true>(g, taddr + c0, stg, crow + c0, bias_p, lane, grp, cc, nvalid, col_ok, sc1, sc2, stats, inv_nb, bm, bq);
+                    else
+                        h_epi_chunk<false>(g, taddr + c0, stg, crow + c0, bias_p, lane, grp, cc, nvalid, col_ok, sc1, sc2, stats && nvalid > 0, inv_nb, bm, bq);
+                    if (stats && nvalid > 0 && grp == t) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            s[q] += __shfl_xor_sync(0xffffffffu, s[q], 8);
-                            s[q] += __shfl_xor_sync(0xffffffffu, s[q], 16);
-                            s[q] *= inv_nb;                                  // block mean
-                        }
-                        float d2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            if (i * 4 + grp < nvalid) {
-                                const float dx = o[i].x - s[0], dy = o[i].y - s[1], dz = o[i].z - s[2], dw = o[i].w - s[3];
-                                d2[0] = fmaf(dx, dx, d2[0]); d2[1] = fmaf(dy, dy, d2[1]); d2[2] = fmaf(dz, dz, d2[2]); d2[3] = fmaf(dw, dw, d2[3]);
-                            }
-                        }
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            d2[q] += __shfl_xor_sync(0xffffffffu, d2[q], 8);
-                            d2[q] += __shfl_xor_sync(0xffffffffu, d2[q], 16);
-                        }
-                        if (grp == (u & 3)) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float delta = s[q] - st_mean[u >> 2][q];
-                                st_mean[u >> 2][q] = fmaf(delta, wgt, st_mean[u >> 2][q]);
-                                st_m2[u >> 2][q] += d2[q] + delta * delta * st_n * wgt;
-                            }
+                            const float delta = bm[q] - st_mean[q];
+                            st_mean[q] = fmaf(delta, wgt, st_mean[q]);
+                            st_m2[q] += bq[q] + delta * delta * st_n * wgt;
                         }
                     }
-                    __syncwarp();
                 }
             }
             st_n += nb;
@@ -453,24 +491,18 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
             if (lane == 0) mbar_arrive(&tempty[acc]);
         }
         if (stats) {
-            const int nt = (int)(blockIdx.x % g.n_tiles);
-            const int n0 = nt * g.bn;
-            const int ncols = min(g.bn, g.n - n0);
             float* row = g.stat_partials + ((int64_t)(blockIdx.x / g.n_tiles) * 4 + quarter) * 3 * g.n;
-#pragma unroll
-            for (int sl = 0; sl < 2; ++sl) {
-                const int c0 = (sl * 4 + grp) * 32;
-                if (c0 + cc < ncols) {
-                    st4(row + 0 * (int64_t)g.n + n0 + c0 + cc, make_float4(st_n, st_n, st_n, st_n));
-                    st4(row + 1 * (int64_t)g.n + n0 + c0 + cc, make_float4(st_mean[sl][0], st_mean[sl][1], st_mean[sl][2], st_mean[sl][3]));
-                    st4(row + 2 * (int64_t)g.n + n0 + c0 + cc, make_float4(st_m2[sl][0], st_m2[sl][1], st_m2[sl][2], st_m2[sl][3]));
-                }
+            const int c0 = (2 * grp + half) * 32;        // the chunk whose moments this lane holds
+            if (c0 + cc < ncols) {
+                st4(row + 0 * (int64_t)g.n + n0 + c0 + cc, make_float4(st_n, st_n, st_n, st_n));
+                st4(row + 1 * (int64_t)g.n + n0 + c0 + cc, make_float4(st_mean[0], st_mean[1], st_mean[2], st_mean[3]));
+                st4(row + 2 * (int64_t)g.n + n0 + c0 + cc, make_float4(st_m2[0], st_m2[1], st_m2[2], st_m2[3]));
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == kHProducerWarps + 1) {
+    if (warp == kHWarpMma) {
         tc_fence_after();
         tmem_dealloc(tmem_base, g.tmem_cols);
     }
@@ -578,9 +610,8 @@ __global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const __grid_const
         const uint32_t lo_off = is_g ? (uint32_t)kTGTile : (uint32_t)a_tile_bytes;
         // rows 4*c4 .. 4*c4+3 of the operand tile, core column mg
         const uint32_t base_off = tile_off + (uint32_t)((c4 * 4) >> 3) * kTSbo + (uint32_t)mg * kTLbo + (uint32_t)((c4 * 4) & 7) * 16;
+        uint32_t s = 0, ph = 0, rs = 0, rph = 0;         // ring positions / phases carried incrementally (no division by a runtime stage count)
         for (int it = 0; it < chunks; ++it) {
-            const int s = it % t.stages, rs = it % kTRawStages;
-            const uint32_t ph = (it / t.stages) & 1, rph = (it / kTRawStages) & 1;
             mbar_wait(&rfull[rs], rph);
             const uint8_t* raw = raw_base + (size_t)rs * raw_bytes + raw_off;
             uint4 h[4], l[4];
@@ -615,29 +646,30 @@ __global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const __grid_const
             }
             fence_proxy_async();
             mbar_arrive(&full[s]);
+            if (++s == (uint32_t)t.stages) { s = 0; ph ^= 1; }
+            if (++rs == (uint32_t)kTRawStages) { rs = 0; rph ^= 1; }
         }
     } else if (warp == kTProducerWarps + 1 + kTDrainWarps) {
         // ================= loader: one lane streams the raw G and A boxes of each 32-vertex stage (TMA 2-D, zero fill) =================
         if (lane == 0) {
             tma_prefetch_desc(&t.g_map);
             tma_prefetch_desc(&t.a_map);
+            uint32_t rs = 0, rph = 0;
             for (int it = 0; it < chunks; ++it) {
-                const int rs = it % kTRawStages;
-                const uint32_t rph = (it / kTRawStages) & 1;
                 mbar_wait(&rempty[rs], rph ^ 1);
                 mbar_arrive_expect_tx(&rfull[rs], (uint32_t)(raw_g_bytes + raw_a_bytes));
                 uint8_t* dst = raw_base + (size_t)rs * raw_bytes;
                 const int row = (int)(ms + (int64_t)it * kTBV);
                 tma_load_2d(dst, &t.g_map, n0, row, &rfull[rs]);
                 tma_load_2d(dst + raw_g_bytes, &t.a_map, k0, row, &rfull[rs]);
+                if (++rs == (uint32_t)kTRawStages) { rs = 0; rph ^= 1; }
             }
         }
     } else if (warp == kTProducerWarps) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc_f16(kTBM, t.bk, 0, 0);        // both operands K-major (K = vertex)
+            uint32_t s = 0, ph = 0;
             for (int it = 0; it < chunks; ++it) {
-                const int s = it % t.stages;
-                const uint32_t ph = (it / t.stages) & 1;
                 const int seg = it / kTSegChunks, in_seg = it % kTSegChunks;
                 const int acc = seg & 1;
                 if (in_seg == 0) {
@@ -663,6 +695,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const __grid_const
                 }
                 umma_commit(&empty[s]);
                 if (in_seg == kTSegChunks - 1 || it == chunks - 1) umma_commit(&tfull[acc]);
+                if (++s == (uint32_t)t.stages) { s = 0; ph ^= 1; }
             }
         }
     } else {
@@ -833,9 +866,9 @@ static TPlan t_plan(int64_t m, int n, int k) {
     p.gbox = n < kTBM ? n : kTBM;
     p.abox = k < p.bk ? k : p.bk;
     int raw = (kTBV * (p.gbox + p.abox) * 4 + 127) / 128 * 128;
-    int st = (kHSmemBudget - 256 - kHEpiBytes - kTRawStages * raw) / sb;
+    int st = (kHSmemBudget - 256 - kTEpiBytes - kTRawStages * raw) / sb;
     p.stages = st > 4 ? 4 : st;
-    p.smem_bytes = (size_t)kTRawStages * raw + (size_t)p.stages * sb + 256 + kHEpiBytes;
+    p.smem_bytes = (size_t)kTRawStages * raw + (size_t)p.stages * sb + 256 + kTEpiBytes;
     int tiles = p.k_tiles * p.n_tiles;
     int64_t want = num_sms() / tiles;
     if (want < 1) want = 1;

@@ -107,11 +107,14 @@ __global__ void __launch_bounds__(kLossThreads) k_step_loss_fwd(const LossArgs a
 }
 
 // out[0] = loss_p, out[1] = loss_n, out[2] = count_v, out[3] = count_f
-__global__ void k_step_loss_finalize(const double* __restrict__ partials, int rows, int t64, double* __restrict__ out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(kLossThreads) k_step_loss_finalize(const double* __restrict__ partials, int rows, int t64, double* __restrict__ out) {
+    // one CTA: thread r sums rows r, r + 256, ... (fixed order), then the fixed-order tree of block_sum -> deterministic
+    __shared__ double sh[kLossThreads];
     double s[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int r = 0; r < rows; ++r)
+    for (int r = threadIdx.x; r < rows; r += kLossThreads)
         for (int j = 0; j < 4; ++j) s[j] += partials[(int64_t)r * 4 + j];
+    for (int j = 0; j < 4; ++j) s[j] = block_sum(s[j], sh);
+    if (threadIdx.x != 0) return;
     double lp = sqrt(s[0] / s[1] + 1.0e-6);            // 0/0 -> NaN like the reference's empty mask
     double ln = s[2] / s[3];
     if (!t64) { lp = (double)sqrtf((float)(s[0] / s[1]) + 1.0e-6f); ln = (double)(float)ln; }
@@ -316,7 +319,7 @@ extern "C" int sgb_step_loss_fwd(const float* pos, int64_t ldp, int64_t n, const
     const int grid = loss_grid(n > nf ? n : nf);
     k_step_loss_fwd<<<grid, kLossThreads, 0, stream>>>(a, fn_out, partials);
     SGB_CHECK_LAUNCH("k_step_loss_fwd");
-    k_step_loss_finalize<<<1, 32, 0, stream>>>(partials, grid, target_f64, out);
+    k_step_loss_finalize<<<1, kLossThreads, 0, stream>>>(partials, grid, target_f64, out);
     SGB_CHECK_LAUNCH("k_step_loss_finalize");
     return SGB_OK;
 }

@@ -19,6 +19,7 @@ import torch
 from torch import Tensor
 
 from . import _lib as L
+from . import profile as _prof
 from ._lib import SgbError, check, ptr, require_cuda, stream_ptr
 
 
@@ -118,7 +119,7 @@ class StepLossFn(torch.autograd.Function):
         rows = lib.sgb_loss_partial_rows()
         partials = torch.empty((rows, 4), dtype=torch.float64, device=dev)
         out = torch.empty(4, dtype=torch.float64, device=dev)
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _prof.region("step_loss", 4.0 * 3 * n + (8.0 if t64 else 4.0) * 3 * (n + nf) + 24.0 * nf):
             check(lib.sgb_step_loss_fwd(ptr(pos), pos.stride(0), n, ptr(tpos), 1 if t64 else 0, ptr(vmask),
                                         ptr(topo.faces) if nf else None, nf, ptr(tfn) if nf else None, ptr(fmask) if nf else None,
                                         None, ptr(partials), ptr(out), stream_ptr(dev)), "sgb_step_loss_fwd")
@@ -137,7 +138,7 @@ class StepLossFn(torch.autograd.Function):
         grads = dres.to(torch.float64).contiguous()
         dpos = torch.empty((n, 3), dtype=torch.float32, device=dev)
         topo, nf = ctx.topo, ctx.nf
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _prof.region("step_loss", 4.0 * 6 * n + (8.0 if ctx.t64 else 4.0) * 3 * (n + nf) + 36.0 * nf):
             check(lib.sgb_step_loss_bwd(ptr(pos), pos.stride(0), n, ptr(ctx.tpos), 1 if ctx.t64 else 0, ptr(ctx.vmask),
                                         ptr(topo.faces) if nf else None, nf, ptr(ctx.tfn) if nf else None, ptr(ctx.fmask) if nf else None,
                                         ptr(topo.rowptr) if nf else None, ptr(topo.inc) if nf else None, ptr(out), ptr(grads),

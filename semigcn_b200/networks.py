@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from . import profile as _prof
 from .nn import ChebConv, GCNConv, Sequential
 
 SGCN_WIDTHS = [4, 16, 32, 64, 128, 256, 256, 512, 256, 256, 128, 64, 32, 16, 3]

@@ -5,6 +5,7 @@ here is ours (libsemigcn_b200.so).  No CPU path: CPU tensors raise.
 from __future__ import annotations
 
 import os
+import weakref
 from collections import OrderedDict
 from typing import Optional, Tuple
 
@@ -113,6 +114,7 @@ _GRAPH_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()   # key -> (graph, edg
 _GRAPH_CACHE_PINNED: set = set()         # partitioned operators registered by dist.register_partition: never evicted
 _GRAPH_CACHE_MAX_BYTES = int(float(os.environ.get("SGB_GRAPH_CACHE_MB", "4096")) * 2 ** 20)
 _GRAPH_BY_CONTENT: dict = {}             # (fingerprint, shape, device, mode, N) -> pointer key of the entry that holds the graph
+_GRAPH_ALIAS: dict = {}                  # pointer key of ANOTHER tensor with the same content -> (weakref to that tensor, canonical pointer key)
 
 
 def _graph_bytes(g: "MeshGraph", edge_index: Tensor) -> int:
@@ -154,10 +156,22 @@ def graph_for(edge_index: Tensor, num_nodes: int, mode: int) -> MeshGraph:
     if hit is not None:
         _GRAPH_CACHE.move_to_end(key)
         return hit[0]
+    alias = _GRAPH_ALIAS.get(key)
+    if alias is not None:
+        # a tensor whose content was fingerprinted before: valid only while that very tensor object is alive (a recycled
+        # pointer under a new tensor object must be fingerprinted again), referenced weakly so the cache never pins copies
+        if alias[0]() is edge_index and alias[1] in _GRAPH_CACHE:
+            _GRAPH_CACHE.move_to_end(alias[1])
+            return _GRAPH_CACHE[alias[1]][0]
+        del _GRAPH_ALIAS[key]
     ckey = (_fingerprint(edge_index), tuple(edge_index.shape), str(edge_index.device), mode, int(num_nodes))
     pkey = _GRAPH_BY_CONTENT.get(ckey)
     if pkey is not None and pkey in _GRAPH_CACHE:
         _GRAPH_CACHE.move_to_end(pkey)
+        if len(_GRAPH_ALIAS) >= 256:         # keys of dead tensors / old version counters
+            for k in [k for k, (wr, _) in _GRAPH_ALIAS.items() if wr() is None or k[2] != wr()._version]:
+                del _GRAPH_ALIAS[k]
+        _GRAPH_ALIAS[key] = (weakref.ref(edge_index), pkey)      # the other convs of this forward hit without hashing
         return _GRAPH_CACHE[pkey][0]
     g = MeshGraph(edge_index, num_nodes, mode)
     _GRAPH_CACHE[key] = (g, edge_index, _graph_bytes(g, edge_index))      # keep the tensor alive so the pointer cannot be recycled
@@ -170,6 +184,7 @@ def clear_graph_cache() -> None:
     _GRAPH_CACHE.clear()
     _GRAPH_CACHE_PINNED.clear()
     _GRAPH_BY_CONTENT.clear()
+    _GRAPH_ALIAS.clear()
 
 
 # ----------------------------------------------------------------------------------------
@@ -311,8 +326,11 @@ def col_stats(y: Tensor) -> Tensor:
     y = _f32c(y, "y")
     m, c = y.shape
     partials = torch.empty((lib.sgb_col_stat_rows(m, c), 3, c), dtype=torch.float32, device=y.device)
+    sp = _prof.span(f"col_stats_c{c}", 4.0 * m * c) if _prof.ACTIVE is not None else None
     with torch.cuda.device(y.device):
         check(lib.sgb_col_stats(ptr(y), y.stride(0), m, c, ptr(partials), stream_ptr(y.device)), "sgb_col_stats")
+    if sp is not None:
+        sp.close()
     L.count(1)
     return partials
 
@@ -365,11 +383,14 @@ def bn_finalize(partials: Tensor, count: int, gamma: Optional[Tensor], beta: Opt
         partials = comm.all_gather_cat(merge_moment_rows(partials).contiguous())
     rows, _, c = partials.shape
     dev = partials.device
+    sp = _prof.span("bn_finalize", 12.0 * rows * c) if _prof.ACTIVE is not None else None
     st = torch.empty((4, c), dtype=torch.float32, device=dev)     # mean, invstd, scale, shift
     with torch.cuda.device(dev):
         check(lib.sgb_bn_finalize(ptr(partials), rows, c, count, ptr(gamma), ptr(beta), float(eps), float(momentum),
                                   ptr(running_mean), ptr(running_var), ptr(st[0]), ptr(st[1]), ptr(st[2]), ptr(st[3]),
                                   stream_ptr(dev)), "sgb_bn_finalize")
+    if sp is not None:
+        sp.close()
     L.count(1)
     return st[0], st[1], st[2], st[3]
 

@@ -57,3 +57,18 @@ class _Span:
 
 def span(family: str, nbytes: float, flops: float = 0.0) -> Optional[_Span]:
     return _Span(family, nbytes, flops) if ACTIVE is not None else None
+
+
+class region:
+    """``with profile.region("adam"):`` -- brackets any stretch of stream work (torch ops included) as one record of the
+    active profile, so that the per-family times of a step add up to the step.  No-op when no profile is active."""
+
+    def __init__(self, family: str, nbytes: float = 0.0, flops: float = 0.0):
+        self.sp = span(family, nbytes, flops)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        if self.sp is not None:
+            self.sp.close()
