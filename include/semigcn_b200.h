@@ -243,6 +243,28 @@ SGB_API int sgb_lap_loss_fwd(const float* pos, int64_t ldp, int64_t n, const int
 SGB_API int sgb_lap_loss_bwd(const float* diff, int64_t n, const int32_t* rowptr, const int32_t* rowptr_t, const sgb_edge_t* edges_t,
                      const double* out, const double* grad /* [1] */, float* dpos, int64_t lddpos, void* stream);
 
+/* ------------------------------------------------------------------------------------ *
+ * 6. Bilateral-normal-filter regulariser (the `-CAD` term of the step, sgcn.py:133-136):
+ *    replaces Loss.fn_bnf_detach_loss(pos, fn, mesh, ltype, loop) (util/loss.py:197-253).
+ *    pos [n,3] (treated as detached), fn [nf,3] = compute_fn(pos) (the differentiable input),
+ *    f2f [nf,3] int32 = the faces across the three sides, -1 where a side is on a boundary
+ *    (Mesh.f2f, util/mesh.py:215-227).  `loop` detached filter iterations with weights
+ *    exp(-|dc|^2 / 2 sigma_c^2) exp(-|dn|^2 / 2 sigma_s^2) area (sigma_s = 0.3, sigma_c = mean
+ *    centroid distance), then the distance of fn to the filtered normals.
+ *    ltype: 0 "mae", 1 "l1mae" (the default), 2 "rmse", 3 "l1rmse".
+ *    work: float[sgb_bnf_work_floats(nf)], partials: double[sgb_bnf_partial_rows()];
+ *    new_fn [nf,3] receives the filtered normals; out[0] = loss, out[1] = internal (for _bwd).
+ *    _bwd: dfn [nf,3] = grad[0] * dloss/dfn (the filtered normals are detached, so this is the
+ *    whole gradient).  fp32 arithmetic like the reference, fp64 sums, deterministic.
+ * ------------------------------------------------------------------------------------ */
+SGB_API size_t sgb_bnf_work_floats(int64_t nf);
+SGB_API int sgb_bnf_partial_rows(void);
+SGB_API int sgb_bnf_loss_fwd(const float* pos, int64_t ldp, int64_t n, const int64_t* faces, const int32_t* f2f, int64_t nf,
+                     const float* fn, int loop, int ltype, float* work, double* partials, float* new_fn, double* out /* [2] */,
+                     void* stream);
+SGB_API int sgb_bnf_loss_bwd(const float* fn, const float* new_fn, int64_t nf, int ltype, const double* out, const double* grad /* [1] */,
+                     float* dfn, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -99,7 +99,7 @@ __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, ui
 constexpr int kHBM = 128;                       // rows per tile == UMMA M
 constexpr int kHBK = 32;                        // K elements per pipeline stage (2 MMA k-slices of 16)
 constexpr int kHCols = kHBK / 8;                // 16-byte core-matrix columns per stage
-constexpr int kHALbo = 160;                     // bytes between K-adjacent core matrices of A (128 + 32 pad: conflict-free 16-byte stores)
+constexpr int kHALbo = 128;                     // bytes between K-adjacent core matrices of A (dense; a quarter-warp of converters fills one whole core matrix)
 constexpr int kHASbo = kHCols * kHALbo;         // bytes between M-adjacent core matrices of A
 constexpr int kHATile = (kHBM / 8) * kHASbo;    // per hi (or lo)
 constexpr int kHBLbo = 128;
@@ -112,12 +112,12 @@ constexpr int kHWarpLoad = kHWarpB + 2;                // A TMA loader
 constexpr int kHThreads = (kHWarpLoad + 1) * 32;       // 480
 constexpr int kHRawBytes = kHBM * kHBK * 4;     // one raw A stage: 128 rows x 32 fp32, 128-byte rows, TMA 128B swizzle
 #ifndef SGB_F16_RAW_STAGES
-#define SGB_F16_RAW_STAGES 2
+#define SGB_F16_RAW_STAGES 3
 #endif
 constexpr int kHRawStages = SGB_F16_RAW_STAGES;
 constexpr int kHMaxStages = 6;
-constexpr int kHEpiLd = 36;                     // floats per row of an epilogue warp's 32 x 32 staging tile (+4: conflict-free)
-constexpr int kHEpiBytes = kHEpiWarps * 32 * kHEpiLd * 4;
+constexpr int kHEpiLd = 36;                     // weight-gradient kernel: floats per row of a drain warp's 32 x 32 staging tile (+4: conflict-free)
+constexpr int kHEpiBytes = kHEpiWarps * 32 * 32 * 4;  // forward kernel: dense 32 x 32 tiles, 16-byte chunks XOR-swizzled by the row (conflict-free both ways)
 constexpr int kTEpiBytes = 4 * 32 * kHEpiLd * 4;      // the weight-gradient kernel has four drain warps
 static const int kHSmemBudget = 227 * 1024;
 
@@ -198,12 +198,12 @@ __device__ __forceinline__ void h_epi_chunk(const HArgs& g, uint32_t taddr, floa
     tmem_ld_32x32(taddr, v);                 // warp-collective: lane = row, registers = 32 consecutive columns
     if (sc2 == 1.f) {                        // 1 / (s_A s_W) is one exact power-of-two factor in all but extreme-range cases
 #pragma unroll
-        for (int e = 0; e < 32; e += 4)
-            *reinterpret_cast<float4*>(stg + lane * kHEpiLd + e) = make_float4(v[e] * sc1, v[e + 1] * sc1, v[e + 2] * sc1, v[e + 3] * sc1);
+        for (int e = 0; e < 32; e += 4)      // row `lane`, 16-byte chunk e / 4 stored at chunk position (e / 4) ^ (lane % 8)
+            *reinterpret_cast<float4*>(stg + lane * 32 + (((e >> 2) ^ (lane & 7)) << 2)) = make_float4(v[e] * sc1, v[e + 1] * sc1, v[e + 2] * sc1, v[e + 3] * sc1);
     } else {
 #pragma unroll
         for (int e = 0; e < 32; e += 4)
-            *reinterpret_cast<float4*>(stg + lane * kHEpiLd + e) =
+            *reinterpret_cast<float4*>(stg + lane * 32 + (((e >> 2) ^ (lane & 7)) << 2)) =
                 make_float4((v[e] * sc1) * sc2, (v[e + 1] * sc1) * sc2, (v[e + 2] * sc1) * sc2, (v[e + 3] * sc1) * sc2);
     }
     __syncwarp();
@@ -214,7 +214,7 @@ __device__ __forceinline__ void h_epi_chunk(const HArgs& g, uint32_t taddr, floa
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const bool on = FULL || (col_ok && i * 4 + grp < nvalid);
-        o[i] = on ? *reinterpret_cast<const float4*>(stg + (i * 4 + grp) * kHEpiLd + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+        o[i] = on ? *reinterpret_cast<const float4*>(stg + (i * 4 + grp) * 32 + ((((lane & 7) ^ ((i * 4 + grp) & 7))) << 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (g.accumulate) {                      // all eight loads in flight before the first add
         float4 old[8];
@@ -314,8 +314,11 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
         // ================= A converters: raw fp32 stage (TMA) -> regs (scale, hi/lo fp16) -> operand stage =================
         float sa, inva;
         f16_scale_from_amax(__ldg(g.a_amax), sa, inva);
-        // stage = 128 rows x kHCols core columns (8 K elements = 32 bytes of the raw row); thread: column cq, rows r0 + 32 i
-        const int cq = threadIdx.x & (kHCols - 1), r0 = threadIdx.x >> 2;      // r0 in 0..31
+        // stage = 128 rows x kHCols core columns (8 K elements = 32 bytes of the raw row).  A quarter-warp (the unit a 16-byte
+        // shared-memory access is processed in) takes the 8 rows of ONE core matrix at one core column: its reads hit 8
+        // distinct swizzled chunks of the raw rows, its writes fill one dense 128-byte core matrix -- conflict-free both ways
+        // without padding the operand tile.  Thread: core column cq, rows r0 + 32 i.
+        const int cq = (threadIdx.x >> 3) & (kHCols - 1), r0 = (threadIdx.x & 7) + 8 * (threadIdx.x >> 5);      // r0 in 0..31
         static_assert(kHCols == 4, "converter thread mapping assumes 4 core columns per stage");
         constexpr int RPT = kHBM * kHCols / (kHConvWarps * 32);              // row slots per thread (4)
         constexpr int RSTEP = kHConvWarps * 32 / kHCols;                       // 32
@@ -440,7 +443,7 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
         const int ew = warp - kHConvWarps;           // 0..7
         const int quarter = warp & 3;                // TMEM lanes 32*quarter .. +31 are accessible to this warp
         const int half = ew >> 2;                    // chunks half, half + 2, half + 4, half + 6 of the n-tile
-        float* stg = reinterpret_cast<float*>(op_base + (size_t)g.stages * stage_bytes + 256) + ew * 32 * kHEpiLd;
+        float* stg = reinterpret_cast<float*>(op_base + (size_t)g.stages * stage_bytes + 256) + ew * 32 * 32;
         const int grp = lane >> 3;                   // row group of the transposed read-back: rows grp, grp + 4, ...
         const int cc = (lane & 7) * 4;               // this lane's float4 inside a 32-column chunk
         const bool stats = g.stat_partials != nullptr;

@@ -243,44 +243,89 @@ def mask_norm_rec_loss(pred_norm: Tensor, real_norm: Tensor, mask: Tensor) -> Te
     return torch.sum(d * m) / torch.sum(m)
 
 
-def fn_bnf_detach_loss(pos: Tensor, fn: Tensor, faces: Tensor, f2f: Tensor, ltype: str = "l1mae", loop: int = 5):
-    """util/loss.py:197-253 (the ``-CAD`` regulariser, sgcn.py:133-136): bilateral filtering of the face normals over the
-    1-ring ``f2f`` (weights exp(-|dc|^2 / 2 sigma_c^2) exp(-|dn|^2 / 2 sigma_s^2) area, sigma_s = 0.3, sigma_c = mean
-    centroid distance, ``loop`` detached iterations) and the distance of ``fn`` to the filtered normals.  Returns
-    ``(loss, new_fn)`` like the reference.  Plain torch ops on the caller's device (v0: ~40 small kernels per call; the
-    fused gather kernel is a next-round row); ``faces`` / ``f2f`` are int64 tensors (``mesh.faces``,
-    ``mesh.f2f`` or ``meshgen.face_adjacency``), -1 = no neighbour."""
-    if ltype not in ("mae", "l1mae", "rmse", "l1rmse"):
+_BNF_LTYPES = {"mae": 0, "l1mae": 1, "rmse": 2, "l1rmse": 3}
+_F2F_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+
+
+def _f2f_i32(f2f, device) -> Tensor:
+    """``mesh.f2f`` (int64 numpy array in the reference, util/mesh.py:227) as the int32 device tensor the kernel reads, cached
+    per array object (the reference passes the same mesh every step, sgcn.py:134)."""
+    if isinstance(f2f, np.ndarray):
+        key = ("np", id(f2f), f2f.shape, str(device))
+    else:
+        key = ("t", f2f.data_ptr(), tuple(f2f.shape), f2f._version, str(f2f.device), str(device))
+    hit = _F2F_CACHE.get(key)
+    if hit is not None:
+        _F2F_CACHE.move_to_end(key)
+        return hit[0]
+    t = torch.from_numpy(np.ascontiguousarray(f2f)) if isinstance(f2f, np.ndarray) else f2f
+    t = t.to(device).to(torch.int32).contiguous()
+    if t.dim() != 2 or t.shape[1] != 3:
+        raise SgbError("f2f must have shape [F, 3]")
+    _F2F_CACHE[key] = (t, f2f)
+    while len(_F2F_CACHE) > 8:
+        _F2F_CACHE.popitem(last=False)
+    return t
+
+
+class BnfLossFn(torch.autograd.Function):
+    """(loss, new_fn) of util/loss.py:197-253 as one autograd node on the kernels of csrc/bnf_loss.cu."""
+
+    @staticmethod
+    def forward(ctx, pos: Tensor, fn: Tensor, faces: Tensor, f2f: Tensor, ltype: int, loop: int):
+        lib = L.load()
+        require_cuda(pos, fn, faces, f2f)
+        if fn.dtype != torch.float32 or pos.dtype != torch.float32:
+            raise SgbError("fn_bnf_detach_loss: pos and fn must be float32 (the network output and its face normals)")
+        pos = pos.detach()
+        if pos.stride(1) != 1:
+            pos = pos.contiguous()
+        fn_c = fn.detach().contiguous()
+        dev = fn.device
+        nf, n = int(fn_c.shape[0]), int(pos.shape[0])
+        if tuple(faces.shape) != (nf, 3) or tuple(f2f.shape) != (nf, 3):
+            raise SgbError("fn_bnf_detach_loss: faces and f2f must be [F, 3] with F = fn.shape[0]")
+        work = torch.empty(lib.sgb_bnf_work_floats(nf), dtype=torch.float32, device=dev)
+        partials = torch.empty(lib.sgb_bnf_partial_rows(), dtype=torch.float64, device=dev)
+        new_fn = torch.empty((nf, 3), dtype=torch.float32, device=dev)
+        out = torch.empty(2, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev), _prof.region("bnf_loss", 4.0 * nf * (13 + 24 * max(loop, 0))):
+            check(lib.sgb_bnf_loss_fwd(ptr(pos), pos.stride(0), n, ptr(faces), ptr(f2f), nf, ptr(fn_c), int(loop), int(ltype),
+                                       ptr(work), ptr(partials), ptr(new_fn), ptr(out), stream_ptr(dev)), "sgb_bnf_loss_fwd")
+        L.count(5 + max(int(loop), 0))
+        ctx.save_for_backward(fn_c, new_fn, out)
+        ctx.ltype = int(ltype)
+        ctx.mark_non_differentiable(new_fn)
+        return out[0].to(torch.float32), new_fn
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_new_fn):
+        lib = L.load()
+        fn_c, new_fn, out = ctx.saved_tensors
+        dev = fn_c.device
+        nf = int(fn_c.shape[0])
+        grad = g_loss.detach().to(torch.float64).reshape(1).contiguous()
+        dfn = torch.empty((nf, 3), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev), _prof.region("bnf_loss", 4.0 * nf * 9):
+            check(lib.sgb_bnf_loss_bwd(ptr(fn_c), ptr(new_fn), nf, ctx.ltype, ptr(out), ptr(grad), ptr(dfn), stream_ptr(dev)),
+                  "sgb_bnf_loss_bwd")
+        L.count(1)
+        return None, dfn, None, None, None, None
+
+
+def fn_bnf_detach_loss(pos, fn: Tensor, faces, f2f, ltype: str = "l1mae", loop: int = 5):
+    """``Loss.fn_bnf_detach_loss(pos, fn, mesh, ltype, loop)`` (util/loss.py:197-253; the ``-CAD`` regulariser of the step,
+    sgcn.py:133-136) on the fused kernels of csrc/bnf_loss.cu: ``faces`` / ``f2f`` are ``mesh.faces`` / ``mesh.f2f`` (numpy
+    arrays as the reference holds them, or tensors; ``meshgen.face_adjacency`` builds ``f2f`` without the reference's
+    ``Mesh``), -1 = no neighbour.  Returns ``(loss, new_fn)`` like the reference; the gradient reaches ``fn`` only (the
+    filtered normals are detached).  CUDA tensors only -- the CPU restatement used by the tests lives in
+    oracle/loss_ref.py."""
+    if ltype not in _BNF_LTYPES:
         raise SgbError(f"fn_bnf_detach_loss: unknown ltype {ltype!r}")
+    require_cuda(fn)
     dev = fn.device
-    pos = pos.detach().to(dev)
-    faces, f2f = faces.to(dev).long(), f2f.to(dev).long()
-    fc = torch.sum(pos[faces], 1) / 3.0
-    fa = torch.linalg.cross(pos[faces[:, 1]] - pos[faces[:, 0]], pos[faces[:, 2]] - pos[faces[:, 0]])
-    fa = 0.5 * torch.sqrt(torch.sum(fa ** 2, dim=1) + 1.0e-12)
-    no_neig = 1.0 * (f2f != -1)
-    neig_fc = fc[f2f]                                  # -1 wraps to the last face exactly as the reference's indexing does
-    neig_fa = fa[f2f] * no_neig
-    fc_dist = torch.sum((neig_fc - fc.reshape(-1, 1, 3)) ** 2, dim=2)
-    sigma_c = torch.sum(torch.sqrt(fc_dist + 1.0e-12)) / (fc_dist.shape[0] * fc_dist.shape[1])
-    wc = torch.exp(-1.0 * fc_dist / (2 * (sigma_c ** 2)))
-    new_fn = fn
-    for _ in range(loop):
-        neig_fn = new_fn[f2f]
-        fn_dist = torch.sum((neig_fn - new_fn.reshape(-1, 1, 3)) ** 2, dim=2)
-        ws = torch.exp(-1.0 * fn_dist / (2 * (0.3 ** 2)))
-        w = (wc * ws * neig_fa).unsqueeze(2)
-        new_fn = torch.sum(w * neig_fn, dim=1)
-        new_fn = new_fn / (torch.sqrt(torch.sum(new_fn * new_fn, dim=1, keepdim=True) + 1.0e-12) + 1.0e-12)
-        new_fn = new_fn.detach()
-    if ltype == "mae":
-        loss = torch.sum(torch.sqrt(torch.sum((new_fn - fn) ** 2, dim=1) + 1.0e-12)) / fn.shape[0]
-    elif ltype == "l1mae":
-        loss = torch.sum(torch.sum(torch.abs(new_fn - fn), dim=1)) / fn.shape[0]
-    elif ltype == "rmse":
-        loss = torch.sqrt(torch.sum(torch.sum((new_fn - fn) ** 2, dim=1)) / fn.shape[0] + 1.0e-12)
-    else:   # "l1rmse" exactly as written in the reference (util/loss.py:246-249)
-        d = torch.sum(torch.abs(new_fn - fn), dim=1)
-        loss = torch.sum(d ** 2) / fn.shape[0]
-        loss = torch.sqrt(loss ** 2 + 1.0e-12)
-    return loss, new_fn
+    if isinstance(pos, np.ndarray):
+        pos = torch.from_numpy(pos)
+    pos = pos.to(dev)
+    topo = topology_for(faces, int(pos.shape[0]), dev)           # int64 device faces, cached per faces object
+    return BnfLossFn.apply(pos, fn, topo.faces, _f2f_i32(f2f, dev), _BNF_LTYPES[ltype], int(loop))

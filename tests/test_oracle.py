@@ -213,11 +213,12 @@ def test_oracle_sgcn_matches_reference_networks_py(conv, skip):
 
 @pytest.mark.parametrize("n", [4, 8])
 def test_fn_bnf_detach_loss_matches_reference(n):
-    """The -CAD regulariser (util/loss.py:197-253) as torch ops (semigcn_b200.losses.fn_bnf_detach_loss; device-agnostic,
-    so the same code is checked here on CPU) against the reference's own output on the reference's own ``Mesh.f2f``,
-    and the vectorised ``f2f`` builder against the reference's (same neighbour sets; slot order is the reference's
-    Counter order there, side order here -- a reordering of a 3-term sum)."""
-    from semigcn_b200 import losses, meshgen
+    """The CPU restatement of the -CAD regulariser (oracle/loss_ref.py, util/loss.py:197-253) against the reference's own
+    output on the reference's own ``Mesh.f2f`` -- this pins the checker the fused CUDA kernels are held to
+    (tests/test_gpu_losses.py) -- and the vectorised ``f2f`` builder against the reference's (same neighbour sets; slot
+    order is the reference's Counter order there, side order here -- a reordering of a 3-term sum)."""
+    from oracle import loss_ref as losses
+    from semigcn_b200 import meshgen
     gold = load_golden(n)
     pred = torch.from_numpy(gold["pred"])
     faces = torch.from_numpy(gold["faces"]).long()
