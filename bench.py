@@ -11,9 +11,15 @@ two step losses + backward + Adam step, on a synthetic geodesic icosphere of fre
 (998 562 vertices, 5 991 360 directed edges).  One "step" = one such train step on one mask
 (sgcn.py:129-146).  metric = directed edges * conv layers / second.
 
-N > 1: one process per GPU (torchrun), each rank trains its own independent mesh of the same size
-(config 5 style: self-prior = one model per mesh, no data-path collective) -> weak scaling;
-timing is barrier + max over ranks.
+N > 1: one process per GPU (torchrun).  The headline `value` is the replica workload -- each rank trains its own
+independent mesh of the same size (self-prior = one model per mesh, sgcn.py:78-80; no data-path collective) -> weak
+scaling, barrier + max over ranks.  The SAME line then carries the runs the north star asks for next to it:
+  "partition": ONE mesh vertex-partitioned over the N GPUs (BASELINE.json configs[3]): per-propagation halo all-to-all
+               over NCCL overlapped with the interior rows, SyncBN, gradient all-reduce; strong scaling against the
+               single-GPU step of the same mesh measured in the same invocation, plus the 16 M-vertex mesh at N >= 4;
+  "batch64":   64 independent 100 k-vertex meshes spread over the N GPUs (configs[4]), several per GPU on streams,
+               each as a whole-step CUDA graph.
+At N = 1 the line also carries configs[0] / configs[1]: the SGCN and MGCN steps on a 10 242-vertex mesh (CUDA graph).
 """
 from __future__ import annotations
 
@@ -51,9 +57,11 @@ def parse():
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel CUDA-event roofline pass")
     ap.add_argument("--cuda-graph", action="store_true",
                     help="replay the whole train step as one CUDA graph (semigcn_b200/graphed.py): the launch-bound small-mesh regime")
-    ap.add_argument("--order", default="given", choices=["given", "morton"],
-                    help="partition mode: vertex numbering the contiguous cut is taken on (morton: Z-order renumbering, balanced halos; "
-                         "CPU-tested, not yet timed on GPUs)")
+    ap.add_argument("--order", default="morton", choices=["given", "morton"],
+                    help="partition mode: vertex numbering the contiguous cut is taken on (morton: Z-order patches, balanced halos; "
+                         "given: the generator's numbering).  Both are followed by the interior-first order inside every rank's range")
+    ap.add_argument("--no-overlap", action="store_true", help="partition mode: do not overlap the halo exchange with the interior rows")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra blocks (partition / batch64 / configs[0], [1]) of the default line")
     ap.add_argument("--mode", default="replicas", choices=["replicas", "partition"],
                     help="replicas: one independent mesh per GPU (default, configs[2]/[4]); partition: ONE mesh vertex-partitioned over the "
                          "GPUs with per-propagation halo exchange over NCCL (configs[3], strong scaling)")
@@ -226,7 +234,8 @@ def run_ours(args, rank, world, local_rank):
         out = net(data_in, dm)
         loss = step_losses(out, prob)
         loss.backward()
-        opt.step()
+        with profile.region("adam"):         # no-op unless the roofline pass below is active
+            opt.step()
         return loss
 
     def barrier():
@@ -355,6 +364,7 @@ def run_ours(args, rank, world, local_rank):
         line["kernel_shapes_top"] = {k: {"ms_per_step": v["ms"] / prof_steps, "GBps": v["bytes"] / (v["ms"] / 1e3) / 1e9,
                                          "launches_per_step": v["launches"] / prof_steps}
                                      for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])[:8]}
+        line["kernel_families_sum_ms"] = tot_ms / prof_steps      # vs ms_per_step: what the per-family records account for
         alg = algorithmic_bytes_per_step(n, nnz, SGCN_WIDTHS)
         line["step_algorithmic_GB"] = alg / 1e9
         line["step_hbm_frac"] = alg / (ms / args.steps / 1e3) / 1e9 / pk["hbm_gbs"]
@@ -364,7 +374,7 @@ def run_ours(args, rank, world, local_rank):
             line["gcnconv_layer"] = gcnconv_layer_bench(mesh.edge_index, n, nnz, dev, pk)
         except Exception as exc:   # noqa: BLE001
             line["gcnconv_layer"] = {"error": repr(exc)[:300]}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:        # the contract: rank 0 at N = 1 only
         line["cpu_baseline"] = cpu_reference(args, steps=2, warmup=1, freq=args.cpu_freq or 100)
     return line
 
@@ -408,7 +418,9 @@ def run_reference(args, rank, world):
     if rank != 0:
         return None
     from semigcn_b200.networks import SGCN_WIDTHS
-    freq = args.cpu_freq or (100 if args.steps + args.warmup <= 16 else 50)
+    # a FIXED sample whatever --steps / --warmup are: the 100 002-vertex icosphere (about 2 s per step on 16 host cores; the
+    # 998 562-vertex mesh of our arm would take ~19 s per step, minutes for the driver's 25 steps).  edges/s normalises the size.
+    freq = args.cpu_freq or 100
     cb = cpu_reference(args, steps=args.steps, warmup=args.warmup, freq=freq)
     return {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
@@ -418,47 +430,108 @@ def run_reference(args, rank, world):
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
-def run_partition(args, rank, world, local_rank):
-    """BASELINE.json configs[3]: ONE mesh, vertices partitioned over the ranks (contiguous ranges of the generator's
-    grid-like numbering), one halo exchange per propagation (all-to-all over NCCL), SyncBN partial all-gather,
-    weight-gradient all-reduce.  Total work is fixed as N grows -> strong scaling.  The step is forward + the masked
-    position loss (the face-normal loss needs faces across cuts; not partitioned yet) + backward + gradient sum + Adam."""
-    from semigcn_b200 import _lib, partition
+def _time_steps(step_fn, steps: int, warmup: int, barrier):
+    """W untimed + K timed calls of ``step_fn(i)``, CUDA events on the current stream, barrier + synchronize on both sides."""
+    for i in range(warmup):
+        step_fn(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = None
+    for i in range(steps):
+        out = step_fn(i)
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1), out
+
+
+def single_gpu_measure(args, dev, freq: int, steps: int, warmup: int):
+    """The UNPARTITIONED train step (forward + both step losses + backward + Adam, exactly the headline workload) on one
+    icosphere of frequency ``freq`` on ``dev``: the like-for-like single-GPU rate the partitioned runs are compared with."""
+    from semigcn_b200 import ops
+    from semigcn_b200.data import Data
+    from semigcn_b200.networks import SingleScaleGCN
+    prob = make_problem(freq, dev, seed=314)
+    mesh = prob["mesh"]
+    torch.manual_seed(314)
+    net = SingleScaleGCN(dev, conv=args.conv).to(dev)
+    opt = torch.optim.Adam(net.parameters(), lr=0.01)
+    data = Data(z1=prob["z1"], x_pos=prob["x_pos"], edge_index=mesh.edge_index)
+
+    def one_step(i):
+        opt.zero_grad(set_to_none=True)
+        loss = step_losses(net(data, prob["dms"][:, i % 8:i % 8 + 1]), prob)
+        loss.backward()
+        opt.step()
+        return loss
+
+    ms, loss = _time_steps(one_step, steps, warmup, torch.cuda.synchronize)
+    res = {"vertices": mesh.num_vertices, "directed_edges": mesh.nnz, "ms_per_step": ms / steps,
+           "edges_per_s": float(mesh.nnz) * N_LAYERS * steps / (ms / 1e3), "final_loss": float(loss.detach())}
+    del net, opt, data, prob, mesh
+    ops.clear_graph_cache()
+    torch.cuda.empty_cache()
+    return res
+
+
+def partition_measure(args, rank, world, local_rank, freq: int, steps: int, warmup: int, e2e: bool = True):
+    """BASELINE.json configs[3]: ONE mesh, vertices partitioned over the ranks -- Morton patches (contiguous ranges of a
+    Z-order renumbering), interior vertices first inside every range.  Per propagation one halo exchange (pack kernel +
+    all-to-all over NCCL) that runs WHILE the interior rows are aggregated; SyncBN all-gathers one merged moment row per
+    rank per layer; weight gradients are all-reduced once per step.  The step is the single-GPU step: forward + masked
+    position loss + face-normal loss across the cuts + backward + gradient sum + Adam.  Total work is fixed as N grows
+    -> strong scaling.  Returns a dict on rank 0 (None elsewhere); device-timed, max over ranks."""
+    from semigcn_b200 import _lib, ops, partition
     from semigcn_b200._lib import MODE_CHEB, MODE_GCN
     from semigcn_b200.data import Data
-    from semigcn_b200.dist import TorchComm, dist_mask_pos_rec_loss, register_partition, sync_gradients
-    from semigcn_b200.networks import SingleScaleGCN, SGCN_WIDTHS
+    from semigcn_b200.dist import (TorchComm, dist_mask_norm_rec_loss, dist_mask_pos_rec_loss, register_partition, sync_gradients)
+    from semigcn_b200.networks import SingleScaleGCN
     dev = torch.device(f"cuda:{local_rank}")
-    torch.cuda.set_device(dev)
-    _lib.load()
     comm = TorchComm()
-    prob = make_problem(args.freq, dev, seed=314)            # the same mesh on every rank
+    prob = make_problem(freq, dev, seed=314)            # the same mesh on every rank
     mesh = prob["mesh"]
     n, nnz = mesh.num_vertices, mesh.nnz
-    ei_global = mesh.edge_index
+    ei, faces = mesh.edge_index, mesh.faces
+    vt = [prob[k] for k in ("z1", "x_pos", "ini", "v_mask", "dms")]
+    ranges = partition.vertex_ranges(n, world)
+
+    def renumbered(perm, ei, faces, vt):
+        ei, *vt = partition.renumber(perm, ei, *vt)
+        inv = torch.empty_like(perm)
+        inv[perm] = torch.arange(n, device=dev)
+        return ei, inv[faces], vt
+
     if args.order == "morton":
-        perm = partition.morton_order(mesh.vs)
-        ei_global, z1_, xp_, ini_, vm_, dms_ = partition.renumber(perm, mesh.edge_index, prob["z1"], prob["x_pos"], prob["ini"],
-                                                                  prob["v_mask"], prob["dms"])
-        prob.update(z1=z1_, x_pos=xp_, ini=ini_, v_mask=vm_, dms=dms_)
-        ei_global = ei_global.contiguous()
-    plan = partition.build_plan(ei_global, n, rank, world)
+        ei, faces, vt = renumbered(partition.morton_order(mesh.vs), ei, faces, vt)
+    ei, faces, vt = renumbered(partition.interior_first_order(ei, n, ranges), ei, faces, vt)
+    ei = ei.contiguous()
+    z1_, xp_, ini_, vm_, dms_ = vt
+    plan = partition.build_plan(ei, n, rank, world, ranges=ranges)
     lo, hi = plan.lo, plan.hi
-    own = {k: prob[k][lo:hi].contiguous() for k in ("z1", "x_pos", "ini", "v_mask", "dms")}
+    own = {"z1": z1_[lo:hi].contiguous(), "x_pos": xp_[lo:hi].contiguous(), "ini": ini_[lo:hi].contiguous(),
+           "v_mask": vm_[lo:hi].contiguous(), "dms": dms_[lo:hi].contiguous()}
+    fid, f_loc = partition.local_faces(plan, faces)
+    fn_loc, fm_loc = prob["fn"][fid].contiguous(), prob["f_mask"][fid].contiguous()
     halo_rows = plan.n_ghost
-    del prob, mesh, ei_global
+    del prob, mesh, ei, faces, vt, z1_, xp_, ini_, vm_, dms_, fid
     torch.cuda.empty_cache()
-    ei_local = register_partition(plan, comm, modes=(MODE_GCN if args.conv == "gcnconv" else MODE_CHEB,))
+    mode = MODE_GCN if args.conv == "gcnconv" else MODE_CHEB
+    ei_local = register_partition(plan, comm, modes=(mode,), overlap=not args.no_overlap)
+    g_part = ops.graph_for(ei_local, hi - lo, mode)
     torch.manual_seed(314)
     net = SingleScaleGCN(dev, conv=args.conv).to(dev)
     net.comm = comm
     opt = torch.optim.Adam(net.parameters(), lr=0.01)
     data = Data(z1=own["z1"], x_pos=own["x_pos"], edge_index=ei_local)
 
-    def one_step(i):
+    def loss_of(out):
+        lp = dist_mask_pos_rec_loss(out, own["ini"], own["v_mask"], comm)
+        ln = dist_mask_norm_rec_loss(out, g_part.halo, f_loc, fn_loc, fm_loc, comm)
+        return lp + K1 * ln
+
+    def one_step(i, dm=None):
         opt.zero_grad(set_to_none=True)
-        out = net(data, own["dms"][:, i % 8:i % 8 + 1])
-        loss = dist_mask_pos_rec_loss(out, own["ini"], own["v_mask"], comm)
+        loss = loss_of(net(data, own["dms"][:, i % 8:i % 8 + 1] if dm is None else dm))
         loss.backward()
         sync_gradients(net, comm)
         opt.step()
@@ -468,73 +541,304 @@ def run_partition(args, rank, world, local_rank):
         torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
+    sampler = ClockSampler(local_rank)
+    for i in range(warmup):
         one_step(i)
     barrier()
-    sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = _lib.LAUNCHES
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        loss = one_step(i)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    launches0, bytes0, calls0 = _lib.LAUNCHES, g_part.halo.bytes_total, g_part.halo.calls
+    ms, loss = _time_steps(one_step, steps, 0, barrier)
     launches = _lib.LAUNCHES - launches0
+    halo_bytes = (g_part.halo.bytes_total - bytes0) / steps
+    halo_calls = (g_part.halo.calls - calls0) / steps
     clocks = sampler.stop()
-    loss_host = torch.empty((), dtype=torch.float64).pin_memory()
-    # e2e: this rank's slice of z1 / x_pos / mask uploaded from pinned host memory every step, loss read back
-    h = {k: own[k].cpu().pin_memory() for k in ("z1", "x_pos")}
-    h_dm = [own["dms"][:, j:j + 1].contiguous().cpu().pin_memory() for j in range(8)]
-    d_dm = torch.empty((hi - lo, 1), dtype=torch.float32, device=dev)
+    ms_e2e, h2d = ms, 0
+    if e2e:
+        # this rank's slice of z1 / x_pos / mask uploaded from pinned host memory every step, loss read back
+        loss_host = torch.empty((), dtype=torch.float64).pin_memory()
+        h = {k: own[k].cpu().pin_memory() for k in ("z1", "x_pos")}
+        h_dm = [own["dms"][:, j:j + 1].contiguous().cpu().pin_memory() for j in range(8)]
+        d_dm = torch.empty((hi - lo, 1), dtype=torch.float32, device=dev)
 
-    def e2e_step(i):
-        own["z1"].copy_(h["z1"], non_blocking=True)
-        own["x_pos"].copy_(h["x_pos"], non_blocking=True)
-        d_dm.copy_(h_dm[i % 8], non_blocking=True)
-        opt.zero_grad(set_to_none=True)
-        out = net(data, d_dm)
-        loss = dist_mask_pos_rec_loss(out, own["ini"], own["v_mask"], comm)
-        loss.backward()
-        sync_gradients(net, comm)
-        opt.step()
-        loss_host.copy_(loss.detach(), non_blocking=True)
+        def e2e_step(i):
+            own["z1"].copy_(h["z1"], non_blocking=True)
+            own["x_pos"].copy_(h["x_pos"], non_blocking=True)
+            d_dm.copy_(h_dm[i % 8], non_blocking=True)
+            loss_host.copy_(one_step(i, d_dm).detach(), non_blocking=True)
 
-    e2e_step(0)
-    barrier()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for i in range(args.steps):
-        e2e_step(i)
-    t1.record()
-    barrier()
-    ms_e2e = t0.elapsed_time(t1)
-    h2d = sum(t.numel() * t.element_size() for t in (h["z1"], h["x_pos"], h_dm[0]))
-    t = torch.tensor([ms, ms_e2e, float(halo_rows), float(h2d)], dtype=torch.float64, device=dev)
+        ms_e2e, _ = _time_steps(e2e_step, steps, 1, barrier)
+        h2d = sum(t.numel() * t.element_size() for t in (h["z1"], h["x_pos"], h_dm[0]))
+    t = torch.tensor([ms, ms_e2e, float(halo_rows), float(h2d), float(halo_bytes), float(g_part.n_interior), float(hi - lo)],
+                     dtype=torch.float64, device=dev)
     tmax = t.clone()
     torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
     torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
-    ms, ms_e2e = float(tmax[0]), float(tmax[1])
+    final_loss = float(loss.detach())
+    del net, opt, data, own, g_part, plan
+    ops.clear_graph_cache()
+    torch.cuda.empty_cache()
     if rank != 0:
         return None
-    units = float(nnz) * N_LAYERS * args.steps
+    ms, ms_e2e = float(tmax[0]), float(tmax[1])
+    units = float(nnz) * N_LAYERS * steps
     return {
-        "metric": METRIC, "value": units / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": f"SGCN ({args.conv}, 13 blocks, widths {SGCN_WIDTHS}) fwd + masked position loss + bwd + gradient all-reduce + Adam "
-                               f"on ONE icosphere n={args.freq} ({n} vertices, {nnz} directed edges) vertex-partitioned over {world} GPU(s); "
-                               "BASELINE.json configs[3] at the largest size that also fits one GPU",
-                   "vertices": n, "directed_edges": nnz, "conv_layers": N_LAYERS,
-                   "parallelism": f"vertex partition x{world}: halo all-to-all per propagation (NCCL), SyncBN partial all-gather, grad all-reduce",
-                   "halo_rows_total": int(t[2]), "halo_rows_max_per_rank": int(tmax[2]), "vertex_order": args.order,
-                   "l2_policy": "inputs larger than L2; no explicit flush"},
-        "train_steps_per_s": args.steps / (ms / 1e3),
-        "e2e": {"value": units / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(t[3]), "d2h_bytes_per_step": 8 * world,
-                "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches, "clocks": clocks, "final_loss": float(loss.detach()),
+        "vertices": n, "directed_edges": nnz, "n_gpus": world, "ms_per_step": ms / steps, "edges_per_s": units / (ms / 1e3),
+        "e2e_ms_per_step": ms_e2e / steps, "e2e_edges_per_s": units / (ms_e2e / 1e3), "h2d_bytes_per_step": int(t[3]),
+        "halo_rows_total": int(t[2]), "halo_rows_max_per_rank": int(tmax[2]), "interior_rows_frac": float(t[5]) / float(t[6]),
+        "halo_exchanges_per_step": halo_calls, "halo_bytes_per_step_per_rank_max": float(tmax[4]), "vertex_order": args.order + " + interior-first",
+        "overlap": not args.no_overlap, "gpu_launches": launches, "clocks": clocks, "final_loss": final_loss,
+        "collectives": "per propagation 1 all_to_all_single (halo rows x C floats, overlapped with the interior rows); per BatchNorm layer 1 "
+                       "all_gather_into_tensor of one (count, mean, M2) row per rank (12 C bytes) + 1 all_reduce (2 C floats, backward); per step "
+                       "1 all_reduce of the parameter gradients (0.49 M floats), 3 scalar all_reduces (losses), 2 all_reduces of 3 floats (bounding box)",
     }
+
+
+def run_partition(args, rank, world, local_rank):
+    """``--mode partition``: the partitioned run alone, as the bench line."""
+    from semigcn_b200.networks import SGCN_WIDTHS
+    r = partition_measure(args, rank, world, local_rank, args.freq, args.steps, args.warmup)
+    if r is None:
+        return None
+    return {
+        "metric": METRIC, "value": r["edges_per_s"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"SGCN ({args.conv}, 13 blocks, widths {SGCN_WIDTHS}) fwd + step losses (position + face normals across cuts) + bwd + "
+                               f"gradient all-reduce + Adam on ONE icosphere n={args.freq} ({r['vertices']} vertices, {r['directed_edges']} directed edges) "
+                               f"vertex-partitioned over {world} GPU(s); BASELINE.json configs[3]",
+                   "vertices": r["vertices"], "directed_edges": r["directed_edges"], "conv_layers": N_LAYERS,
+                   "parallelism": f"vertex partition x{world}: " + r["collectives"],
+                   "halo_rows_total": r["halo_rows_total"], "halo_rows_max_per_rank": r["halo_rows_max_per_rank"], "vertex_order": r["vertex_order"],
+                   "overlap": r["overlap"], "l2_policy": "inputs larger than L2; no explicit flush"},
+        "train_steps_per_s": 1e3 / r["ms_per_step"],
+        "e2e": {"value": r["e2e_edges_per_s"], "unit": UNIT, "h2d_bytes_per_step": r["h2d_bytes_per_step"], "d2h_bytes_per_step": 8 * world,
+                "ms_per_step": r["e2e_ms_per_step"]},
+        "gpu_launches": r["gpu_launches"], "clocks": r["clocks"], "final_loss": r["final_loss"], "partition": r,
+    }
+
+
+def partition_block(args, rank, world, local_rank):
+    """The partitioned runs carried by the default ``--gpus N`` line (N > 1):
+      * the 3 994 242-vertex mesh (the largest of the series that also fits ONE GPU) partitioned over the N GPUs, against the
+        unpartitioned step on the same mesh measured by rank 0 alone in this invocation  -> like-for-like strong scaling;
+      * N >= 4: the 16 002 252-vertex mesh (configs[3]; needs >= 2 GPUs: ~260 GB of saved activations), against N x the
+        single-GPU rate on a mesh of the PER-RANK size (16 M / N vertices) and against the 4 M single-GPU rate."""
+    dev = torch.device(f"cuda:{local_rank}")
+    steps, warmup = min(args.steps, 5), 3
+    out = {}
+    single = None
+    if rank == 0:
+        single = single_gpu_measure(args, dev, 632, steps, warmup)
+    torch.distributed.barrier()
+    p4 = partition_measure(args, rank, world, local_rank, 632, steps, warmup, e2e=False)
+    if rank == 0:
+        p4["single_gpu_same_mesh"] = single
+        p4["speedup_vs_single_gpu_same_mesh"] = single["ms_per_step"] / p4["ms_per_step"]
+        out["mesh_4m"] = p4
+    if world >= 4:
+        per_rank = None
+        if rank == 0:
+            import math
+            f_pr = int(round(math.sqrt((16002252 / world - 2) / 10.0)))
+            per_rank = single_gpu_measure(args, dev, f_pr, steps, warmup)
+        torch.distributed.barrier()
+        p16 = partition_measure(args, rank, world, local_rank, 1265, steps, warmup, e2e=False)
+        if rank == 0:
+            p16["single_gpu_per_rank_size_mesh"] = per_rank
+            p16["speedup_vs_single_gpu_rate_at_per_rank_size"] = p16["edges_per_s"] / per_rank["edges_per_s"]
+            p16["speedup_vs_single_gpu_rate_4m_mesh"] = p16["edges_per_s"] / single["edges_per_s"]
+            p16["target"] = ">= 6x at 8 GPUs (BASELINE.json north_star)"
+            out["mesh_16m"] = p16
+    return out if rank == 0 else None
+
+
+# ------------------------------------------------------------------------------------------
+# extra blocks of the default line: BASELINE.json configs[0], [1], [4]
+# ------------------------------------------------------------------------------------------
+def small_mesh_block(args, dev, freq: int = 32, reps: int = 20):
+    """configs[0] / configs[1] sizes (the reference's own meshes: 10-30 k vertices), one GPU: the SGCN step with the live
+    conv of the reference (ChebConv, util/networks.py:13) and with GCNConv, and the MGCN step (util/meshnet.py mirror on a
+    synthetic 3-level hierarchy), eager and replayed as ONE CUDA graph (the step is launch-bound at this size)."""
+    from semigcn_b200 import losses, meshgen, ops
+    from semigcn_b200.data import Data
+    from semigcn_b200.graphed import GraphedTrainStep
+    from semigcn_b200.meshnet import MGCN
+    from semigcn_b200.networks import SingleScaleGCN
+    from semigcn_b200.nn import MeshPool
+    out = {}
+
+    def timeit(fn):
+        ms, _ = _time_steps(fn, reps, 3, torch.cuda.synchronize)
+        return ms / reps
+
+    prob = make_problem(freq, dev)
+    mesh = prob["mesh"]
+    dm0 = prob["dms"][:, 0:1].contiguous()
+    for conv in ("chebconv", "gcnconv"):
+        torch.manual_seed(314)
+        net = SingleScaleGCN(dev, conv=conv).to(dev)
+        opt = torch.optim.Adam(net.parameters(), lr=0.01, capturable=True)
+        data = Data(z1=prob["z1"], x_pos=prob["x_pos"], edge_index=mesh.edge_index)
+
+        def eager(i):
+            opt.zero_grad(set_to_none=True)
+            loss = step_losses(net(data, prob["dms"][:, i % 8:i % 8 + 1]), prob)
+            loss.backward()
+            opt.step()
+            return loss
+
+        ms_eager = timeit(eager)
+        g = GraphedTrainStep(net, lambda o: step_losses(o, prob), opt, prob["z1"], prob["x_pos"], mesh.edge_index, dm0)
+        ms_graph = timeit(lambda i: g(prob["dms"][:, i % 8:i % 8 + 1]))
+        out[f"sgcn_{conv}"] = {"vertices": mesh.num_vertices, "directed_edges": mesh.nnz, "eager_ms_per_step": ms_eager, "graph_ms_per_step": ms_graph,
+                               "train_steps_per_s": 1e3 / ms_graph, "edges_per_s": float(mesh.nnz) * N_LAYERS / (ms_graph / 1e3),
+                               "kernels_per_step": g.launches_per_replay}
+        del g, net, opt
+    # MGCN: 4 resolutions (N, 0.6 N, 0.36 N, 0.216 N), 33 ChebConv(K=3) layers
+    sp = meshgen.synth_inpainting_problem(freq, device=dev, smooth_iters=10, n_dummy=8)
+    smesh = sp["mesh"]
+    hier = meshgen.synth_pool_hierarchy(smesh)
+    sm, ini, vmask = [sp["x_pos"]], [sp["ini_vs"].float()], [sp["v_mask"]]
+    for lvl in range(3):
+        pool = MeshPool(hier["p_hashes"][lvl]).to(dev)
+        sm.append(pool(sm[-1]))
+        ini.append(pool(ini[-1]))
+        vmask.append(pool(vmask[-1].float().reshape(-1, 1)).reshape(-1) == 1.0)
+    torch.manual_seed(314)
+    net = MGCN(dev, hier["edge_inds"], hier["p_hashes"], hier["up_hashes"], sm, skip=False, drop_rate=0.0, tensor_masks=True).to(dev)
+    opt = torch.optim.Adam(net.parameters(), lr=0.01, capturable=True)
+    pos_w = [0.35, 0.3, 0.2, 0.15]                                                     # mgcn.py:82
+
+    def mgcn_loss(poss):
+        lp = sum(losses.fused_mask_pos_rec_loss(p, t, m) * w for p, t, m, w in zip(poss, ini, vmask, pos_w))
+        _, ln = losses.sgcn_step_losses(poss[0], smesh.faces, sp["ini_vs"], sp["fn"], sp["v_mask"], sp["f_mask"])
+        return lp + K1 * ln
+
+    data = Data(z1=sp["z1"], x_pos=sp["x_pos"])
+    dm = sp["vmask_dummy"][:, :1].contiguous()
+
+    def mgcn_eager(i):
+        opt.zero_grad(set_to_none=True)
+        loss = mgcn_loss(net(data, dm))
+        loss.backward()
+        opt.step()
+        return loss
+
+    ms_eager = timeit(mgcn_eager)
+    g = GraphedTrainStep(net, mgcn_loss, opt, sp["z1"], sp["x_pos"], None, dm)
+    ms_graph = timeit(lambda i: g(dm))
+    nnz_l = [int(e.shape[1]) for e in hier["edge_inds"]]
+    out["mgcn_chebconv"] = {"vertices_per_level": hier["sizes"], "directed_edges_per_level": nnz_l, "conv_layers": 33,
+                            "eager_ms_per_step": ms_eager, "graph_ms_per_step": ms_graph, "train_steps_per_s": 1e3 / ms_graph,
+                            "kernels_per_step": g.launches_per_replay}
+    del g, net, opt
+    ops.clear_graph_cache()
+    torch.cuda.empty_cache()
+    return out
+
+
+def batch64_block(args, rank, world, local_rank, meshes_total: int = 64, freq: int = 100, steps_per_mesh: int = 10, slots: int = 4):
+    """configs[4]: a batch of 64 independent 100 k-vertex meshes, one self-prior network per mesh (sgcn.py:78-80), spread over
+    the N GPUs: rank r trains meshes r, r + N, ...  No data-path collective.  On each GPU ``slots`` meshes train CONCURRENTLY,
+    one CUDA stream each, every step a whole-step CUDA graph (the 100 k-vertex step is launch-bound: DESIGN.md §5.7); when
+    a mesh is done the slot's graph is reused for the next one -- new inputs / targets copied into the static buffers,
+    parameters and optimizer state reset in place.  ``steps_per_mesh`` steps per mesh are timed (a bounded sample of the
+    4 000 steps of a real run).  Aggregate over ranks, max-over-ranks time."""
+    from semigcn_b200 import ops
+    from semigcn_b200.graphed import GraphedTrainStep
+    from semigcn_b200.networks import SingleScaleGCN
+    dev = torch.device(f"cuda:{local_rank}")
+    mine = list(range(rank, meshes_total, world))
+    slots = max(1, min(slots, len(mine)))
+    lanes = []
+    for sidx in range(slots):
+        prob = make_problem(freq, dev, seed=1000 + mine[sidx])
+        torch.manual_seed(314 + mine[sidx])
+        net = SingleScaleGCN(dev, conv=args.conv).to(dev)
+        opt = torch.optim.Adam(net.parameters(), lr=0.01, capturable=True)
+        init = [p.detach().clone() for p in net.parameters()] + [b.detach().clone() for b in net.buffers()]
+        g = GraphedTrainStep(net, (lambda pr: (lambda o: step_losses(o, pr)))(prob), opt, prob["z1"], prob["x_pos"], prob["mesh"].edge_index,
+                             prob["dms"][:, 0:1].contiguous())
+        lanes.append(dict(prob=prob, net=net, opt=opt, init=init, graph=g, stream=torch.cuda.Stream(device=dev), queue=mine[sidx::slots]))
+    nnz = lanes[0]["prob"]["mesh"].nnz
+    nv = lanes[0]["prob"]["mesh"].num_vertices
+    # per-mesh inputs: same topology (icosphere n=100), different geometry noise -> generated up front, copied in when a mesh starts
+    gen = torch.Generator(device=dev)
+
+    def mesh_inputs(mesh_id, prob):
+        gen.manual_seed(1000 + mesh_id)
+        bump = torch.randn(nv, 1, generator=gen, dtype=torch.float64, device=dev)
+        return prob["mesh"].vs * (1.0 + 0.02 * bump)
+
+    def start_mesh(lane, mesh_id):
+        from semigcn_b200 import meshgen
+        pr = lane["prob"]
+        with torch.no_grad():
+            ini = mesh_inputs(mesh_id, pr)
+            smo = meshgen.uniform_laplacian_smooth(ini, pr["mesh"].edge_index, 30)
+            pr["ini"].copy_(ini)
+            pr["fn"].copy_(meshgen.face_normals(ini, pr["mesh"].faces))
+            lane["graph"].z1.copy_((ini - smo).float())
+            lane["graph"].x_pos.copy_(smo.float())
+            for t, v in zip(list(lane["net"].parameters()) + list(lane["net"].buffers()), lane["init"]):
+                t.copy_(v)
+            for st in lane["opt"].state.values():
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+
+    def run_all():
+        cur = torch.cuda.current_stream(dev)
+        for lane in lanes:
+            lane["stream"].wait_stream(cur)
+        rounds = max(len(l["queue"]) for l in lanes)
+        for rnd in range(rounds):
+            for lane in lanes:
+                if rnd < len(lane["queue"]):
+                    with torch.cuda.stream(lane["stream"]):
+                        start_mesh(lane, lane["queue"][rnd])
+            for i in range(steps_per_mesh):
+                for lane in lanes:
+                    if rnd < len(lane["queue"]):
+                        with torch.cuda.stream(lane["stream"]):
+                            lane["graph"](lane["prob"]["dms"][:, i % 8:i % 8 + 1])
+        for lane in lanes:
+            cur.wait_stream(lane["stream"])
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for lane in lanes:                       # warm-up: one mesh start + two steps per lane
+        with torch.cuda.stream(lane["stream"]):
+            start_mesh(lane, lane["queue"][0])
+            lane["graph"](lane["prob"]["dms"][:, 0:1])
+            lane["graph"](lane["prob"]["dms"][:, 1:2])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_all()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = sum(l["graph"].launches_per_replay for l in lanes[:1]) * steps_per_mesh * len(mine)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t[0])
+    del lanes
+    ops.clear_graph_cache()
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    total_steps = meshes_total * steps_per_mesh
+    return {"meshes": meshes_total, "vertices_per_mesh": nv, "directed_edges_per_mesh": nnz, "n_gpus": world, "meshes_per_gpu": len(mine),
+            "concurrent_meshes_per_gpu": slots, "steps_per_mesh_timed": steps_per_mesh, "ms_total": ms, "train_steps_per_s": total_steps / (ms / 1e3),
+            "edges_per_s": float(nnz) * N_LAYERS * total_steps / (ms / 1e3), "ms_per_step_per_gpu": ms / (len(mine) * steps_per_mesh),
+            "gpu_launches_rank0": launches, "collectives": "none (independent meshes)",
+            "includes": "per mesh: geometry + 30 smoothing iterations + target normals on the GPU, in-place reset of parameters / Adam state, "
+                        f"then {steps_per_mesh} whole-step CUDA-graph replays (forward + both step losses + backward + Adam)"}
 
 
 def main():
@@ -568,6 +872,30 @@ def main():
         os.environ.setdefault("WORLD_SIZE", "1")
         torch.distributed.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     line = (run_partition if args.mode == "partition" else run_ours)(args, rank, world, local_rank)
+    if args.mode == "replicas" and not args.no_extras and not args.cuda_graph:
+        # extra blocks (every rank takes part; rank 0 holds the results).  They must never cost the bench line.
+        from semigcn_b200 import ops
+        ops.clear_graph_cache()
+        torch.cuda.empty_cache()
+        extras = {}
+
+        def guarded(name, fn):
+            try:
+                r = fn()
+                if r is not None:
+                    extras[name] = r
+            except Exception as exc:   # noqa: BLE001
+                extras[name] = {"error": repr(exc)[:400]}
+                ops.clear_graph_cache()
+                torch.cuda.empty_cache()
+
+        if world > 1:
+            guarded("partition", lambda: partition_block(args, rank, world, local_rank))
+        guarded("batch64", lambda: batch64_block(args, rank, world, local_rank))
+        if world == 1:
+            guarded("small_meshes", lambda: small_mesh_block(args, torch.device(f"cuda:{local_rank}")))
+        if line is not None:
+            line.update(extras)
     if line is not None:
         print(json.dumps(line), flush=True)
     if dist_on:

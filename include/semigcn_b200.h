@@ -127,6 +127,15 @@ SGB_API int sgb_spmm_halo(const int32_t* rowptr, const sgb_edge_t* edges, const 
                   const float* in_mean, const float* in_scale, const float* in_shift, float slope,
                   float alpha, const float* addend, int64_t ld_addend, float beta,
                   const float* bias, float* y, int64_t ldy, float* stat_partials, float* amax_out, void* stream);
+/* Rows [row_begin, row_begin + n) of the same operator (all pointers are the whole-matrix ones; y / addend / x are addressed
+ * by absolute row).  With the owned vertices numbered interior-first, the rows without ghost columns run as one launch
+ * (x_ghost = NULL) WHILE the halo all-to-all of the boundary rows is in flight, the boundary rows as a second launch after
+ * it: the exchange hides behind the interior aggregation.  stat_partials: sgb_spmm_stat_rows(n, c) rows PER LAUNCH. */
+SGB_API int sgb_spmm_range(const int32_t* rowptr, const sgb_edge_t* edges, const float* dis, int mode,
+                   const float* x, int64_t ldx, int64_t row_begin, int64_t n, int c, const float* x_ghost, int64_t ld_ghost, int64_t n_split,
+                   const float* in_mean, const float* in_scale, const float* in_shift, float slope,
+                   float alpha, const float* addend, int64_t ld_addend, float beta,
+                   const float* bias, float* y, int64_t ldy, float* stat_partials, float* amax_out, void* stream);
 /* out[k, :] = x[idx[k], :] (halo pack; also MeshUnpool-style row gathers), c floats per row */
 SGB_API int sgb_gather_rows(const float* x, int64_t ldx, const int32_t* idx, int64_t count, int c, float* out, int64_t ldo, void* stream);
 

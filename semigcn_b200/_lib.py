@@ -35,6 +35,8 @@ SIGNATURES = {
                         _vp, _vp, _i64, _vp, _vp, _vp]),
     "sgb_spmm_halo": (_i32, [_vp, _vp, _vp, _i32, _vp, _i64, _i64, _i32, _vp, _i64, _i64, _vp, _vp, _vp, _f32, _f32, _vp, _i64, _f32,
                              _vp, _vp, _i64, _vp, _vp, _vp]),
+    "sgb_spmm_range": (_i32, [_vp, _vp, _vp, _i32, _vp, _i64, _i64, _i64, _i32, _vp, _i64, _i64, _vp, _vp, _vp, _f32, _f32, _vp, _i64, _f32,
+                              _vp, _vp, _i64, _vp, _vp, _vp]),
     "sgb_gather_rows": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
     "sgb_gemm_stat_rows": (_i32, [_i64]),
     "sgb_gemm_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),

@@ -79,6 +79,7 @@ struct SpmmArgs {
     int64_t ldxg;
     int32_t split;                    // INT32_MAX when there are no ghost rows
     float* amax;                      // optional: max |y| (atomicMax on the float bits; caller zeroes it)
+    int64_t row0;                     // first row of the range this launch computes (rows row0 .. row0 + n - 1 of the operator)
 };
 
 // A warp owns "runs" of VPW consecutive vertices; run r of the grid goes to warp (r mod total warps), so the
@@ -155,15 +156,15 @@ __global__ void __launch_bounds__(kSpmmThreads, (VEC * ITERS >= 8) ? (STATS ? SG
 
     auto stage_rowptr = [&](int64_t ri, int buf) {         // async; ri (schedule position) may be past the end
         if (ri < rcount) {
-            const int64_t v0 = (gw + ri * tw) * VPW;
-            const int nv = (int)min64(VPW, a.n - v0);
+            const int64_t v0 = a.row0 + (gw + ri * tw) * VPW;
+            const int nv = (int)min64(VPW, a.row0 + a.n - v0);
             for (int i = lane; i <= nv; i += 32) cp_async4(&w_rp[buf * (VPW + 2) + i], a.rowptr + v0 + i);
         }
     };
     auto stage_edges = [&](int64_t ri, int buf) {          // needs the row pointers of that run to be visible
         if (ri < rcount) {
-            const int64_t v0 = (gw + ri * tw) * VPW;
-            const int nv = (int)min64(VPW, a.n - v0);
+            const int64_t v0 = a.row0 + (gw + ri * tw) * VPW;
+            const int nv = (int)min64(VPW, a.row0 + a.n - v0);
             const int e0 = w_rp[buf * (VPW + 2)], ne = w_rp[buf * (VPW + 2) + nv] - e0;
             if (ne <= ECAP)
                 for (int i = lane; i < ne; i += 32) cp_async8(&w_edge[buf * EBUF + i], a.edges + e0 + i);
@@ -210,8 +211,8 @@ __global__ void __launch_bounds__(kSpmmThreads, (VEC * ITERS >= 8) ? (STATS ? SG
             cp_async_commit_wait_all();
             __syncwarp();                                     // this run's edges + next run's row pointers have landed
             stage_edges(ri + 1, buf ^ 1);
-            const int64_t v0 = (gw + ri * tw) * VPW;
-            const int nv = (int)min64(VPW, a.n - v0);
+            const int64_t v0 = a.row0 + (gw + ri * tw) * VPW;
+            const int nv = (int)min64(VPW, a.row0 + a.n - v0);
             const int* srp = w_rp + buf * (VPW + 2);
             const int e0 = srp[0];
             const bool staged = (srp[nv] - e0) <= ECAP;
@@ -439,6 +440,15 @@ extern "C" int sgb_spmm_halo(const int32_t* rowptr, const sgb_edge_t* edges, con
                              const float* in_mean, const float* in_scale, const float* in_shift, float slope,
                              float alpha, const float* addend, int64_t ld_addend, float beta,
                              const float* bias, float* y, int64_t ldy, float* stat_partials, float* amax_out, void* stream_) {
+    return sgb_spmm_range(rowptr, edges, dis, mode, x, ldx, 0, n, c, x_ghost, ld_ghost, n_split, in_mean, in_scale, in_shift, slope, alpha, addend,
+                          ld_addend, beta, bias, y, ldy, stat_partials, amax_out, stream_);
+}
+
+extern "C" int sgb_spmm_range(const int32_t* rowptr, const sgb_edge_t* edges, const float* dis, int mode,
+                              const float* x, int64_t ldx, int64_t row_begin, int64_t n, int c, const float* x_ghost, int64_t ld_ghost, int64_t n_split,
+                              const float* in_mean, const float* in_scale, const float* in_shift, float slope,
+                              float alpha, const float* addend, int64_t ld_addend, float beta,
+                              const float* bias, float* y, int64_t ldy, float* stat_partials, float* amax_out, void* stream_) {
     using namespace sgb;
     cudaStream_t stream = (cudaStream_t)stream_;
     SGB_CHECK_ARG(n >= 0 && c > 0, "sgb_spmm: bad shape n=%lld c=%d", (long long)n, c);
@@ -449,7 +459,8 @@ extern "C" int sgb_spmm_halo(const int32_t* rowptr, const sgb_edge_t* edges, con
     SGB_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr) && (in_scale == nullptr) == (in_mean == nullptr),
                   "sgb_spmm: in_mean / in_scale / in_shift must come together");
     SGB_CHECK_ARG(x != y, "sgb_spmm: in-place aggregation is not supported");
-    SGB_CHECK_ARG(ldx < (int64_t)1 << 30 && ld_ghost < (int64_t)1 << 30 && n < (int64_t)0x7fffffff, "sgb_spmm: row stride / vertex count out of range");
+    SGB_CHECK_ARG(row_begin >= 0 && ldx < (int64_t)1 << 30 && ld_ghost < (int64_t)1 << 30 && row_begin + n < (int64_t)0x7fffffff,
+                  "sgb_spmm: row stride / vertex count out of range");
     SGB_CHECK_ARG(!x_ghost || (ld_ghost >= c && n_split >= 0 && n_split < (int64_t)0x7fffffff), "sgb_spmm_halo: bad ghost block");
     if (n == 0) return SGB_OK;
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
@@ -466,7 +477,7 @@ extern "C" int sgb_spmm_halo(const int32_t* rowptr, const sgb_edge_t* edges, con
     const bool pro = in_scale != nullptr, st = stat_partials != nullptr, halo = x_ghost != nullptr;
     if (!pro) slope = 1.f;            // the general instantiation applies lrelu((x - 0) * 1 + 0, slope): identity
     SpmmArgs a{rowptr, reinterpret_cast<const int2*>(edges), dis, mode, x, ldx, n, c, in_mean, in_scale, in_shift, slope, alpha, addend, ld_addend, beta, bias, y, ldy, stat_partials,
-               x_ghost, ld_ghost, x_ghost ? (int32_t)n_split : (int32_t)0x7fffffff, amax_out};
+               x_ghost, ld_ghost, x_ghost ? (int32_t)n_split : (int32_t)0x7fffffff, amax_out, row_begin};
     // the BatchNorm prologue and ragged widths are rare operands: they share one (slower, fully general) instantiation
 #define SGB_SPMM_CASE(L, V, I)                                                                                  \
     if (k.lpv == L && k.vec == V && k.iters == I) {                                                             \

@@ -99,12 +99,22 @@ _DUMMY_P = [0.014, 0.014, 0.014, 0.014, 0.014, 0.014, 0.014, 0.0014, 0.014]     
 def dilate_mask(edge_index: torch.Tensor, seeds: torch.Tensor, rings: int) -> torch.Tensor:
     """``rings`` times ``M <- (AdjI @ M > 0)`` (util/datamaker.py:127-129) on the sparse ``edge_index`` [2, 2E] instead of
     the reference's dense-built ``mesh.AdjI`` (util/mesh.py:271-272): a vertex is marked when it or a neighbour is.
-    ``seeds`` [N, D] float (0 / 1); returns the same shape.  Plain torch ops on the tensors' device; the sums are small
-    non-negative integers, exact in float32, so ``> 0`` is the boolean semiring."""
-    row, col = edge_index[0], edge_index[1]
-    m = seeds.to(torch.float32)
+    ``seeds`` [N, D] float (0 / 1); returns the same shape.
+
+    Each ring is ONE launch of the aggregation kernel in ``SGB_MODE_ADJ`` (plain adjacency sum, weights 1) with the
+    identity folded into its epilogue (``A m + m``: alpha = 1, addend = m, beta = 1), then a threshold -- the boolean
+    semiring: the sums are small non-negative integers, exact in float32, so ``> 0`` is OR.  The CSR is the cached one of
+    this ``edge_index`` (shared with ``mesh_laplacian_loss``).  CUDA tensors only, like every op that has a kernel; the
+    CPU restatement the tests pin against the reference's own masks lives in oracle/mask_ref.py."""
+    from . import ops
+    from ._lib import MODE_ADJ, require_cuda
+    require_cuda(edge_index, seeds)
+    m = seeds.to(torch.float32).contiguous()
+    if int(rings) <= 0:
+        return m.clone()
+    g = ops.graph_for(edge_index, int(m.shape[0]), MODE_ADJ)
     for _ in range(int(rings)):
-        m = ((torch.zeros_like(m).index_add_(0, col, m[row]) + m) > 0).to(torch.float32)
+        m = (ops.spmm(g, m, addend=m, beta=1.0) > 0).to(torch.float32)
     return m
 
 
@@ -123,7 +133,8 @@ def make_dummy_mask(edge_index: torch.Tensor, faces: torch.Tensor, num_vertices:
     """util/datamaker.py:110-136 (without the .ply dumps): for each ring count k in ``kn``, ``dm_size`` Bernoulli(p_k) seed
     sets grown k rings; ``vmask`` [N, dm_size * len(kn)] is 1 outside the fake holes, ``fmask`` the matching face masks.
     The seeds are drawn with ``np.random.binomial`` in the reference's order, so the reference's ``np.random.seed`` gives
-    the reference's masks (``rng``: a ``numpy.random.RandomState``-like object; default the global numpy state)."""
+    the reference's masks (``rng``: a ``numpy.random.RandomState``-like object; default the global numpy state).
+    ``edge_index`` lives on the GPU: the dilation runs on the aggregation kernel (``dilate_mask``)."""
     import numpy as np
     rng = np.random if rng is None else rng
     dev = edge_index.device

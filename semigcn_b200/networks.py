@@ -46,6 +46,7 @@ class SingleScaleGCN(nn.Module):
 
     def forward(self, data, dm=None):
         z1, x_pos, edge_index = data.z1.to(self.device), data.x_pos.to(self.device), data.edge_index.to(self.device)
+        prep = _prof.span("input_prep", 4.0 * 11 * z1.shape[0]) if _prof.ACTIVE is not None else None
         z_min, z_max = torch.min(z1, dim=0, keepdim=True)[0], torch.max(z1, dim=0, keepdim=True)[0]
         if self.comm is not None:           # bounding box of the WHOLE mesh (util/networks.py:67-68)
             z_min, z_max = self.comm.all_reduce_min(z_min.clone()), self.comm.all_reduce_max(z_max.clone())
@@ -59,6 +60,8 @@ class SingleScaleGCN(nn.Module):
         dm = dm.to(self.device)
         z1 = dm * z1
         x = torch.cat([z1, dm], dim=1)
+        if prep is not None:
+            prep.close()
         skip_in = []
         nblk = len(self.blocks)
         for i, b in enumerate(self.blocks):

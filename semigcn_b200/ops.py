@@ -201,28 +201,39 @@ def spmm(g: MeshGraph, x: Tensor, transpose: bool = False, in_affine: Affine = N
     if n != g.n:
         raise SgbError(f"x has {n} rows but the graph has {g.n} vertices")
     y = out if out is not None else torch.empty((n, c), dtype=torch.float32, device=x.device)
-    # partitioned mode: fetch the halo rows of x from their owners (gather -> all-to-all), then gather locally
-    xg = g.halo.exchange(x) if g.halo is not None else None
     if addend is not None:
         addend = _f32c(addend, "addend")
-    partials = None
-    if want_stats:
-        rows = lib.sgb_spmm_stat_rows(n, c)
-        partials = torch.empty((rows, 3, c), dtype=torch.float32, device=x.device)
     rowptr, edges = g.csr(transpose)
     mu, sc, sh, slope = (in_affine if in_affine is not None else (None, None, None, 0.0))
     nnz_eff = int(g.nnz) + (n if g.mode == MODE_GCN else 0)
     sp = _prof.span(f"spmm_c{c}", 4.0 * (2 * n * c + nnz_eff + 2 * n + 1 + (n * c if addend is not None else 0)),
                     2.0 * nnz_eff * c) if _prof.ACTIVE is not None else None
+    # Vertex-partitioned mode: the ghost rows of x come from their owners (pack -> all-to-all).  With the owned vertices
+    # numbered interior-first, the rows that touch no ghost are aggregated WHILE the exchange is in flight (the collective
+    # runs on the communicator's stream), the boundary rows after it: two launches over disjoint row ranges of one operator.
+    n_int = int(getattr(g, "n_interior", 0)) if g.halo is not None else 0
+    ranges = [(0, n, True)] if not (0 < n_int < n) else [(0, n_int, False), (n_int, n - n_int, True)]
+    pending = g.halo.start(x) if g.halo is not None else None
+    partials, row_off = None, 0
+    if want_stats:
+        rows = sum(lib.sgb_spmm_stat_rows(cnt, c) for (_, cnt, _) in ranges)
+        partials = torch.empty((rows, 3, c), dtype=torch.float32, device=x.device)
+    xg = None
     with torch.cuda.device(x.device):
-        check(lib.sgb_spmm_halo(ptr(rowptr), ptr(edges), ptr(g.dis), g.mode, ptr(x), x.stride(0), n, c,
-                                ptr(xg), xg.stride(0) if xg is not None else 0, n,
-                                ptr(mu), ptr(sc), ptr(sh), float(slope), float(alpha), ptr(addend),
-                                addend.stride(0) if addend is not None else 0, float(beta), ptr(bias),
-                                ptr(y), y.stride(0), ptr(partials), ptr(amax_out), stream_ptr(x.device)), "sgb_spmm")
+        for (r0, cnt, needs_ghosts) in ranges:
+            if needs_ghosts and pending is not None:
+                xg = g.halo.finish(pending)
+            part = partials[row_off:] if partials is not None else None
+            check(lib.sgb_spmm_range(ptr(rowptr), ptr(edges), ptr(g.dis), g.mode, ptr(x), x.stride(0), r0, cnt, c,
+                                     ptr(xg) if needs_ghosts else None, xg.stride(0) if (needs_ghosts and xg is not None) else 0, n,
+                                     ptr(mu), ptr(sc), ptr(sh), float(slope), float(alpha), ptr(addend),
+                                     addend.stride(0) if addend is not None else 0, float(beta), ptr(bias),
+                                     ptr(y), y.stride(0), ptr(part), ptr(amax_out), stream_ptr(x.device)), "sgb_spmm")
+            if partials is not None:
+                row_off += lib.sgb_spmm_stat_rows(cnt, c)
+            L.count(1)
     if sp is not None:
         sp.close()
-    L.count(1)
     return (y, partials) if want_stats else y
 
 

@@ -122,3 +122,51 @@ def build_plan(edge_index: Tensor, n: int, rank: int, world: int,
         send_counts.append(int(mine.numel()))
     send_idx = (torch.cat(send_parts) if send_parts else torch.zeros(0, dtype=torch.int64, device=edge_index.device)).to(torch.int32)
     return PartitionPlan(rank, world, int(n), lo, hi, ghosts, send_idx, send_counts, [int(c) for c in recv_counts], ei_local)
+
+
+def interior_first_order(edge_index: Tensor, n: int, ranges: Sequence[Tuple[int, int]]) -> Tensor:
+    """Permutation ``perm`` (new id -> old id) that keeps every rank's vertex RANGE but lists, inside it, the interior
+    vertices (all neighbours owned by the same rank) before the boundary ones (at least one neighbour on another rank),
+    each group in its previous order.  Rows [0, n_interior) of a rank's operator then have no ghost columns: their
+    aggregation can run while the halo exchange of the boundary rows is still in flight (dist.PartitionedGraph)."""
+    dev = edge_index.device
+    bounds = torch.tensor([lo for (lo, _) in ranges] + [ranges[-1][1]], dtype=torch.int64, device=dev)
+    owner = torch.searchsorted(bounds, torch.arange(n, device=dev), right=True) - 1
+    row, col = edge_index[0], edge_index[1]
+    cross = owner[row] != owner[col]
+    boundary = torch.zeros(n, dtype=torch.bool, device=dev)
+    boundary[row[cross]] = True
+    boundary[col[cross]] = True
+    key = owner * 2 + boundary.to(torch.int64)              # (rank, interior < boundary), stable inside
+    return torch.argsort(key, stable=True)
+
+
+def count_interior(edge_index_local: Tensor, n_own: int) -> int:
+    """Number of leading owned rows of a plan's local ``edge_index`` that touch no ghost (valid as a split point when the
+    numbering came from ``interior_first_order``: the first boundary vertex ends the interior block)."""
+    src, dst = edge_index_local[0], edge_index_local[1]
+    touched = torch.zeros(n_own + 1, dtype=torch.bool, device=src.device)
+    ghost_src = src >= n_own
+    touched[dst[ghost_src].clamp(max=n_own)] = True          # owned target with a ghost source
+    ghost_dst = dst >= n_own
+    touched[src[ghost_dst].clamp(max=n_own)] = True          # owned source with a ghost target (transpose operator)
+    first = torch.nonzero(touched[:n_own])
+    return int(first[0]) if first.numel() else n_own
+
+
+def local_faces(plan: "PartitionPlan", faces: Tensor) -> Tuple[Tensor, Tensor]:
+    """Faces this rank accounts for in a face-wise loss: those whose FIRST vertex it owns (every face is counted by exactly
+    one rank).  The other two vertices are neighbours of the first, hence owned or in the rank's ghost set.  Returns
+    (global face ids [F_r], faces in LOCAL vertex ids [F_r, 3])."""
+    lo, hi, n_own = plan.lo, plan.hi, plan.n_own
+    mine = (faces[:, 0] >= lo) & (faces[:, 0] < hi)
+    fid = torch.nonzero(mine).reshape(-1)
+    f = faces[fid]
+    owned = (f >= lo) & (f < hi)
+    gpos = torch.searchsorted(plan.ghost_gid, f.reshape(-1).clamp(min=0)).reshape(f.shape)
+    gpos = gpos.clamp(max=max(plan.n_ghost - 1, 0))
+    if plan.n_ghost:
+        ok = owned | (plan.ghost_gid[gpos] == f)
+        if not bool(ok.all()):
+            raise ValueError("local_faces: a face vertex is neither owned nor a ghost of this rank")
+    return fid, torch.where(owned, f - lo, n_own + gpos).contiguous()

@@ -24,7 +24,7 @@ def _rel(a, b):
     return (a.double() - b.double()).abs().max().item() / max(b.double().abs().max().item(), 1e-30)
 
 
-def _worker(rank, world, port, conv, slope=0.01, ranges=None):
+def _worker(rank, world, port, conv, slope=0.01, ranges=None, order="given", with_normals=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     import torch.distributed as dist
@@ -43,6 +43,20 @@ def _worker(rank, world, port, conv, slope=0.01, ranges=None):
         ei = mesh.edge_index.to(dev)
         z1, x_pos, dm = prob["z1"].to(dev), prob["x_pos"].to(dev), prob["vmask_dummy"][:, :1].to(dev)
         target, vmask = prob["ini_vs"].to(dev), prob["v_mask"].to(dev)
+        faces, fn_t, fmask = mesh.faces.to(dev), prob["fn"].to(dev), prob["f_mask"].to(dev)
+        if order == "interior":
+            # Morton patches, then interior vertices before boundary ones inside every rank's range: the interior rows are
+            # aggregated while the halo all-to-all is in flight (two launches per propagation, ops.spmm)
+            perm = partition.morton_order(mesh.vs.to(dev))
+            ei, z1, x_pos, dm, target, vmask = partition.renumber(perm, ei, z1, x_pos, dm, target, vmask)
+            inv = torch.empty_like(perm)
+            inv[perm] = torch.arange(n, device=dev)
+            perm2 = partition.interior_first_order(ei, n, ranges or partition.vertex_ranges(n, world))
+            ei, z1, x_pos, dm, target, vmask = partition.renumber(perm2, ei, z1, x_pos, dm, target, vmask)
+            inv2 = torch.empty_like(perm2)
+            inv2[perm2] = torch.arange(n, device=dev)
+            faces = inv2[inv[faces]]
+            ei = ei.contiguous()
         torch.manual_seed(314)
         net = SingleScaleGCN(dev, conv=conv).to(dev)
         for mod in net.modules():
@@ -51,6 +65,8 @@ def _worker(rank, world, port, conv, slope=0.01, ranges=None):
         # ---- unpartitioned reference on this process
         out_ref = net(Data(z1=z1, x_pos=x_pos, edge_index=ei), dm)
         loss_ref = losses.mask_pos_rec_loss(out_ref, target, vmask)
+        if with_normals:      # the full step loss of sgcn.py:130-137
+            loss_ref = loss_ref + 4.0 * losses.mask_norm_rec_loss(losses.compute_fn(out_ref, faces), fn_t, fmask)
         loss_ref.backward()
         grads_ref = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
         net.zero_grad(set_to_none=True)
@@ -61,6 +77,15 @@ def _worker(rank, world, port, conv, slope=0.01, ranges=None):
         lo, hi = plan.lo, plan.hi
         out = net(Data(z1=z1[lo:hi].contiguous(), x_pos=x_pos[lo:hi].contiguous(), edge_index=ei_local), dm[lo:hi].contiguous())
         loss = dist_mask_pos_rec_loss(out, target[lo:hi], vmask[lo:hi], comm)
+        if with_normals:
+            from semigcn_b200.dist import dist_mask_norm_rec_loss
+            from semigcn_b200 import ops
+            from semigcn_b200._lib import MODE_GCN, MODE_CHEB
+            g_part = ops.graph_for(ei_local, hi - lo, MODE_GCN if conv == "gcnconv" else MODE_CHEB)
+            fid, f_loc = partition.local_faces(plan, faces)
+            loss = loss + 4.0 * dist_mask_norm_rec_loss(out, g_part.halo, f_loc, fn_t[fid], fmask[fid], comm)
+            if order == "interior":
+                assert 0 < g_part.n_interior < hi - lo
         loss.backward()
         sync_gradients(net, comm)
         torch.cuda.synchronize()
@@ -120,3 +145,11 @@ def test_partitioned_sgcn_uneven_ranges(world, ranges):
     """Uneven vertex ranges straddling the 128-row tile boundary: the ranks' kernels produce different numbers of
     BatchNorm partial rows; SyncBN gathers ONE merged row per rank, so the payload is rank-invariant."""
     mp.spawn(_worker, args=(world, _free_port(), "gcnconv", 0.01, ranges), nprocs=world, join=True)
+
+
+@pytest.mark.parametrize("conv", ["gcnconv", "chebconv"])
+def test_partitioned_sgcn_overlapped_halo_and_normal_loss(conv):
+    """Interior-first numbering (interior rows aggregated while the halo all-to-all is in flight: two launches per
+    propagation over disjoint row ranges) + the face-normal loss across the cuts (ghost positions through the exchange,
+    their gradients back through the reverse exchange): the partitioned step equals the single-GPU step of sgcn.py:129-143."""
+    mp.spawn(_worker, args=(3, _free_port(), conv, 1.0, None, "interior", True), nprocs=3, join=True)

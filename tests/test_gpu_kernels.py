@@ -380,3 +380,34 @@ def test_bn_near_constant_channels():
     e_ours, e_t32 = rel_err(z, zr), rel_err(z32, zr)
     assert e_ours <= max(2.0 * e_t32, 1e-5), f"ours {e_ours:.2e} vs torch-fp32 {e_t32:.2e}"
     assert_close(bn.running_var, bn_ref.running_var, 1e-4, "running_var")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# mask generation on the aggregation kernel, boolean semiring
+# ------------------------------------------------------------------------------------------------------------------
+def test_mask_dilation_on_the_spmm_kernel():
+    """semigcn_b200.data.make_dummy_mask / dilate_mask / vmask_to_fmask on the GPU (k-ring dilation = SpMM in SGB_MODE_ADJ
+    with the identity in the epilogue, then > 0) against the masks the REFERENCE's own util/datamaker.py:110-159 produced
+    under its numpy seed (tests/golden/make_golden_masks.py): bit-identical."""
+    import numpy as np
+    from oracle import mask_ref
+    from semigcn_b200 import SgbError, data as sdata, meshgen
+    gold = load_golden("ref_masks_n4.npz")
+    ei = torch.from_numpy(gold["edge_index"]).to(DEV)
+    faces = torch.from_numpy(gold["faces"]).long().to(DEV)
+    n = int(ei.max()) + 1
+    rng = np.random.RandomState(int(gold["seed"]))
+    vmask, fmask = sdata.make_dummy_mask(ei, faces, n, dm_size=int(gold["dm_size"]), kn=[int(k) for k in gold["kn"]], rng=rng)
+    assert torch.equal(vmask.cpu(), torch.from_numpy(gold["vmask_dummy"]))
+    assert torch.equal(fmask.cpu(), torch.from_numpy(gold["fmask_dummy"]))
+    f_real = sdata.vmask_to_fmask(faces, torch.from_numpy(gold["v_real"]).to(DEV))
+    assert f_real.dtype == torch.bool and torch.equal(f_real.cpu(), torch.from_numpy(gold["f_real"]))
+    # a larger mesh, the reference's default sizes (40 masks per ring count, 3 / 4 / 5 rings), against the CPU restatement
+    m = meshgen.icosphere(20)
+    g = torch.Generator().manual_seed(3)
+    seeds = (torch.rand(m.num_vertices, 40, generator=g) < 0.014).float()
+    for rings in (0, 1, 4):
+        got = sdata.dilate_mask(m.edge_index.to(DEV), seeds.to(DEV), rings)
+        assert torch.equal(got.cpu(), mask_ref.dilate_mask(m.edge_index, seeds, rings)), rings
+    with pytest.raises(SgbError):
+        sdata.dilate_mask(m.edge_index, seeds, 1)              # CPU tensors are refused: no fallback

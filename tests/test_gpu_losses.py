@@ -117,3 +117,60 @@ def test_laplacian_loss_gradient_vs_oracle():
     l.backward()
     assert abs(l.item() - l_ref.item()) <= 2e-6 * abs(l_ref.item())
     assert rel_err(p.grad, p_ref.grad) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fused bilateral-normal-filter regulariser (csrc/bnf_loss.cu) -- SURVEY.md §8(f)-1
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [4, 8])
+def test_bnf_loss_matches_reference_golden(n):
+    """Loss and filtered normals the reference's own Loss.fn_bnf_detach_loss (util/loss.py:197-253) produced on its own
+    Mesh.f2f (tests/golden/make_golden.py), numpy faces / f2f as sgcn.py:134 passes them."""
+    L = _losses()
+    gold = load_golden(n)
+    pred = torch.from_numpy(gold["pred"]).to(DEV)
+    fn_pred = torch.from_numpy(gold["compute_fn_f32"]).to(DEV)
+    loss, new_fn = L.fn_bnf_detach_loss(pred, fn_pred, gold["faces"], gold["f2f"], loop=5)
+    assert loss.dtype == torch.float32 and new_fn.shape == fn_pred.shape
+    assert torch.allclose(new_fn.cpu(), torch.from_numpy(gold["bnf_fn_f32"]), rtol=0, atol=1e-6)
+    assert abs(loss.item() - float(gold["loss_bnf_f32"])) <= 1e-6 * abs(float(gold["loss_bnf_f32"]))
+    # compute_fn through our own fused kernel feeds it too (what the step does: sgcn.py:130,134)
+    loss2, _ = L.fn_bnf_detach_loss(pred, L.compute_fn(pred, torch.from_numpy(gold["faces"]).long().to(DEV)), gold["faces"], gold["f2f"])
+    assert abs(loss2.item() - loss.item()) <= 1e-6 * abs(loss.item())
+
+
+@pytest.mark.parametrize("ltype", ["mae", "l1mae", "rmse", "l1rmse"])
+@pytest.mark.parametrize("loop", [0, 1, 5])
+def test_bnf_loss_all_types_and_gradient_vs_oracle(ltype, loop):
+    """Every ltype / loop count against the pinned CPU restatement (oracle/loss_ref.py), forward and the gradient with
+    respect to fn, on a mesh WITH a boundary (f2f == -1 slots: the reference's wrap-around indexing of the last face)."""
+    from oracle import loss_ref
+    from semigcn_b200 import meshgen
+    L = _losses()
+    gold = load_golden(8)
+    faces = torch.from_numpy(gold["faces"]).long()
+    keep = torch.ones(faces.shape[0], dtype=torch.bool)
+    keep[::7] = False
+    faces = faces[keep].contiguous()
+    f2f = meshgen.face_adjacency(faces)
+    assert int((f2f == -1).sum()) > 0
+    pred = torch.from_numpy(gold["pred"])
+    fn0 = O.compute_fn(pred, faces)
+    g = torch.Generator().manual_seed(5)
+    fn_in = (fn0 + 0.05 * torch.randn(fn0.shape, generator=g)).requires_grad_(True)      # generic input, not unit length
+    loss_r, new_r = loss_ref.fn_bnf_detach_loss(pred, fn_in, faces, f2f, ltype=ltype, loop=loop)
+    loss_r.backward()
+    fn_dev = fn_in.detach().to(DEV).requires_grad_(True)
+    loss, new_fn = L.fn_bnf_detach_loss(pred.to(DEV), fn_dev, faces.to(DEV), f2f.to(DEV), ltype=ltype, loop=loop)
+    (3.0 * loss).backward()
+    assert abs(loss.item() - loss_r.item()) <= 2e-6 * abs(loss_r.item()), (loss.item(), loss_r.item())
+    assert torch.allclose(new_fn.cpu(), new_r, rtol=0, atol=2e-6)
+    assert not new_fn.requires_grad
+    assert rel_err(fn_dev.grad, 3.0 * fn_in.grad) <= 1e-5
+
+
+def test_bnf_loss_refuses_cpu_tensors():
+    from semigcn_b200 import SgbError
+    gold = load_golden(4)
+    with pytest.raises(SgbError):
+        _losses().fn_bnf_detach_loss(torch.from_numpy(gold["pred"]), torch.from_numpy(gold["compute_fn_f32"]), gold["faces"], gold["f2f"])

@@ -246,11 +246,12 @@ def test_fn_bnf_detach_loss_matches_reference(n):
 
 
 def test_dummy_masks_match_reference_datamaker():
-    """semigcn_b200.data.make_dummy_mask / vmask_to_fmask / dilate_mask (sparse edge_index, no dense AdjI) against the
+    """The CPU restatement of the mask generation (oracle/mask_ref.py: sparse edge_index, no dense AdjI) against the
     reference's own util/datamaker.py:110-159 run on its dense-built AdjI / f2v_mat (tests/golden/make_golden_masks.py):
-    identical masks under the reference's numpy seed."""
+    identical masks under the reference's numpy seed.  (The product's dilation runs on the aggregation kernel and is held
+    to the same fixture on the GPU: tests/test_gpu_kernels.py::test_mask_dilation_on_the_spmm_kernel.)"""
     import numpy as np
-    from semigcn_b200 import data as sdata
+    from oracle import mask_ref as sdata
     gold = load_golden("ref_masks_n4.npz")
     ei = torch.from_numpy(gold["edge_index"])
     faces = torch.from_numpy(gold["faces"]).long()
