@@ -213,13 +213,14 @@ def test_sgcn_forward_backward_vs_oracle(conv, skip):
 
 def test_sgcn_training_100_steps_tracks_oracle():
     """BASELINE.json asks for a final vertex error <= 1e-4 of the bounding-box diagonal after 100
-    steps.  That bar is not attainable by ANY pair of fp32 implementations: the training dynamics
-    of this 13-block BatchNorm network are chaotic -- the CPU oracle diverges from its own fp64
-    evaluation by ~8e-2 of the diagonal after 100 Adam steps and by ~6e-4 after ONE step, and a
-    1e-7 relative weight perturbation does the same (DESIGN.md "Parity", measured).  What can be
-    demanded, and is: after 100 identical-schedule steps our trajectory is no further from the fp64
-    oracle than a small multiple of the fp32 oracle's own distance, the training loss has dropped
-    alike, and the first step (before chaos sets in) agrees tightly."""
+    steps.  MEASURED (tools/measure_training_divergence.py -> profiles/r2_training_divergence.json,
+    oracle only, no product code): the fp32 CPU oracle is 5.6e-4 of the diagonal away
+    from its own fp64 evaluation after ONE Adam step and 7.9e-2 after 100, and a 1-ulp perturbation of
+    the initial weights does the same -- so that bar cannot be met by any pair of fp32 implementations.
+    The replacement gate stated in BASELINE.md §5 is what this test enforces: with the fp64 oracle
+    as the truth, after 1 step and after 100 identical-schedule steps our trajectory is no further
+    from it than a small multiple of the fp32 oracle's own distance, and the training loss has
+    dropped alike."""
     from semigcn_b200.data import Data
     prob = meshgen.synth_inpainting_problem(6, smooth_iters=10, n_dummy=8)
     mesh = prob["mesh"]
