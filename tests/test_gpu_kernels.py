@@ -411,3 +411,33 @@ def test_mask_dilation_on_the_spmm_kernel():
         assert torch.equal(got.cpu(), mask_ref.dilate_mask(m.edge_index, seeds, rings)), rings
     with pytest.raises(SgbError):
         sdata.dilate_mask(m.edge_index, seeds, 1)              # CPU tensors are refused: no fallback
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Mesh drop-in (topology tables + CG refinement) on the GPU
+# ------------------------------------------------------------------------------------------------------------------
+def test_mesh_dropin_on_gpu(tmp_path):
+    """The same tensor code as tests/test_mesh_topology.py with device="cuda": identical tables on the reference fixture, and a
+    100 002-vertex mesh (the reference's dense N x N construction would need 40 GB there) whose refinement solve converges."""
+    import os
+    from semigcn_b200 import meshgen
+    from semigcn_b200.mesh import Mesh
+    from test_mesh_topology import check_against_fixture
+    gold = load_golden("ref_meshtopo_n8.npz")
+    path = os.path.join(str(tmp_path), "m.obj")
+    meshgen.write_obj(path, torch.from_numpy(gold["obj_vs"]), torch.from_numpy(gold["faces"]))
+    m = Mesh(path, device=DEV)
+    assert m.Lap.is_cuda
+    check_against_fixture(m, gold)
+    out = Mesh.mesh_merge(m.Lap, m, torch.from_numpy(gold["merge_new_pos"]), torch.from_numpy(gold["merge_preserve"]), w=1.0)
+    assert out.is_cuda and np.abs(out.cpu().numpy() - gold["merge_f64"]).max() <= 1e-6 * np.abs(gold["merge_f64"]).max()
+    ico = meshgen.icosphere(100, dtype=torch.float64)
+    big = Mesh(vs=ico.vs.numpy(), faces=ico.faces.numpy(), device=DEV)
+    assert len(big.edges) == 300000 and big.edge_index.shape == (2, 600000)
+    g = torch.Generator().manual_seed(1)
+    new_pos = torch.from_numpy(big.vs).float() + 0.01 * torch.randn(len(big.vs), 3, generator=g)
+    preserve = torch.from_numpy(big.vs[:, 2] < 0.9)
+    ref, info = Mesh.mesh_merge(big.Lap, big, new_pos, preserve, w=1.0, return_info=True)
+    assert info["relative_residual"] <= 1e-8, info
+    keep = preserve.numpy()
+    assert np.abs(ref.cpu().numpy()[keep] - big.vs[keep].astype(np.float32)).max() <= 0.05
