@@ -274,6 +274,15 @@ SGB_API int sgb_bnf_loss_fwd(const float* pos, int64_t ldp, int64_t n, const int
 SGB_API int sgb_bnf_loss_bwd(const float* fn, const float* new_fn, int64_t nf, int ltype, const double* out, const double* grad /* [1] */,
                      float* dfn, void* stream);
 
+/* ------------------------------------------------------------------------------------ *
+ * 7. Input preparation of the network forward (util/networks.py:67-79, util/meshnet.py:282-293):
+ *    x[n,4] = (dm * ((z1 - zc) / z_sc), dm) with zc = (min + max) / 2 and z_sc = max_d (max - min) of
+ *    z1 over the vertices -- the reference's ~10 ATen launches as a bounding-box reduction + one
+ *    elementwise pass, bit-identical arithmetic.  dm [n] (NULL = all ones, the reference's default
+ *    mask); scratch: float[16] (receives zc[3], z_sc at scratch[8..11] for inspection).
+ * ------------------------------------------------------------------------------------ */
+SGB_API int sgb_input_prep(const float* z1, int64_t ldz, int64_t n, const float* dm, float* x, float* scratch /* [16] */, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,7 @@ SIGNATURES = {
     "sgb_step_loss_fwd": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgb_step_loss_bwd": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "sgb_lap_loss_fwd": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sgb_input_prep": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "sgb_bnf_work_floats": (_sz, [_i64]),
     "sgb_bnf_partial_rows": (_i32, []),
     "sgb_bnf_loss_fwd": (_i32, [_vp, _i64, _i64, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),

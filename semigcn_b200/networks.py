@@ -46,22 +46,27 @@ class SingleScaleGCN(nn.Module):
 
     def forward(self, data, dm=None):
         z1, x_pos, edge_index = data.z1.to(self.device), data.x_pos.to(self.device), data.edge_index.to(self.device)
-        prep = _prof.span("input_prep", 4.0 * 11 * z1.shape[0]) if _prof.ACTIVE is not None else None
-        z_min, z_max = torch.min(z1, dim=0, keepdim=True)[0], torch.max(z1, dim=0, keepdim=True)[0]
-        if self.comm is not None:           # bounding box of the WHOLE mesh (util/networks.py:67-68)
-            z_min, z_max = self.comm.all_reduce_min(z_min.clone()), self.comm.all_reduce_max(z_max.clone())
-        z_sc = torch.max(z_max - z_min)
-        zc = (z_min + z_max) * 0.5
-        z1 = (z1 - zc) / z_sc
         if type(dm) == np.ndarray:
             dm = torch.from_numpy(dm)
         elif type(dm) != torch.Tensor:
             dm = torch.ones([z1.shape[0], 1])
         dm = dm.to(self.device)
-        z1 = dm * z1
-        x = torch.cat([z1, dm], dim=1)
-        if prep is not None:
-            prep.close()
+        if self.comm is None and z1.is_cuda and not z1.requires_grad and dm.numel() == z1.shape[0]:
+            # util/networks.py:67-79 as two kernels (bounding box, then normalise + mask + concatenate), bit-identical
+            x = ops.input_prep(z1, dm)
+        else:
+            # the torch form: a differentiable z1 (tests), or the partitioned mode (bounding box of the WHOLE mesh)
+            prep = _prof.span("input_prep", 4.0 * 11 * z1.shape[0]) if _prof.ACTIVE is not None else None
+            z_min, z_max = torch.min(z1, dim=0, keepdim=True)[0], torch.max(z1, dim=0, keepdim=True)[0]
+            if self.comm is not None:           # util/networks.py:67-68 over all ranks
+                z_min, z_max = self.comm.all_reduce_min(z_min.clone()), self.comm.all_reduce_max(z_max.clone())
+            z_sc = torch.max(z_max - z_min)
+            zc = (z_min + z_max) * 0.5
+            z1 = (z1 - zc) / z_sc
+            z1 = dm * z1
+            x = torch.cat([z1, dm], dim=1)
+            if prep is not None:
+                prep.close()
         skip_in = []
         nblk = len(self.blocks)
         for i, b in enumerate(self.blocks):

@@ -332,6 +332,30 @@ def amax(x: Tensor) -> Optional[Tensor]:
     return out
 
 
+def input_prep(z1: Tensor, dm: Optional[Tensor]) -> Tensor:
+    """x [N, 4] = (dm * ((z1 - zc) / z_sc), dm): the bounding-box normalisation + mask + concatenation of
+    util/networks.py:67-79 as two kernels (csrc/prep.cu), bit-identical to the torch ops.  No gradient (inputs)."""
+    lib = L.load()
+    require_cuda(z1, dm)
+    z1 = _f32c(z1.detach(), "z1")
+    n = int(z1.shape[0])
+    if z1.dim() != 2 or z1.shape[1] != 3:
+        raise SgbError("input_prep: z1 must be [N, 3]")
+    if dm is not None:
+        dm = dm.detach().to(torch.float32).reshape(-1).contiguous()
+        if dm.numel() != n:
+            raise SgbError("input_prep: mask must have one entry per vertex")
+    x = torch.empty((n, 4), dtype=torch.float32, device=z1.device)
+    scratch = torch.empty(16, dtype=torch.float32, device=z1.device)
+    sp = _prof.span("input_prep", 4.0 * 11 * n) if _prof.ACTIVE is not None else None
+    with torch.cuda.device(z1.device):
+        check(lib.sgb_input_prep(ptr(z1), z1.stride(0), n, ptr(dm), ptr(x), ptr(scratch), stream_ptr(z1.device)), "sgb_input_prep")
+    if sp is not None:
+        sp.close()
+    L.count(3)
+    return x
+
+
 def col_stats(y: Tensor) -> Tensor:
     lib = L.load()
     y = _f32c(y, "y")

@@ -441,3 +441,22 @@ def test_mesh_dropin_on_gpu(tmp_path):
     assert info["relative_residual"] <= 1e-8, info
     keep = preserve.numpy()
     assert np.abs(ref.cpu().numpy()[keep] - big.vs[keep].astype(np.float32)).max() <= 0.05
+
+
+def test_input_prep_bit_identical_to_the_reference_ops():
+    """util/networks.py:67-79 (bounding-box normalise, mask multiply, concatenate) as two kernels: bit-identical to the torch ops."""
+    from semigcn_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    for n in (1, 37, 10242, 300001):
+        z1 = (torch.randn(n, 3, generator=g) * torch.tensor([0.3, 2.0, 0.01]) + torch.tensor([-1.0, 0.5, 3.0]))
+        dm = (torch.rand(n, 1, generator=g) > 0.2).float()
+        z_min, z_max = torch.min(z1, dim=0, keepdim=True)[0], torch.max(z1, dim=0, keepdim=True)[0]
+        z_sc = torch.max(z_max - z_min)
+        zc = (z_min + z_max) * 0.5
+        want = torch.cat([dm * ((z1 - zc) / z_sc), dm], dim=1)
+        if n == 1:
+            continue                       # z_sc = 0: the reference divides by zero (NaN); nothing to pin
+        got = ops.input_prep(z1.to(DEV), dm.to(DEV))
+        assert_bit_equal(got, want, f"input_prep n={n}")
+        ones = ops.input_prep(z1.to(DEV), None)
+        assert_bit_equal(ones, torch.cat([(z1 - zc) / z_sc, torch.ones(n, 1)], dim=1), f"input_prep (no mask) n={n}")
