@@ -60,6 +60,9 @@ def parse():
     ap.add_argument("--order", default="morton", choices=["given", "morton"],
                     help="partition mode: vertex numbering the contiguous cut is taken on (morton: Z-order patches, balanced halos; "
                          "given: the generator's numbering).  Both are followed by the interior-first order inside every rank's range")
+    ap.add_argument("--mesh-order", default="given", choices=["given", "morton"],
+                    help="replicas mode: numbering of the synthetic mesh handed to the network (given: the generator's row-by-row numbering; "
+                         "morton: Z-order patches) -- an experiment knob for the locality of the aggregation kernel")
     ap.add_argument("--no-overlap", action="store_true", help="partition mode: do not overlap the halo exchange with the interior rows")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra blocks (partition / batch64 / configs[0], [1]) of the default line")
     ap.add_argument("--mode", default="replicas", choices=["replicas", "partition"],
@@ -185,9 +188,16 @@ def gcnconv_layer_bench(edge_index, n: int, nnz: int, dev, pk, cin: int = 256, c
             "hbm_frac": gbs / pk["hbm_gbs"], "reps": reps}
 
 
-def make_problem(freq: int, device, seed: int = 314):
+def make_problem(freq: int, device, seed: int = 314, order: str = "given"):
     from semigcn_b200 import meshgen
     mesh = meshgen.icosphere(freq, device=device, dtype=torch.float64)
+    if order == "morton":
+        from semigcn_b200 import partition
+        perm = partition.morton_order(mesh.vs)
+        inv = torch.empty_like(perm)
+        inv[perm] = torch.arange(perm.numel(), device=perm.device)
+        mesh = meshgen.SynthMesh(vs=mesh.vs[perm].contiguous(), faces=inv[mesh.faces].contiguous(), edges=inv[mesh.edges].contiguous(),
+                                 edge_index=inv[mesh.edge_index].contiguous())
     g = torch.Generator(device="cpu").manual_seed(seed)
     nv = mesh.num_vertices
     bump = torch.randn(nv, 1, generator=g, dtype=torch.float64).to(device)
@@ -214,7 +224,7 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
     _lib.load()
-    prob = make_problem(args.freq, dev, seed=314 + rank)
+    prob = make_problem(args.freq, dev, seed=314 + rank, order=args.mesh_order)
     mesh = prob["mesh"]
     n, nnz = mesh.num_vertices, mesh.nnz
     torch.manual_seed(314)

@@ -108,16 +108,19 @@ class MGCN(nn.Module):
 
     def forward(self, data, dm=None):
         z1 = data.z1.to(self.device)
-        z_min, z_max = torch.min(z1, dim=0, keepdim=True)[0], torch.max(z1, dim=0, keepdim=True)[0]
-        z_sc = torch.max(z_max - z_min)
-        zc = (z_min + z_max) * 0.5
-        z1 = (z1 - zc) / z_sc
         if type(dm) == np.ndarray:
             dm = torch.from_numpy(dm)
         elif not (self.tensor_masks and isinstance(dm, torch.Tensor)):
             dm = torch.ones([z1.shape[0], 1])
         dm = dm.to(self.device).to(z1.dtype)
-        z1 = torch.cat([dm * z1[:, 0:3], dm], dim=1)
+        if z1.is_cuda and z1.dtype == torch.float32 and z1.shape[1] == 3 and not z1.requires_grad and dm.numel() == z1.shape[0]:
+            z1 = ops.input_prep(z1, dm)             # util/meshnet.py:282-293 as two kernels, bit-identical (csrc/prep.cu)
+        else:
+            z_min, z_max = torch.min(z1, dim=0, keepdim=True)[0], torch.max(z1, dim=0, keepdim=True)[0]
+            z_sc = torch.max(z_max - z_min)
+            zc = (z_min + z_max) * 0.5
+            z1 = (z1 - zc) / z_sc
+            z1 = torch.cat([dm * z1[:, 0:3], dm], dim=1)
         res1_enc = self.encoder1(z1)
         res2_enc = self.encoder2(res1_enc)
         res3_bot = self.encoder3(res2_enc)
