@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; ++s) {
-            mbar_init(&full[s], kHConvWarps * 32 + 1);
+            mbar_init(&full[s], kHConvWarps * 32 / 2 + 1);        // one converter group (64 threads) + the B copy's expect_tx arrive
             mbar_init(&empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
         }
         for (int s = 0; s < kHRawStages; ++s) {
             mbar_init(&rfull[s], 1);
-            mbar_init(&rempty[s], kHConvWarps * 32);
+            mbar_init(&rempty[s], kHConvWarps * 32 / 2);
         }
         fence_barrier_init();
     }
@@ -312,39 +312,52 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
 
     if (warp < kHConvWarps) {
         // ================= A converters: raw fp32 stage (TMA) -> regs (scale, hi/lo fp16) -> operand stage =================
+        // Two groups of two warps, group g takes the stages g, g + 2, g + 4, ...: a group's chain for one stage (wait for the TMA
+        // -> shared-memory loads -> convert -> fence -> wait for the operand slot -> stores -> fence -> arrive) is long and strictly
+        // serial; with ONE group it was the period of the whole pipeline (measured: every shape ran ~0.4 us per stage above its
+        // HBM time).  Two groups overlap stage i + 1's loads / conversion with stage i's stores / fences.
         float sa, inva;
         f16_scale_from_amax(__ldg(g.a_amax), sa, inva);
+        constexpr int GROUPS = 2, GTHREADS = kHConvWarps * 32 / GROUPS;        // 64 threads per group
+        const int grp = warp / (kHConvWarps / GROUPS);                          // 0: warps 0-1, 1: warps 2-3
+        const int gt = threadIdx.x - grp * GTHREADS;                            // 0..63 inside the group
         // stage = 128 rows x kHCols core columns (8 K elements = 32 bytes of the raw row).  A quarter-warp (the unit a 16-byte
         // shared-memory access is processed in) takes the 8 rows of ONE core matrix at one core column: its reads hit 8
         // distinct swizzled chunks of the raw rows, its writes fill one dense 128-byte core matrix -- conflict-free both ways
-        // without padding the operand tile.  Thread: core column cq, rows r0 + 32 i.
-        const int cq = (threadIdx.x >> 3) & (kHCols - 1), r0 = (threadIdx.x & 7) + 8 * (threadIdx.x >> 5);      // r0 in 0..31
+        // without padding the operand tile.  Thread: core column cq, rows r0 + 16 i (8 row slots, converted four at a time).
+        const int cq = (gt >> 3) & (kHCols - 1), r0 = (gt & 7) + 8 * (gt >> 5);      // r0 in 0..15
         static_assert(kHCols == 4, "converter thread mapping assumes 4 core columns per stage");
-        constexpr int RPT = kHBM * kHCols / (kHConvWarps * 32);              // row slots per thread (4)
-        constexpr int RSTEP = kHConvWarps * 32 / kHCols;                       // 32
+        constexpr int RPT = kHBM * kHCols / GTHREADS;                           // row slots per thread (8)
+        constexpr int RSTEP = GTHREADS / kHCols;                                // 16
+        constexpr int HALF = RPT / 2;
         const uint32_t total_it = my_tiles * k_chunks;
-        uint32_t s = 0, ph = 0, rs = 0, rph = 0;
-        for (uint32_t it = 0; it < total_it; ++it) {
+        uint32_t s = (uint32_t)grp % stages, ph = ((uint32_t)grp / stages) & 1u;
+        uint32_t rs = (uint32_t)grp % (uint32_t)kHRawStages, rph = ((uint32_t)grp / (uint32_t)kHRawStages) & 1u;
+        for (uint32_t it = (uint32_t)grp; it < total_it; it += GROUPS) {
             mbar_wait(&rfull[rs], rph);
             const uint8_t* raw = raw_base + (size_t)rs * kHRawBytes;
-            float4 v[RPT][2];
-#pragma unroll
-            for (int i = 0; i < RPT; ++i) {
-                const int r = r0 + RSTEP * i;
-                // 128-byte swizzle: 16-byte chunk j of row r sits at chunk position j ^ (r % 8)
-                v[i][0] = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * cq) ^ (r & 7)) << 4));
-                v[i][1] = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * cq + 1) ^ (r & 7)) << 4));
-            }
-            // convert first: the shared-memory reads must have returned before the raw slot is handed back to the TMA
-            // engine (an arrive issued right behind the loads can overtake them in the memory pipeline)
             uint4 h[RPT], l[RPT];
 #pragma unroll
-            for (int i = 0; i < RPT; ++i) {
-                split_f16x2(v[i][0].x * sa, v[i][0].y * sa, h[i].x, l[i].x);
-                split_f16x2(v[i][0].z * sa, v[i][0].w * sa, h[i].y, l[i].y);
-                split_f16x2(v[i][1].x * sa, v[i][1].y * sa, h[i].z, l[i].z);
-                split_f16x2(v[i][1].z * sa, v[i][1].w * sa, h[i].w, l[i].w);
+            for (int hf = 0; hf < 2; ++hf) {
+                float4 v[HALF][2];
+#pragma unroll
+                for (int i = 0; i < HALF; ++i) {
+                    const int r = r0 + RSTEP * (hf * HALF + i);
+                    // 128-byte swizzle: 16-byte chunk j of row r sits at chunk position j ^ (r % 8)
+                    v[i][0] = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * cq) ^ (r & 7)) << 4));
+                    v[i][1] = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * cq + 1) ^ (r & 7)) << 4));
+                }
+#pragma unroll
+                for (int i = 0; i < HALF; ++i) {
+                    const int k = hf * HALF + i;
+                    split_f16x2(v[i][0].x * sa, v[i][0].y * sa, h[k].x, l[k].x);
+                    split_f16x2(v[i][0].z * sa, v[i][0].w * sa, h[k].y, l[k].y);
+                    split_f16x2(v[i][1].x * sa, v[i][1].y * sa, h[k].z, l[k].z);
+                    split_f16x2(v[i][1].z * sa, v[i][1].w * sa, h[k].w, l[k].w);
+                }
             }
+            // converted first: the shared-memory reads must have returned before the raw slot is handed back to the TMA
+            // engine (an arrive issued right behind the loads can overtake them in the memory pipeline)
             fence_proxy_async();
             mbar_arrive(&rempty[rs]);
             mbar_wait(&empty[s], ph ^ 1);
@@ -359,8 +372,10 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
             }
             fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
             mbar_arrive(&full[s]);
-            if (++s == stages) { s = 0; ph ^= 1; }
-            if (++rs == (uint32_t)kHRawStages) { rs = 0; rph ^= 1; }
+            s += GROUPS;
+            if (s >= stages) { s -= stages; ph ^= 1; }
+            rs += GROUPS;
+            if (rs >= (uint32_t)kHRawStages) { rs -= (uint32_t)kHRawStages; rph ^= 1; }
         }
     } else if (warp == kHWarpLoad) {
         // ================= A loader: one lane streams the raw A tiles (TMA 2-D, 128B swizzle, zero fill past m / k) =================

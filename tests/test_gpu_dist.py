@@ -92,7 +92,9 @@ def _worker(rank, world, port, conv, slope=0.01, ranges=None, order="given", wit
         assert out.shape == (hi - lo, 3)
         e_out = _rel(out, out_ref[lo:hi])
         assert e_out <= 1e-5, f"rank {rank}: output differs {e_out:.2e}"
-        assert abs(loss.item() - loss_ref.item()) <= 1e-6 * abs(loss_ref.item())
+        # the position loss agrees to 1e-6; the face-normal term is a function of the OUTPUT (within 1e-5 of the unpartitioned one)
+        # through normals of faces whose sides are ~0.1 long: an output deviation of a few 1e-6 moves it by up to ~1e-4 relative
+        assert abs(loss.item() - loss_ref.item()) <= (2e-4 if with_normals else 1e-6) * abs(loss_ref.item()), (loss.item(), loss_ref.item())
         worst, who = 0.0, ""
         for k, p in net.named_parameters():
             if p.grad is None:
