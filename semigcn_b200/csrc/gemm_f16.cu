@@ -26,6 +26,19 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+// Ablation switches for tools/ablate_gemm.sh (timing experiments: which role bounds the pipeline?).  Each removes the WORK of one
+// role of k_gemm_f16 and keeps its barrier protocol, so the kernel still terminates; the results are garbage.  Never set in the
+// library build.
+#ifndef SGB_ABL
+#define SGB_ABL 0
+#endif
+#define SGB_ABL_NO_BCOPY 1      // weights copied for the first ring round only
+#define SGB_ABL_NO_STORE 2      // epilogue: no global stores
+#define SGB_ABL_NO_EPI 4        // epilogue: only the accumulator hand-shake
+#define SGB_ABL_NO_CONV 8       // converters: only the hand-shakes
+#define SGB_ABL_NO_TMA 16       // A loader: no TMA
+#define SGB_ABL_NO_MMA 32       // MMA issuer: no tcgen05.mma
+
 namespace sgb {
 
 // ------------------------------------------------------------------------------------------
@@ -231,7 +244,7 @@ __device__ __forceinline__ void h_epi_chunk(const HArgs& g, uint32_t taddr, floa
         const bool on = FULL || (col_ok && i * 4 + grp < nvalid);
         if (on) {
             o[i].x += b.x; o[i].y += b.y; o[i].z += b.z; o[i].w += b.w;
-            *reinterpret_cast<float4*>(cp + i * ld4) = o[i];
+            if (!(SGB_ABL & SGB_ABL_NO_STORE)) *reinterpret_cast<float4*>(cp + i * ld4) = o[i];
         }
     }
     if (stats) {
@@ -334,11 +347,17 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
         uint32_t s = (uint32_t)grp % stages, ph = ((uint32_t)grp / stages) & 1u;
         uint32_t rs = (uint32_t)grp % (uint32_t)kHRawStages, rph = ((uint32_t)grp / (uint32_t)kHRawStages) & 1u;
         for (uint32_t it = (uint32_t)grp; it < total_it; it += GROUPS) {
+            // The previous user of this raw slot (stage it - kHRawStages) is the OTHER group when the ring length is odd, and
+            // TMA completions are not ordered: without this wait a group that runs ahead could test rfull[rs] while the slot's
+            // previous phase has not even completed -- the parity test would alias (phase p - 1 incomplete looks like phase p
+            // complete) and the group would convert stale data and release the slot twice.  rempty[rs] completes only after the
+            // previous user has seen its data, and its next phase cannot complete without this group: no aliasing here.
+            mbar_wait(&rempty[rs], rph ^ 1);
             mbar_wait(&rfull[rs], rph);
             const uint8_t* raw = raw_base + (size_t)rs * kHRawBytes;
             uint4 h[RPT], l[RPT];
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
+            for (int hf = 0; hf < ((SGB_ABL & SGB_ABL_NO_CONV) ? 0 : 2); ++hf) {
                 float4 v[HALF][2];
 #pragma unroll
                 for (int i = 0; i < HALF; ++i) {
@@ -364,7 +383,7 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
             uint8_t* a_hi = op_base + (size_t)s * stage_bytes;
             uint8_t* a_lo = a_hi + kHATile;
 #pragma unroll
-            for (int i = 0; i < RPT; ++i) {
+            for (int i = 0; i < ((SGB_ABL & SGB_ABL_NO_CONV) ? 0 : RPT); ++i) {
                 const int r = r0 + RSTEP * i;
                 const uint32_t off = (uint32_t)(r >> 3) * kHASbo + (uint32_t)cq * kHALbo + (uint32_t)(r & 7) * 16;
                 *reinterpret_cast<uint4*>(a_hi + off) = h[i];
@@ -387,8 +406,11 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
                 const int m0 = (int)((tile / g.n_tiles) * kHBM);
                 for (uint32_t q = 0; q < k_chunks; ++q) {
                     mbar_wait(&rempty[rs], rph ^ 1);
-                    mbar_arrive_expect_tx(&rfull[rs], kHRawBytes);
-                    tma_load_2d(raw_base + (size_t)rs * kHRawBytes, &g.a_map, (int)(q * kHBK), m0, &rfull[rs]);
+                    if (SGB_ABL & SGB_ABL_NO_TMA) { mbar_arrive(&rfull[rs]); }
+                    else {
+                        mbar_arrive_expect_tx(&rfull[rs], kHRawBytes);
+                        tma_load_2d(raw_base + (size_t)rs * kHRawBytes, &g.a_map, (int)(q * kHBK), m0, &rfull[rs]);
+                    }
                     if (++rs == (uint32_t)kHRawStages) { rs = 0; rph ^= 1; }
                 }
             }
@@ -403,8 +425,11 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
                 for (uint32_t q = 0; q < k_chunks; ++q) {
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* b_dst = op_base + (size_t)s * stage_bytes + 2 * kHATile;
-                    mbar_arrive_expect_tx(&full[s], 2 * b_tile_bytes);
-                    bulk_g2s(b_dst, src0 + (size_t)q * 2 * b_tile_bytes, 2 * b_tile_bytes, &full[s]);
+                    if ((SGB_ABL & SGB_ABL_NO_BCOPY) && (t * k_chunks + q) >= stages) { mbar_arrive(&full[s]); }
+                    else {
+                        mbar_arrive_expect_tx(&full[s], 2 * b_tile_bytes);
+                        bulk_g2s(b_dst, src0 + (size_t)q * 2 * b_tile_bytes, 2 * b_tile_bytes, &full[s]);
+                    }
                     if (++s == stages) { s = 0; ph ^= 1; }
                 }
             }
@@ -429,7 +454,7 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
                     const uint32_t b_hi = a_hi + 2 * kHATile;
                     const uint32_t b_lo = b_hi + b_tile_bytes;
 #pragma unroll
-                    for (int j = 0; j < kHBK / 16; ++j) {
+                    for (int j = 0; j < ((SGB_ABL & SGB_ABL_NO_MMA) ? 0 : kHBK / 16); ++j) {
                         const uint64_t dah = make_desc(a_hi + j * 2 * kHALbo, kHALbo, kHASbo);
                         const uint64_t dal = make_desc(a_lo + j * 2 * kHALbo, kHALbo, kHASbo);
                         const uint64_t dbh = make_desc(b_hi + j * 2 * kHBLbo, kHBLbo, kHBSbo);
@@ -485,7 +510,7 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
 #pragma unroll
             for (int t = 0; t < 4; ++t) {            // unrolled: the moment registers are indexed statically
                 const int c0 = (2 * t + half) * 32;
-                if (c0 < ncols) {
+                if (c0 < ncols && !(SGB_ABL & SGB_ABL_NO_EPI)) {
                     float bm[4], bq[4];
                     const bool col_ok = c0 + cc < ncols;             // ncols is a multiple of 16 => whole float4 valid
                     const float* bias_p = g.bias ? g.bias + n0 + c0 + cc : nullptr;

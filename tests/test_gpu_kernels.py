@@ -274,7 +274,11 @@ def test_bn_act_forward_backward_vs_torch(m, c, slope):
 
 # ------------------------------------------------------------------ 5. tcgen05 3xTF32 engine
 TC_SHAPES = [(1000, 64, 64), (129, 16, 8), (5000, 256, 256), (4100, 512, 256), (3000, 128, 64), (2500, 256, 512), (1000, 48, 36),
-             (20000, 256, 128), (777, 80, 200)]
+             (20000, 256, 128), (777, 80, 200),
+             # many tiles per CTA (the kernels are persistent, one CTA per SM): the ring positions / phases of every role wrap
+             # dozens of times and the converter groups drift apart -- the regime of the 1 M-vertex bench (a parity-aliasing
+             # hang of the two-group converter only showed there, never on the one-tile-per-CTA shapes above)
+             (150001, 256, 256), (120000, 512, 96), (90000, 64, 352)]
 
 
 @pytest.mark.parametrize("m,n,k", TC_SHAPES)
