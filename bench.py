@@ -94,17 +94,21 @@ def ncu_traffic(kernel: str):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  nvidia-smi takes a few hundred
+    milliseconds to come up (longer on an 8-GPU box), so it is started BEFORE the warm-up steps; ``mark_start()`` / ``stop()``
+    bracket the timed region and only the samples inside it are used -- unless the region was shorter than the sampling period,
+    in which case the samples taken under the identical warm-up load are reported and ``window`` says so."""
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
+        self.t_start = None
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -112,19 +116,30 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_start(self):
+        self.t_start = time.time()
 
     def stop(self):
+        t_end = time.time()
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.06)                      # let the sample that covers the end of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t0 = self.t_start if self.t_start is not None else 0.0
+        inside = [ln for (t, ln) in self.lines if t0 <= t <= t_end + 0.06]
+        window = "timed region"
+        if not inside:                        # region shorter than the sampling period: the warm-up ran the same load
+            inside = [ln for (_, ln) in self.lines[1:]] or [ln for (_, ln) in self.lines]
+            window = "warm-up + timed region (timed region shorter than the sampling period)"
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -137,7 +152,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------
@@ -254,11 +269,12 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---------------- device-resident timing ("value")
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(args.warmup):
         one_step(i, data, prob["dms"][:, i % 8:i % 8 + 1])
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark_start()
     launches0 = _lib.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -283,31 +299,42 @@ def run_ours(args, rank, world, local_rank):
     h = {k: prob[k].cpu().pin_memory() for k in ("z1", "x_pos")}
     h["edge_index"] = mesh.edge_index.cpu().pin_memory()
     h["dms"] = [prob["dms"][:, j:j + 1].contiguous().cpu().pin_memory() for j in range(8)]
-    d_z1, d_xp, d_ei = torch.empty_like(prob["z1"]), torch.empty_like(prob["x_pos"]), torch.empty_like(mesh.edge_index)
-    d_dm = torch.empty((n, 1), dtype=torch.float32, device=dev)
     loss_host = torch.empty((), dtype=torch.float64).pin_memory()
 
-    def e2e_step(i):
+    from semigcn_b200.data import HostInputPipeline
+    pipe = None
+    if graphed is None:
+        # util/networks.py:65 uploads z1 / x_pos / edge_index on every forward, :77 the mask.  Every step's inputs cross PCIe
+        # from pinned host memory inside the timed region; the upload of step i + 1 runs on a copy stream while step i computes
+        # (semigcn_b200.data.HostInputPipeline, two device slots).
+        pipe = HostInputPipeline(dev, z1=h["z1"], x_pos=h["x_pos"], edge_index=h["edge_index"], dm=h["dms"][0])
+
+    def submit(i):
+        pipe.submit(z1=h["z1"], x_pos=h["x_pos"], edge_index=h["edge_index"], dm=h["dms"][i % 8])
+
+    def e2e_step(i, last=False):
         if graphed is not None:      # graph mode: the mesh (edge_index) is fixed at capture; z1 / x_pos / mask come from pinned host memory
             loss = one_step(i, Data(z1=h["z1"], x_pos=h["x_pos"], edge_index=None), h["dms"][i % 8])
             loss_host.copy_(loss.detach(), non_blocking=True)
             return
-        # util/networks.py:65 uploads z1 / x_pos / edge_index on every forward, :77 the mask
-        d_z1.copy_(h["z1"], non_blocking=True)
-        d_xp.copy_(h["x_pos"], non_blocking=True)
-        d_ei.copy_(h["edge_index"], non_blocking=True)
-        d_dm.copy_(h["dms"][i % 8], non_blocking=True)
-        loss = one_step(i, Data(z1=d_z1, x_pos=d_xp, edge_index=d_ei), d_dm)
+        if not last:
+            submit(i + 1)
+        d = pipe.get()
+        loss = one_step(i, Data(z1=d["z1"], x_pos=d["x_pos"], edge_index=d["edge_index"]), d["dm"])
+        pipe.release()
         loss_host.copy_(loss.detach(), non_blocking=True)
 
-    for i in range(max(1, args.warmup)):
+    n_e2e_warm = max(1, args.warmup)
+    if pipe is not None:
+        submit(0)
+    for i in range(n_e2e_warm):
         e2e_step(i)
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    for i in range(args.steps):
-        e2e_step(i)
+    for i in range(n_e2e_warm, n_e2e_warm + args.steps):
+        e2e_step(i, last=(i == n_e2e_warm + args.steps - 1))
     t1.record()
     barrier()
     ms_e2e = t0.elapsed_time(t1)
@@ -330,8 +357,9 @@ def run_ours(args, rank, world, local_rank):
                                f"({n} vertices, {nnz} directed edges) per GPU; BASELINE.json configs[2]",
                    "vertices": n, "directed_edges": nnz, "conv_layers": N_LAYERS, "parallelism": f"replicas x{world} (independent meshes, no collective)",
                    "l2_policy": "inputs larger than L2 (activations of one step ~16 GB >> 126 MB); no explicit flush",
-                   "e2e_inputs": "z1, x_pos, edge_index, mask uploaded from pinned host memory every step (as util/networks.py:65,77); "
-                                 "edge_index re-upload forces a CSR rebuild every step"},
+                   "e2e_inputs": "z1, x_pos, edge_index, mask uploaded from pinned host memory every step (as util/networks.py:65,77) through the "
+                                 "public double-buffered input pipeline (semigcn_b200.data.HostInputPipeline: the upload of step i+1 overlaps step i); "
+                                 "the re-uploaded edge_index is resolved by the CSR cache by content (no rebuild)"},
         "train_steps_per_s": args.steps * world / (ms / 1e3),
         "e2e": {"value": units / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                 "ms_per_step": ms_e2e / args.steps},
@@ -552,10 +580,11 @@ def partition_measure(args, rank, world, local_rank, freq: int, steps: int, warm
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(warmup):
         one_step(i)
     barrier()
-    sampler.start()
+    sampler.mark_start()
     launches0, bytes0, calls0 = _lib.LAUNCHES, g_part.halo.bytes_total, g_part.halo.calls
     ms, loss = _time_steps(one_step, steps, 0, barrier)
     launches = _lib.LAUNCHES - launches0
@@ -820,18 +849,22 @@ def batch64_block(args, rank, world, local_rank, meshes_total: int = 64, freq: i
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for lane in lanes:                       # warm-up: one mesh start + two steps per lane
         with torch.cuda.stream(lane["stream"]):
             start_mesh(lane, lane["queue"][0])
             lane["graph"](lane["prob"]["dms"][:, 0:1])
             lane["graph"](lane["prob"]["dms"][:, 1:2])
     barrier()
+    sampler.mark_start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     run_all()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
     launches = sum(l["graph"].launches_per_replay for l in lanes[:1]) * steps_per_mesh * len(mine)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -846,7 +879,7 @@ def batch64_block(args, rank, world, local_rank, meshes_total: int = 64, freq: i
     return {"meshes": meshes_total, "vertices_per_mesh": nv, "directed_edges_per_mesh": nnz, "n_gpus": world, "meshes_per_gpu": len(mine),
             "concurrent_meshes_per_gpu": slots, "steps_per_mesh_timed": steps_per_mesh, "ms_total": ms, "train_steps_per_s": total_steps / (ms / 1e3),
             "edges_per_s": float(nnz) * N_LAYERS * total_steps / (ms / 1e3), "ms_per_step_per_gpu": ms / (len(mine) * steps_per_mesh),
-            "gpu_launches_rank0": launches, "collectives": "none (independent meshes)",
+            "gpu_launches_rank0": launches, "clocks": clocks, "collectives": "none (independent meshes)",
             "includes": "per mesh: geometry + 30 smoothing iterations + target normals on the GPU, in-place reset of parameters / Adam state, "
                         f"then {steps_per_mesh} whole-step CUDA-graph replays (forward + both step losses + backward + Adam)"}
 
