@@ -776,6 +776,44 @@ def small_mesh_block(args, dev, freq: int = 32, reps: int = 20):
     return out
 
 
+def mesh_order_block(args, dev):
+    """the headline runs on the generator's vertex numbering (subdivision order, row by row inside each
+    icosahedron face); this is the same step on the SAME mesh renumbered along a Morton (Z-order) curve -- compact patches
+    instead of mesh rows per CTA, i.e. more neighbour rows served by L1 in the aggregation kernel.  A dataset property, not a
+    kernel change: reported next to the headline, never instead of it."""
+    from semigcn_b200 import ops, profile
+    from semigcn_b200.data import Data
+    from semigcn_b200.networks import SingleScaleGCN
+    prob = make_problem(args.freq, dev, seed=314, order="morton")
+    mesh = prob["mesh"]
+    torch.manual_seed(314)
+    net = SingleScaleGCN(dev, conv=args.conv).to(dev)
+    opt = torch.optim.Adam(net.parameters(), lr=0.01)
+    data = Data(z1=prob["z1"], x_pos=prob["x_pos"], edge_index=mesh.edge_index)
+
+    def one_step(i):
+        opt.zero_grad(set_to_none=True)
+        loss = step_losses(net(data, prob["dms"][:, i % 8:i % 8 + 1]), prob)
+        loss.backward()
+        opt.step()
+        return loss
+
+    steps = min(args.steps, 10)
+    ms, _ = _time_steps(one_step, steps, 3, torch.cuda.synchronize)
+    with profile.KernelProfile() as kp:
+        for i in range(3):
+            one_step(i)
+        fam = kp.summary()
+    spmm_ms = sum(v["ms"] for k, v in fam.items() if k.startswith("spmm_c")) / 3
+    spmm_b = sum(v["bytes"] for k, v in fam.items() if k.startswith("spmm_c")) / 3
+    out = {"vertices": mesh.num_vertices, "ms_per_step": ms / steps, "edges_per_s": float(mesh.nnz) * N_LAYERS * steps / (ms / 1e3),
+           "spmm_ms_per_step": spmm_ms, "spmm_GBps": spmm_b / (spmm_ms / 1e3) / 1e9 if spmm_ms else None}
+    del net, opt, data, prob
+    ops.clear_graph_cache()
+    torch.cuda.empty_cache()
+    return out
+
+
 def batch64_block(args, rank, world, local_rank, meshes_total: int = 64, freq: int = 100, steps_per_mesh: int = 10, slots: int = 4):
     """configs[4]: a batch of 64 independent 100 k-vertex meshes, one self-prior network per mesh (sgcn.py:78-80), spread over
     the N GPUs: rank r trains meshes r, r + N, ...  No data-path collective.  On each GPU ``slots`` meshes train CONCURRENTLY,
@@ -937,6 +975,7 @@ def main():
         guarded("batch64", lambda: batch64_block(args, rank, world, local_rank))
         if world == 1:
             guarded("small_meshes", lambda: small_mesh_block(args, torch.device(f"cuda:{local_rank}")))
+            guarded("mesh_order_morton", lambda: mesh_order_block(args, torch.device(f"cuda:{local_rank}")))
         if line is not None:
             line.update(extras)
     if line is not None:
