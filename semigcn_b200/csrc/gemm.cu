@@ -20,6 +20,10 @@ int gemm_f16_launch(const GemmArgs& g, const float* a_amax, void* ws, size_t ws_
 size_t gemm_tn_f16_workspace(int64_t m, int n, int k);
 int gemm_tn_f16_launch(const float* g, int64_t ldg, const float* a, int64_t lda, const float* g_amax, const float* a_amax, float* d,
                        int64_t ldd, int64_t m, int n, int k, int accumulate, void* ws, size_t ws_bytes, cudaStream_t stream);
+bool gemm_tn_pair_ok(int64_t m, int n, int k);
+size_t gemm_tn_pair_workspace(int64_t m, int n, int k);
+int gemm_tn_pair_launch(const float* g, int64_t ldg, const float* a, int64_t lda, const float* g_amax, const float* a_amax, float* d,
+                        int64_t ldd, int64_t m, int n, int k, int accumulate, void* ws, size_t ws_bytes, cudaStream_t stream);
 static bool tn_tc_worthwhile(int64_t m, int n, int k) { return n >= 64 && k >= 32 && m >= 4096; }
 
 // auto policy: the tensor pipe only where the transform is a real dense contraction
@@ -85,8 +89,10 @@ extern "C" size_t sgb_gemm_tn_workspace_bytes(int64_t m, int n, int k) {
     if (m < 0 || n <= 0 || k <= 0) return 0;
     size_t a = gemm_tn_simt_workspace(m, n, k), b = (n % 4 == 0 && k % 4 == 0) ? gemm_tn_tc_workspace(m, n, k) : 0;
     size_t c = (n % 4 == 0 && k % 4 == 0) ? gemm_tn_f16_workspace(m, n, k) : 0;
+    size_t e = gemm_tn_pair_workspace(m, n, k);
     a = a > b ? a : b;
-    return a > c ? a : c;
+    a = a > c ? a : c;
+    return a > e ? a : e;
 }
 
 extern "C" int sgb_gemm_tn(const float* g, int64_t ldg, const float* a, int64_t lda, float* d, int64_t ldd, int64_t m, int n, int k,
@@ -94,8 +100,18 @@ extern "C" int sgb_gemm_tn(const float* g, int64_t ldg, const float* a, int64_t 
                            void* stream) {
     SGB_CHECK_ARG(g && a && d && m >= 0 && n > 0 && k > 0, "sgb_gemm_tn: bad argument");
     SGB_CHECK_ARG(ldg >= n && lda >= k && ldd >= k, "sgb_gemm_tn: leading dimension too small");
-    SGB_CHECK_ARG(engine >= 0 && engine <= 3, "sgb_gemm_tn: bad engine %d", engine);
+    SGB_CHECK_ARG(engine >= 0 && engine <= 4, "sgb_gemm_tn: bad engine %d", engine);
     const bool tc_ok = gemm_tn_tc_supported(m, n, k, ldg, lda, g, a);
+    // auto: 256-row multiples of D go to CTA pairs (measured on 998 562 vertices, amax supplied: n256_k256 0.517 -> 0.425 ms,
+    // n512_k256 0.994 -> 0.839 ms, n256_k64 0.390 -> 0.310 ms against the single-CTA engine)
+    if (engine == 0 && tc_ok && gemm_tn_pair_ok(m, n, k) && m >= 32768) engine = 4;
+    if (engine == 4) {       // tcgen05 fp16-split tiles on CTA pairs (cta_group::2)
+        if (!tc_ok || !gemm_tn_pair_ok(m, n, k)) {
+            set_error("sgb_gemm_tn: the pair engine needs n %% 256 == 0, k %% 32 == 0 (k <= 256 or k %% 256 == 0), m >= 4096 and 16-byte aligned operands");
+            return SGB_ENOTSUP;
+        }
+        return gemm_tn_pair_launch(g, ldg, a, lda, g_amax, a_amax, d, ldd, m, n, k, accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
+    }
     if (engine == 2) {
         if (!tc_ok) {
             set_error("sgb_gemm_tn: tcgen05 engine needs n %% 4 == 0, k %% 4 == 0 and 16-byte aligned operands");

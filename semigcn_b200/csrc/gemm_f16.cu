@@ -697,14 +697,15 @@ __global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const __grid_const
         if (lane == 0) {
             tma_prefetch_desc(&t.g_map);
             tma_prefetch_desc(&t.a_map);
+            const uint64_t stream_policy = l2_policy_evict_first();      // G and A are read once: do not push the partial tiles out of L2
             uint32_t rs = 0, rph = 0;
             for (int it = 0; it < chunks; ++it) {
                 mbar_wait(&rempty[rs], rph ^ 1);
                 mbar_arrive_expect_tx(&rfull[rs], (uint32_t)(raw_g_bytes + raw_a_bytes));
                 uint8_t* dst = raw_base + (size_t)rs * raw_bytes;
                 const int row = (int)(ms + (int64_t)it * kTBV);
-                tma_load_2d(dst, &t.g_map, n0, row, &rfull[rs]);
-                tma_load_2d(dst + raw_g_bytes, &t.a_map, k0, row, &rfull[rs]);
+                tma_load_2d_hint(dst, &t.g_map, n0, row, &rfull[rs], stream_policy);
+                tma_load_2d_hint(dst + raw_g_bytes, &t.a_map, k0, row, &rfull[rs], stream_policy);
                 if (++rs == (uint32_t)kTRawStages) { rs = 0; rph ^= 1; }
             }
         }
@@ -749,6 +750,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const __grid_const
         const int gn = n0 + quarter * 32 + lane;
         const int kcols = min(t.bk, t.k - k0);
         const bool vec_ok = (t.k % 4 == 0) && (k0 % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+        const uint64_t keep_policy = l2_policy_evict_last();             // the running partial tile stays in L2 between segments
         if (segments == 0) {
             if (gn < t.n)
                 for (int c = 0; c < kcols; ++c) out[(int64_t)gn * t.k + k0 + c] = 0.f;
@@ -778,14 +780,14 @@ __global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const __grid_const
                         if (seg != 0) {                          // all eight loads in flight before the first add
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
-                                old[i] = (4 * i < nrows) ? __ldcg(reinterpret_cast<const float4*>(op0 + (int64_t)(4 * i) * t.k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                old[i] = (4 * i < nrows) ? ldcg_hint(reinterpret_cast<const float4*>(op0 + (int64_t)(4 * i) * t.k), keep_policy) : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             if (4 * i < nrows) {
                                 float4 o = *reinterpret_cast<const float4*>(stg + (i * 4 + (lane >> 3)) * kHEpiLd + cc);
                                 if (seg != 0) { o.x += old[i].x; o.y += old[i].y; o.z += old[i].z; o.w += old[i].w; }
-                                __stcg(reinterpret_cast<float4*>(op0 + (int64_t)(4 * i) * t.k), o);
+                                stcg_hint(reinterpret_cast<float4*>(op0 + (int64_t)(4 * i) * t.k), o, keep_policy);
                             }
                         }
                     }
@@ -807,6 +809,246 @@ __global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const __grid_const
     if (warp == kTProducerWarps) {
         tc_fence_after();
         tmem_dealloc(tmem_base, t.tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight gradient on CTA PAIRS (cta_group::2):  D[256 n-rows, bk k-cols] per pair, UMMA M = 256 (128 rows per CTA), N = bk.
+//   k_gemm_tn_f16 is bound by the shared-memory data pipe (ncu: 79 %; 216 KB of shared-memory traffic per 32-vertex stage against
+//   48 KB of HBM traffic).  In a pair, CTA r converts its own G box (32 vertices x its 128 n-rows) and only HALF of the A box (the
+//   k-columns [k0 + r bk/2, + bk/2)): the tensor cores exchange the B-operand halves, so the per-CTA traffic of a stage drops to
+//   144 KB (raw boxes in + out 64, operand tiles in 32, tensor-core reads 48) and every A element is converted once per pair.
+//   Protocol: every CTA has its own raw ring (TMA, local barriers).  Operand ring: the converter warps of BOTH CTAs arrive (one
+//   elected lane per warp, after the warp's stores and proxy fences) on the LEADER's (cluster rank 0) full[s]; the leader's MMA lane
+//   issues tcgen05.mma.cta_group::2 and commits with a multicast arrive on empty[s] / tfull[acc] of both CTAs; each CTA's drain
+//   warps read their own TMEM lanes and arrive on the leader's tempty[acc].
+// ------------------------------------------------------------------------------------------
+constexpr int kPConvWarps = 8;                   // warps 0..3: G box, warps 4..7: this CTA's half of the A box
+constexpr int kPWarpMma = kPConvWarps;           // MMA issuer (leader only) and TMEM owner (both CTAs)
+constexpr int kPWarpDrain0 = kPConvWarps + 1;    // warps 9..12 (TMEM lane quarter = warp % 4)
+constexpr int kPWarpLoad = kPWarpDrain0 + kTDrainWarps;
+constexpr int kPThreads = (kPWarpLoad + 1) * 32; // 448
+constexpr int kPMaxRawStages = 4;
+
+struct TPArgs {
+    CUtensorMap g_map, a_map;         // G [m, n] box {128, 32}; A [m, k] box {ah, 32}; dense (no swizzle) box images
+    int ah;                           // k-columns per CTA = bk / 2 (multiple of 8, <= 128)
+    const float* g_amax; const float* a_amax;
+    float* partial;                   // [splits][n][k]
+    int64_t m; int n; int k;
+    int bk;                           // UMMA N (multiple of 16, <= 256)
+    int k_tiles; int stages; int raw_stages;
+    int64_t m_per_split;
+    uint32_t tmem_cols; int acc_stride;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPThreads, 1) k_gemm_tn_f16_pair(const __grid_constant__ TPArgs t) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();                 // 0 = leader
+    const int a_tile_bytes = t_a_tile_bytes(t.ah);
+    const int stage_bytes = 2 * kTGTile + 2 * a_tile_bytes;
+    constexpr int raw_g_bytes = kTBV * kTBM * 4;
+    const int raw_a_bytes = kTBV * t.ah * 4;
+    const int raw_bytes = (raw_g_bytes + raw_a_bytes + 127) / 128 * 128;
+    uint8_t* const raw_base = smem;
+    uint8_t* const op_base = smem + (size_t)t.raw_stages * raw_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(op_base + (size_t)t.stages * stage_bytes);
+    uint64_t* empty = full + kHMaxStages;
+    uint64_t* tfull = empty + kHMaxStages;      // [2]
+    uint64_t* tempty = tfull + 2;               // [2]
+    uint64_t* rfull = tempty + 2;               // [raw_stages]
+    uint64_t* rempty = rfull + kPMaxRawStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + kPMaxRawStages);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < t.stages; ++s) {
+            mbar_init(&full[s], 2 * kPConvWarps);            // one elected lane per converter warp, both CTAs (leader's copy is the live one)
+            mbar_init(&empty[s], 1);                         // multicast commit
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tfull[b], 1);                         // multicast commit
+            mbar_init(&tempty[b], 2 * kTDrainWarps);         // drain warps of both CTAs (leader's copy is the live one)
+        }
+        for (int s = 0; s < t.raw_stages; ++s) {
+            mbar_init(&rfull[s], 1);
+            mbar_init(&rempty[s], kPConvWarps * 32);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    cluster_sync_all();                                      // both CTAs' barriers exist before anyone arrives remotely
+    if (warp == kPWarpMma) tmem_alloc_pair(tmem_slot, t.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int pair = blockIdx.x >> 1;
+    const int n0 = (pair / t.k_tiles) * 2 * kTBM + (int)rank * kTBM;      // this CTA's 128 n-rows
+    const int k0 = (pair % t.k_tiles) * t.bk;                              // the pair's k-tile
+    const int ka = k0 + (int)rank * t.ah;                                  // the k-columns this CTA converts
+    const int64_t ms = (int64_t)blockIdx.y * t.m_per_split;
+    const int64_t me = min64(t.m, ms + t.m_per_split);
+    const int chunks = me > ms ? (int)((me - ms + kTBV - 1) / kTBV) : 0;
+    const int segments = (chunks + kTSegChunks - 1) / kTSegChunks;
+    float sg, invg, sa, inva;
+    f16_scale_from_amax(__ldg(t.g_amax), sg, invg);
+    f16_scale_from_amax(__ldg(t.a_amax), sa, inva);
+
+    if (warp < kPConvWarps) {
+        // converter item: 8 consecutive vertices (core column mg) x 4 consecutive columns (float4 index c4); threads 0..127 take the
+        // G box, 128..255 the A half box; the 8 x 4 register block is four 16-byte K-major rows (the transposition happens in registers)
+        const int tid = threadIdx.x;
+        const bool is_g = tid < 128;
+        const int idx = tid & 127;
+        const int mg = idx >> 5, c4 = idx & 31;
+        const int box = is_g ? kTBM : t.ah;
+        const bool in_tile = c4 * 4 < box;
+        const float sc = is_g ? sg : sa;
+        const uint32_t raw_off = (is_g ? 0u : (uint32_t)raw_g_bytes) + (uint32_t)(mg * 8) * (uint32_t)box * 4u + (uint32_t)c4 * 16u;
+        const uint32_t tile_off = is_g ? 0u : (uint32_t)(2 * kTGTile);
+        const uint32_t lo_off = is_g ? (uint32_t)kTGTile : (uint32_t)a_tile_bytes;
+        const uint32_t base_off = tile_off + (uint32_t)((c4 * 4) >> 3) * kTSbo + (uint32_t)mg * kTLbo + (uint32_t)((c4 * 4) & 7) * 16;
+        uint32_t s = 0, ph = 0, rs = 0, rph = 0;
+        for (int it = 0; it < chunks; ++it) {
+            mbar_wait(&rfull[rs], rph);
+            const uint8_t* raw = raw_base + (size_t)rs * raw_bytes + raw_off;
+            uint4 h[4], l[4];
+            if (in_tile) {
+                float4 v[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) v[r] = *reinterpret_cast<const float4*>(raw + (size_t)r * box * 4);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float x0 = (&v[0].x)[q], x1 = (&v[1].x)[q], x2 = (&v[2].x)[q], x3 = (&v[3].x)[q];
+                    const float x4 = (&v[4].x)[q], x5 = (&v[5].x)[q], x6 = (&v[6].x)[q], x7 = (&v[7].x)[q];
+                    split_f16x2(x0 * sc, x1 * sc, h[q].x, l[q].x);
+                    split_f16x2(x2 * sc, x3 * sc, h[q].y, l[q].y);
+                    split_f16x2(x4 * sc, x5 * sc, h[q].z, l[q].z);
+                    split_f16x2(x6 * sc, x7 * sc, h[q].w, l[q].w);
+                }
+            }
+            fence_proxy_async();                 // the conversion consumed the loaded values: the raw slot may go back to the TMA engine
+            mbar_arrive(&rempty[rs]);
+            mbar_wait(&empty[s], ph ^ 1);        // multicast commit of the leader's MMAs that read this slot (in BOTH CTAs)
+            if (in_tile) {
+                uint8_t* st = op_base + (size_t)s * stage_bytes + base_off;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    *reinterpret_cast<uint4*>(st + q * 16) = h[q];
+                    *reinterpret_cast<uint4*>(st + lo_off + q * 16) = l[q];
+                }
+            }
+            fence_proxy_async();                 // generic-proxy stores -> visible to the tensor cores
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&full[s], 0);     // this warp's part of the stage is in place (leader's barrier)
+            if (++s == (uint32_t)t.stages) { s = 0; ph ^= 1; }
+            if (++rs == (uint32_t)t.raw_stages) { rs = 0; rph ^= 1; }
+        }
+    } else if (warp == kPWarpLoad) {
+        if (lane == 0) {
+            tma_prefetch_desc(&t.g_map);
+            tma_prefetch_desc(&t.a_map);
+            const uint64_t stream_policy = l2_policy_evict_first();      // G and A are read once: do not push the partial tiles out of L2
+            uint32_t rs = 0, rph = 0;
+            for (int it = 0; it < chunks; ++it) {
+                mbar_wait(&rempty[rs], rph ^ 1);
+                mbar_arrive_expect_tx(&rfull[rs], (uint32_t)(raw_g_bytes + raw_a_bytes));
+                uint8_t* dst = raw_base + (size_t)rs * raw_bytes;
+                const int row = (int)(ms + (int64_t)it * kTBV);
+                tma_load_2d_hint(dst, &t.g_map, n0, row, &rfull[rs], stream_policy);
+                tma_load_2d_hint(dst + raw_g_bytes, &t.a_map, ka, row, &rfull[rs], stream_policy);
+                if (++rs == (uint32_t)t.raw_stages) { rs = 0; rph ^= 1; }
+            }
+        }
+    } else if (warp == kPWarpMma) {
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = make_idesc_f16(2 * kTBM, t.bk, 0, 0);      // M = 256 over the pair; both operands K-major (K = vertex)
+            uint32_t s = 0, ph = 0;
+            for (int it = 0; it < chunks; ++it) {
+                const int seg = it / kTSegChunks, in_seg = it % kTSegChunks;
+                const int acc = seg & 1;
+                if (in_seg == 0) {
+                    mbar_wait_cluster(&tempty[acc], ((seg >> 1) & 1) ^ 1);    // drained in BOTH CTAs
+                    tc_fence_after();
+                }
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * t.acc_stride);
+                mbar_wait_cluster(&full[s], ph);                              // converted in BOTH CTAs
+                tc_fence_after();
+                const uint32_t g_hi = smem_u32(op_base + (size_t)s * stage_bytes);
+                const uint32_t g_lo = g_hi + kTGTile;
+                const uint32_t a_hi = g_lo + kTGTile;
+                const uint32_t a_lo = a_hi + a_tile_bytes;
+#pragma unroll
+                for (int j = 0; j < kTBV / 16; ++j) {
+                    const uint64_t dgh = make_desc(g_hi + j * 2 * kTLbo, kTLbo, kTSbo);
+                    const uint64_t dgl = make_desc(g_lo + j * 2 * kTLbo, kTLbo, kTSbo);
+                    const uint64_t dah = make_desc(a_hi + j * 2 * kTLbo, kTLbo, kTSbo);
+                    const uint64_t dal = make_desc(a_lo + j * 2 * kTLbo, kTLbo, kTSbo);
+                    umma_f16_pair(d_tmem, dgl, dah, idesc, (in_seg | j) ? 1u : 0u);
+                    umma_f16_pair(d_tmem, dgh, dal, idesc, 1u);
+                    umma_f16_pair(d_tmem, dgh, dah, idesc, 1u);
+                }
+                umma_commit_pair(&empty[s]);
+                if (in_seg == kTSegChunks - 1 || it == chunks - 1) umma_commit_pair(&tfull[acc]);
+                if (++s == (uint32_t)t.stages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        // drain warps: TMEM lane quarter = warp % 4 (this CTA's 128 rows of D, all bk columns); running total in the partial tile
+        const int quarter = warp & 3;
+        float* out = t.partial + (int64_t)blockIdx.y * t.n * t.k;
+        const int kcols = min(t.bk, t.k - k0);
+        float* stg = reinterpret_cast<float*>(op_base + (size_t)t.stages * stage_bytes + 256) + quarter * 32 * kHEpiLd;
+        const int cc = (lane & 7) * 4;
+        const uint64_t keep_policy = l2_policy_evict_last();             // the running partial tile stays in L2 between segments
+        float* const orow = out + (int64_t)(n0 + quarter * 32 + (lane >> 3)) * t.k + k0 + cc;
+        if (segments == 0) {
+            for (int c0 = 0; c0 < kcols; c0 += 32)
+                if (c0 + cc < kcols)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) __stcg(reinterpret_cast<float4*>(orow + (int64_t)(4 * i) * t.k + c0), make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+        for (int seg = 0; seg < segments; ++seg) {
+            const int acc = seg & 1;
+            mbar_wait(&tfull[acc], (seg >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * t.acc_stride);
+            for (int c0 = 0; c0 < kcols; c0 += 32) {
+                float v[32];
+                tmem_ld_32x32(taddr + (uint32_t)c0, v);          // lane = row of D, registers = 32 consecutive columns
+#pragma unroll
+                for (int e = 0; e < 32; e += 4)
+                    *reinterpret_cast<float4*>(stg + lane * kHEpiLd + e) =
+                        make_float4((v[e] * invg) * inva, (v[e + 1] * invg) * inva, (v[e + 2] * invg) * inva, (v[e + 3] * invg) * inva);
+                __syncwarp();
+                if (c0 + cc < kcols) {                           // kcols is a multiple of 32 here (k % 32 == 0)
+                    float4 old[8];
+                    if (seg != 0) {                              // all eight loads in flight before the first add
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) old[i] = ldcg_hint(reinterpret_cast<const float4*>(orow + (int64_t)(4 * i) * t.k + c0), keep_policy);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float4 o = *reinterpret_cast<const float4*>(stg + (i * 4 + (lane >> 3)) * kHEpiLd + cc);
+                        if (seg != 0) { o.x += old[i].x; o.y += old[i].y; o.z += old[i].z; o.w += old[i].w; }
+                        stcg_hint(reinterpret_cast<float4*>(orow + (int64_t)(4 * i) * t.k + c0), o, keep_policy);
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tempty[acc], 0);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                          // neither CTA may free its TMEM (or exit) while the pair's MMAs can still touch it
+    if (warp == kPWarpMma) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, t.tmem_cols);
     }
 }
 
@@ -969,6 +1211,87 @@ int gemm_tn_f16_launch(const float* g, int64_t ldg, const float* a, int64_t lda,
     dim3 grid((unsigned)(p.n_tiles * p.k_tiles), (unsigned)p.splits);
     k_gemm_tn_f16<<<grid, kTThreads, p.smem_bytes, stream>>>(t);
     SGB_CHECK_LAUNCH("k_gemm_tn_f16");
+    return reduce_splits_launch(partial, p.splits, n, k, d, ldd, accumulate, stream);
+}
+
+// ---- weight gradient on CTA pairs ----
+bool gemm_tn_pair_ok(int64_t m, int n, int k) { return n % 256 == 0 && k % 32 == 0 && (k <= 256 || k % 256 == 0) && m >= 4096; }
+
+struct PPlan {
+    int bk, ah, k_tiles, pairs, stages, raw_stages, splits, acc_stride;
+    int64_t m_per_split;
+    size_t smem_bytes, ws_bytes;
+    uint32_t tmem_cols;
+};
+
+static PPlan p_plan(int64_t m, int n, int k) {
+    PPlan p;
+    p.bk = k <= 256 ? k : 256;
+    p.ah = p.bk / 2;
+    p.k_tiles = k / p.bk;
+    p.pairs = (n / 256) * p.k_tiles;
+    const int sb = 2 * kTGTile + 2 * t_a_tile_bytes(p.ah);
+    const int raw = (kTBV * (kTBM + p.ah) * 4 + 127) / 128 * 128;
+    p.raw_stages = 3;
+    if (const char* e = getenv("SGB_PAIR_RAW")) { int v = atoi(e); if (v >= 2 && v <= kPMaxRawStages) p.raw_stages = v; }
+    int st = (kHSmemBudget - 256 - kTEpiBytes - p.raw_stages * raw) / sb;
+    p.stages = st > kHMaxStages ? kHMaxStages : st;
+    p.smem_bytes = (size_t)p.raw_stages * raw + (size_t)p.stages * sb + 256 + kTEpiBytes;
+    int64_t want = num_sms() / (2 * p.pairs);
+    if (want < 1) want = 1;
+    const int64_t maxs = ceil_div(m > 0 ? m : 1, 1024);
+    p.splits = (int)(want < maxs ? want : maxs);
+    p.m_per_split = ceil_div(ceil_div(m, p.splits), kTBV) * kTBV;
+    p.ws_bytes = (size_t)p.splits * n * k * sizeof(float) + 512;
+    p.acc_stride = (p.bk + 31) / 32 * 32;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * p.acc_stride)) cols <<= 1;
+    p.tmem_cols = cols;
+    return p;
+}
+
+size_t gemm_tn_pair_workspace(int64_t m, int n, int k) { return gemm_tn_pair_ok(m, n, k) ? p_plan(m, n, k).ws_bytes : 0; }
+
+int gemm_tn_pair_launch(const float* g, int64_t ldg, const float* a, int64_t lda, const float* g_amax, const float* a_amax, float* d,
+                        int64_t ldd, int64_t m, int n, int k, int accumulate, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    PPlan p = p_plan(m, n, k);
+    if (!ws || ws_bytes < p.ws_bytes) {
+        set_error("sgb_gemm_tn: pair engine needs %zu bytes of workspace, got %zu", p.ws_bytes, ws_bytes);
+        return SGB_ENOSPC;
+    }
+    if (p.stages < 2) {
+        set_error("sgb_gemm_tn: pair tile does not fit shared memory");
+        return SGB_ENOTSUP;
+    }
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    float* hdr = reinterpret_cast<float*>(base);
+    float* partial = reinterpret_cast<float*>(base + 256);
+    if (!g_amax) {
+        int rc = amax_launch(g, ldg, m, n, reinterpret_cast<uint32_t*>(hdr + 0), stream);
+        if (rc != SGB_OK) return rc;
+        g_amax = hdr + 0;
+    }
+    if (!a_amax) {
+        int rc = amax_launch(a, lda, m, k, reinterpret_cast<uint32_t*>(hdr + 1), stream);
+        if (rc != SGB_OK) return rc;
+        a_amax = hdr + 1;
+    }
+    {
+        static std::atomic<uint64_t> optin{0};
+        int rc = smem_optin(reinterpret_cast<const void*>(k_gemm_tn_f16_pair), kHSmemBudget, &optin);
+        if (rc != SGB_OK) return rc;
+    }
+    TPArgs t{};
+    {
+        int rc = make_tmap_2d(&t.g_map, g, m, n, ldg, kTBM, kTBV, false);
+        if (rc == SGB_OK) rc = make_tmap_2d(&t.a_map, a, m, k, lda, p.ah, kTBV, false);
+        if (rc != SGB_OK) return rc;
+    }
+    t.ah = p.ah; t.g_amax = g_amax; t.a_amax = a_amax; t.partial = partial; t.m = m; t.n = n; t.k = k;
+    t.bk = p.bk; t.k_tiles = p.k_tiles; t.stages = p.stages; t.raw_stages = p.raw_stages; t.m_per_split = p.m_per_split; t.tmem_cols = p.tmem_cols; t.acc_stride = p.acc_stride;
+    dim3 grid((unsigned)(2 * p.pairs), (unsigned)p.splits);
+    k_gemm_tn_f16_pair<<<grid, kPThreads, p.smem_bytes, stream>>>(t);
+    SGB_CHECK_LAUNCH("k_gemm_tn_f16_pair");
     return reduce_splits_launch(partial, p.splits, n, k, d, ldd, accumulate, stream);
 }
 

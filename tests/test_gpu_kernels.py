@@ -464,3 +464,21 @@ def test_input_prep_bit_identical_to_the_reference_ops():
         assert_bit_equal(got, want, f"input_prep n={n}")
         ones = ops.input_prep(z1.to(DEV), None)
         assert_bit_equal(ones, torch.cat([(z1 - zc) / z_sc, torch.ones(n, 1)], dim=1), f"input_prep (no mask) n={n}")
+
+
+PAIR_SHAPES = [(100000, 256, 256), (65537, 512, 256), (40000, 256, 512), (20011, 256, 128), (9000, 256, 32), (33000, 512, 96)]
+
+
+@pytest.mark.parametrize("m,n,k", PAIR_SHAPES)
+def test_gemm_tn_pair_engine(m, n, k):
+    """Weight gradient on CTA pairs (cta_group::2, engine=4): same accuracy / determinism bar as the single-CTA engines."""
+    ops = _ops()
+    gen = torch.Generator().manual_seed(m + n + k)
+    g = torch.randn(m, n, generator=gen) * 1e-3
+    a = torch.randn(m, k, generator=gen)
+    want = g.double().t() @ a.double()
+    got = ops.gemm_tn(g.to(DEV), a.to(DEV), engine=4)
+    assert_close(got, want, 1e-5, f"gemm_tn pair engine {m}x{n}x{k}")
+    assert torch.equal(got, ops.gemm_tn(g.to(DEV), a.to(DEV), engine=4)), "must be deterministic"
+    acc = ops.gemm_tn(g.to(DEV), a.to(DEV), out=got.clone(), accumulate=True, engine=4)
+    assert_close(acc, 2 * want, 1e-5, "accumulate")
