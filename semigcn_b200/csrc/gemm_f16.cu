@@ -124,10 +124,8 @@ constexpr int kHWarpMma = kHWarpB + 1;                 // MMA issuer, TMEM owner
 constexpr int kHWarpLoad = kHWarpB + 2;                // A TMA loader
 constexpr int kHThreads = (kHWarpLoad + 1) * 32;       // 480
 constexpr int kHRawBytes = kHBM * kHBK * 4;     // one raw A stage: 128 rows x 32 fp32, 128-byte rows, TMA 128B swizzle
-#ifndef SGB_F16_RAW_STAGES
-#define SGB_F16_RAW_STAGES 3
-#endif
-constexpr int kHRawStages = SGB_F16_RAW_STAGES;
+constexpr int kHMaxRawStages = 6;               // raw fp32 A stages in flight (runtime: HArgs::raw_stages)
+constexpr int kHBarBytes = 512;                 // forward kernel: barrier block between the operand ring and the epilogue staging
 constexpr int kHMaxStages = 6;
 constexpr int kHEpiLd = 36;                     // weight-gradient kernel: floats per row of a drain warp's 32 x 32 staging tile (+4: conflict-free)
 constexpr int kHEpiBytes = kHEpiWarps * 32 * 32 * 4;  // forward kernel: dense 32 x 32 tiles, 16-byte chunks XOR-swizzled by the row (conflict-free both ways)
@@ -136,6 +134,8 @@ static const int kHSmemBudget = 227 * 1024;
 
 __host__ __device__ constexpr int h_b_tile_bytes(int bn) { return (bn / 8) * kHBSbo; }
 __host__ __device__ constexpr int h_stage_bytes(int bn) { return (2 * kHATile + 2 * h_b_tile_bytes(bn) + 1023) / 1024 * 1024; }
+// CTA pairs (cta_group::2): each CTA stages its own 128 rows of A and HALF of the weight tile (bn / 2 rows of B, hi and lo)
+__host__ __device__ constexpr int h_stage_bytes_pair(int bn) { return (2 * kHATile + h_b_tile_bytes(bn) + 1023) / 1024 * 1024; }
 
 struct HArgs {
     CUtensorMap a_map;                // A as a [m, k] fp32 tensor, box {32, 128}, 128-byte swizzle
@@ -145,7 +145,7 @@ struct HArgs {
     const float* a_amax;              // device scalar: max |A|
     float* c; int64_t ldc;
     int64_t m; int n; int k;
-    int bn; int n_tiles; int k_chunks; int stages;
+    int bn; int n_tiles; int k_chunks; int stages; int raw_stages;
     const float* bias; int accumulate;
     float* stat_partials;             // optional BatchNorm partials of C: [4 * gridDim.x / n_tiles][3][n] (count, mean, M2), one row per epilogue warp
     uint32_t tmem_cols; int acc_stride;
@@ -278,50 +278,72 @@ __device__ __forceinline__ void h_epi_chunk(const HArgs& g, uint32_t taddr, floa
     __syncwarp();                            // the staging tile is free for the next chunk
 }
 
+// PAIR: the kernel runs as clusters of two CTAs (launch attribute) on UMMA M = 256: CTA r of a pair owns the m-tile 2 u + r of its
+// unit's tile pair u and the B rows [r ncols / 2, + ncols / 2) of the n-tile; the tensor cores exchange the B halves, so a stage
+// costs each SM 16 KB less weight copy and 24 KB less operand reads (the kernel is bound by the shared-memory data pipe).  The
+// leader (cluster rank 0) issues the MMAs and owns full[] / tempty[]; commits arrive on empty[] / tfull[] of both CTAs.
+template <bool PAIR>
 __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant__ HArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int stage_bytes = h_stage_bytes(g.bn);
-    const int b_tile_bytes = h_b_tile_bytes(g.bn);
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int stage_bytes = PAIR ? h_stage_bytes_pair(g.bn) : h_stage_bytes(g.bn);
+    const int b_tile_bytes = h_b_tile_bytes(g.bn);                       // one full hi (or lo) weight tile of the global image
+    const int b_smem_bytes = PAIR ? b_tile_bytes / 2 : b_tile_bytes;     // what this CTA stages of it
     const uint32_t stages = (uint32_t)g.stages;
-    // smem: [raw ring: kHRawStages x 16 KB][operand ring: stages x stage_bytes][barriers 256 B][epilogue staging: 8 x 4.5 KB]
+    // smem: [raw ring: raw_stages x 16 KB][operand ring: stages x stage_bytes][barriers 512 B][epilogue staging: 8 x 4 KB]
     uint8_t* const raw_base = smem;
-    uint8_t* const op_base = smem + kHRawStages * kHRawBytes;
+    const uint32_t raw_stages = (uint32_t)g.raw_stages;
+    uint8_t* const op_base = smem + raw_stages * kHRawBytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(op_base + (size_t)g.stages * stage_bytes);
     uint64_t* empty = full + kHMaxStages;
     uint64_t* tfull = empty + kHMaxStages;
     uint64_t* tempty = tfull + 2;
     uint64_t* rfull = tempty + 2;               // raw stage landed (TMA complete_tx)
-    uint64_t* rempty = rfull + kHRawStages;     // raw stage consumed by all converter threads
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + kHRawStages);
+    uint64_t* rempty = rfull + kHMaxRawStages;  // raw stage consumed by all converter threads
+    uint64_t* bfull = rempty + kHMaxRawStages;  // PAIR: this CTA's half of the weight tile landed (bulk copy complete_tx)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + kHMaxStages);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; ++s) {
-            mbar_init(&full[s], kHConvWarps * 32 / 2 + 1);        // one converter group (64 threads) + the B copy's expect_tx arrive
+            // single CTA: one converter group (64 threads) + the B copy's expect_tx arrive;  PAIR: one elected lane per warp of the
+            // stage's converter group, in both CTAs (each arrives once its CTA's A tile is converted AND its B half has landed)
+            mbar_init(&full[s], PAIR ? 2 * (kHConvWarps / 2) : kHConvWarps * 32 / 2 + 1);
             mbar_init(&empty[s], 1);
+            mbar_init(&bfull[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull[b], 1);
-            mbar_init(&tempty[b], kHEpiWarps);
+            mbar_init(&tempty[b], PAIR ? 2 * kHEpiWarps : kHEpiWarps);
         }
-        for (int s = 0; s < kHRawStages; ++s) {
+        for (uint32_t s = 0; s < raw_stages; ++s) {
             mbar_init(&rfull[s], 1);
             mbar_init(&rempty[s], kHConvWarps * 32 / 2);
         }
         fence_barrier_init();
     }
-    if (warp == kHWarpMma) tmem_alloc(tmem_slot, g.tmem_cols);
+    if (PAIR) {
+        __syncthreads();
+        cluster_sync_all();                     // both CTAs' barriers exist before anyone arrives remotely
+        if (warp == kHWarpMma) tmem_alloc_pair(tmem_slot, g.tmem_cols);
+    } else {
+        if (warp == kHWarpMma) tmem_alloc(tmem_slot, g.tmem_cols);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int64_t m_tiles = (g.m + kHBM - 1) / kHBM;
-    const int64_t total_tiles = m_tiles * g.n_tiles;
-    // tiles blockIdx.x, + gridDim.x, ...; gridDim.x is a multiple of n_tiles, so the n-tile of a CTA never changes.
+    // A unit (a CTA, or a CTA pair) works on the tiles unit, + units, ... of the (m-tile or m-tile pair) x n-tile grid; the number
+    // of units is a multiple of n_tiles, so the n-tile of a unit never changes.  m0_of(tile): first row of THIS CTA's m-tile.
     // All ring positions / phases below are carried incrementally (no per-iteration division by a runtime stage count).
-    const uint32_t my_tiles = total_tiles > blockIdx.x ? (uint32_t)((total_tiles - 1 - blockIdx.x) / gridDim.x + 1) : 0u;
+    const uint32_t unit = PAIR ? blockIdx.x >> 1 : blockIdx.x, units = PAIR ? gridDim.x >> 1 : gridDim.x;
+    const int64_t m_tiles = (g.m + kHBM - 1) / kHBM;
+    const int64_t total_tiles = (PAIR ? (m_tiles + 1) / 2 : m_tiles) * g.n_tiles;
+    const uint32_t my_tiles = total_tiles > unit ? (uint32_t)((total_tiles - 1 - unit) / units + 1) : 0u;
     const uint32_t k_chunks = (uint32_t)g.k_chunks;
+    const int nt = (int)(unit % (uint32_t)g.n_tiles);
+#define SGB_H_M0_OF(tile) ((PAIR ? ((tile) / g.n_tiles) * 2 + (int64_t)rank : (tile) / g.n_tiles) * kHBM)
 
     if (warp < kHConvWarps) {
         // ================= A converters: raw fp32 stage (TMA) -> regs (scale, hi/lo fp16) -> operand stage =================
@@ -345,9 +367,9 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
         constexpr int HALF = RPT / 2;
         const uint32_t total_it = my_tiles * k_chunks;
         uint32_t s = (uint32_t)grp % stages, ph = ((uint32_t)grp / stages) & 1u;
-        uint32_t rs = (uint32_t)grp % (uint32_t)kHRawStages, rph = ((uint32_t)grp / (uint32_t)kHRawStages) & 1u;
+        uint32_t rs = (uint32_t)grp % raw_stages, rph = ((uint32_t)grp / raw_stages) & 1u;
         for (uint32_t it = (uint32_t)grp; it < total_it; it += GROUPS) {
-            // The previous user of this raw slot (stage it - kHRawStages) is the OTHER group when the ring length is odd, and
+            // The previous user of this raw slot (stage it - raw_stages) is the OTHER group when the ring length is odd, and
             // TMA completions are not ordered: without this wait a group that runs ahead could test rfull[rs] while the slot's
             // previous phase has not even completed -- the parity test would alias (phase p - 1 incomplete looks like phase p
             // complete) and the group would convert stale data and release the slot twice.  rempty[rs] completes only after the
@@ -390,20 +412,28 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
                 *reinterpret_cast<uint4*>(a_lo + off) = l[i];
             }
             fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            mbar_arrive(&full[s]);
+            if (PAIR) {
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_wait(&bfull[s], ph);                 // this CTA's B half is in place as well (bfull[s] cannot run ahead: its next copy needs empty[s])
+                    mbar_arrive_cluster(&full[s], 0);
+                }
+            } else {
+                mbar_arrive(&full[s]);
+            }
             s += GROUPS;
             if (s >= stages) { s -= stages; ph ^= 1; }
             rs += GROUPS;
-            if (rs >= (uint32_t)kHRawStages) { rs -= (uint32_t)kHRawStages; rph ^= 1; }
+            if (rs >= raw_stages) { rs -= raw_stages; rph ^= 1; }
         }
     } else if (warp == kHWarpLoad) {
         // ================= A loader: one lane streams the raw A tiles (TMA 2-D, 128B swizzle, zero fill past m / k) =================
         if (lane == 0) {
             tma_prefetch_desc(&g.a_map);
             uint32_t rs = 0, rph = 0;
-            int64_t tile = blockIdx.x;
-            for (uint32_t t = 0; t < my_tiles; ++t, tile += gridDim.x) {
-                const int m0 = (int)((tile / g.n_tiles) * kHBM);
+            int64_t tile = unit;
+            for (uint32_t t = 0; t < my_tiles; ++t, tile += units) {
+                const int m0 = (int)SGB_H_M0_OF(tile);
                 for (uint32_t q = 0; q < k_chunks; ++q) {
                     mbar_wait(&rempty[rs], rph ^ 1);
                     if (SGB_ABL & SGB_ABL_NO_TMA) { mbar_arrive(&rfull[rs]); }
@@ -411,21 +441,28 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
                         mbar_arrive_expect_tx(&rfull[rs], kHRawBytes);
                         tma_load_2d(raw_base + (size_t)rs * kHRawBytes, &g.a_map, (int)(q * kHBK), m0, &rfull[rs]);
                     }
-                    if (++rs == (uint32_t)kHRawStages) { rs = 0; rph ^= 1; }
+                    if (++rs == raw_stages) { rs = 0; rph ^= 1; }
                 }
             }
         }
     } else if (warp == kHWarpB) {
         // ================= B copy: one bulk copy of the pre-tiled hi|lo weight image per stage =================
         if (lane == 0) {
-            const int nt = (int)(blockIdx.x % g.n_tiles);
             const uint8_t* src0 = g.wp + (size_t)nt * g.k_chunks * 2 * b_tile_bytes;
+            // PAIR: rows [rank ncols / 2, + ncols / 2) of the hi and of the lo tile (whole 8-row core-matrix rows, contiguous in the image)
+            const int ncols = min(g.bn, g.n - nt * g.bn);
+            const uint32_t half_bytes = (uint32_t)(ncols / 16) * kHBSbo;
+            const uint8_t* src_half = src0 + (size_t)rank * half_bytes;
             uint32_t s = 0, ph = 0;
             for (uint32_t t = 0; t < my_tiles; ++t) {
                 for (uint32_t q = 0; q < k_chunks; ++q) {
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* b_dst = op_base + (size_t)s * stage_bytes + 2 * kHATile;
-                    if ((SGB_ABL & SGB_ABL_NO_BCOPY) && (t * k_chunks + q) >= stages) { mbar_arrive(&full[s]); }
+                    if (PAIR) {
+                        mbar_arrive_expect_tx(&bfull[s], 2 * half_bytes);
+                        bulk_g2s(b_dst, src_half + (size_t)q * 2 * b_tile_bytes, half_bytes, &bfull[s]);
+                        bulk_g2s(b_dst + b_smem_bytes, src_half + (size_t)q * 2 * b_tile_bytes + b_tile_bytes, half_bytes, &bfull[s]);
+                    } else if ((SGB_ABL & SGB_ABL_NO_BCOPY) && (t * k_chunks + q) >= stages) { mbar_arrive(&full[s]); }
                     else {
                         mbar_arrive_expect_tx(&full[s], 2 * b_tile_bytes);
                         bulk_g2s(b_dst, src0 + (size_t)q * 2 * b_tile_bytes, 2 * b_tile_bytes, &full[s]);
@@ -436,23 +473,24 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
         }
     } else if (warp == kHWarpMma) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            const int nt = (int)(blockIdx.x % g.n_tiles);
+        if (lane == 0 && rank == 0) {
             const int ncols = min(g.bn, g.n - nt * g.bn);                     // multiple of 16
-            const uint32_t idesc = make_idesc_f16(kHBM, ncols, 0, 0);
+            const uint32_t idesc = make_idesc_f16(PAIR ? 2 * kHBM : kHBM, ncols, 0, 0);
             uint32_t s = 0, ph = 0;
             for (uint32_t tcount = 0; tcount < my_tiles; ++tcount) {
                 const uint32_t acc = tcount & 1;
-                mbar_wait(&tempty[acc], ((tcount >> 1) & 1) ^ 1);
+                if (PAIR) mbar_wait_cluster(&tempty[acc], ((tcount >> 1) & 1) ^ 1);      // drained in BOTH CTAs
+                else mbar_wait(&tempty[acc], ((tcount >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)g.acc_stride;
                 for (uint32_t q = 0; q < k_chunks; ++q) {
-                    mbar_wait(&full[s], ph);
+                    if (PAIR) mbar_wait_cluster(&full[s], ph);                           // converted / landed in BOTH CTAs
+                    else mbar_wait(&full[s], ph);
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(op_base + (size_t)s * stage_bytes);
                     const uint32_t a_lo = a_hi + kHATile;
                     const uint32_t b_hi = a_hi + 2 * kHATile;
-                    const uint32_t b_lo = b_hi + b_tile_bytes;
+                    const uint32_t b_lo = b_hi + b_smem_bytes;
 #pragma unroll
                     for (int j = 0; j < ((SGB_ABL & SGB_ABL_NO_MMA) ? 0 : kHBK / 16); ++j) {
                         const uint64_t dah = make_desc(a_hi + j * 2 * kHALbo, kHALbo, kHASbo);
@@ -460,14 +498,22 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
                         const uint64_t dbh = make_desc(b_hi + j * 2 * kHBLbo, kHBLbo, kHBSbo);
                         const uint64_t dbl = make_desc(b_lo + j * 2 * kHBLbo, kHBLbo, kHBSbo);
                         // small terms first, the dominant hi*hi product last
-                        umma_f16(d_tmem, dal, dbh, idesc, (q | (uint32_t)j) ? 1u : 0u);
-                        umma_f16(d_tmem, dah, dbl, idesc, 1u);
-                        umma_f16(d_tmem, dah, dbh, idesc, 1u);
+                        if (PAIR) {
+                            umma_f16_pair(d_tmem, dal, dbh, idesc, (q | (uint32_t)j) ? 1u : 0u);
+                            umma_f16_pair(d_tmem, dah, dbl, idesc, 1u);
+                            umma_f16_pair(d_tmem, dah, dbh, idesc, 1u);
+                        } else {
+                            umma_f16(d_tmem, dal, dbh, idesc, (q | (uint32_t)j) ? 1u : 0u);
+                            umma_f16(d_tmem, dah, dbl, idesc, 1u);
+                            umma_f16(d_tmem, dah, dbh, idesc, 1u);
+                        }
                     }
-                    umma_commit(&empty[s]);          // frees the smem slot when the MMAs above have read it
+                    if (PAIR) umma_commit_pair(&empty[s]);       // frees the smem slot (in both CTAs) when the MMAs above have read it
+                    else umma_commit(&empty[s]);
                     if (++s == stages) { s = 0; ph ^= 1; }
                 }
-                umma_commit(&tfull[acc]);            // accumulator complete
+                if (PAIR) umma_commit_pair(&tfull[acc]);         // accumulator complete
+                else umma_commit(&tfull[acc]);
             }
         }
     } else {
@@ -483,20 +529,19 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
         const int ew = warp - kHConvWarps;           // 0..7
         const int quarter = warp & 3;                // TMEM lanes 32*quarter .. +31 are accessible to this warp
         const int half = ew >> 2;                    // chunks half, half + 2, half + 4, half + 6 of the n-tile
-        float* stg = reinterpret_cast<float*>(op_base + (size_t)g.stages * stage_bytes + 256) + ew * 32 * 32;
+        float* stg = reinterpret_cast<float*>(op_base + (size_t)g.stages * stage_bytes + kHBarBytes) + ew * 32 * 32;
         const int grp = lane >> 3;                   // row group of the transposed read-back: rows grp, grp + 4, ...
         const int cc = (lane & 7) * 4;               // this lane's float4 inside a 32-column chunk
         const bool stats = g.stat_partials != nullptr;
-        const int nt = (int)(blockIdx.x % g.n_tiles);
         const int n0 = nt * g.bn;
         const int ncols = min(g.bn, g.n - n0);
         // Running column moments (count, mean, M2) of every row this warp has stored, Chan-merged one 32-row block at a
         // time while the block is still in registers (no second pass over C).  A CTA only ever sees one n-tile, so the
         // count is the same for all of its columns.  Of the warp's four chunks, chunk t is owned by the lanes of row group t.
         float st_mean[4] = {0.f, 0.f, 0.f, 0.f}, st_m2[4] = {0.f, 0.f, 0.f, 0.f}, st_n = 0.f;
-        int64_t tile = blockIdx.x;
-        for (uint32_t tcount = 0; tcount < my_tiles; ++tcount, tile += gridDim.x) {
-            const int64_t m0 = (tile / g.n_tiles) * kHBM;
+        int64_t tile = unit;
+        for (uint32_t tcount = 0; tcount < my_tiles; ++tcount, tile += units) {
+            const int64_t m0 = SGB_H_M0_OF(tile);
             const uint32_t acc = tcount & 1;
             mbar_wait(&tfull[acc], (tcount >> 1) & 1);
             tc_fence_after();
@@ -531,10 +576,14 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
             st_n += nb;
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_cluster(&tempty[acc], 0);
+                else mbar_arrive(&tempty[acc]);
+            }
         }
         if (stats) {
-            float* row = g.stat_partials + ((int64_t)(blockIdx.x / g.n_tiles) * 4 + quarter) * 3 * g.n;
+            const int64_t group = PAIR ? (int64_t)(unit / (uint32_t)g.n_tiles) * 2 + rank : (int64_t)(blockIdx.x / g.n_tiles);
+            float* row = g.stat_partials + (group * 4 + quarter) * 3 * g.n;
             const int c0 = (2 * grp + half) * 32;        // the chunk whose moments this lane holds
             if (c0 + cc < ncols) {
                 st4(row + 0 * (int64_t)g.n + n0 + c0 + cc, make_float4(st_n, st_n, st_n, st_n));
@@ -545,10 +594,13 @@ __global__ void __launch_bounds__(kHThreads, 1) k_gemm_f16(const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();                // neither CTA may free its TMEM (or exit) while the pair's MMAs can still touch it
     if (warp == kHWarpMma) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, g.tmem_cols);
+        if (PAIR) tmem_dealloc_pair(tmem_base, g.tmem_cols);
+        else tmem_dealloc(tmem_base, g.tmem_cols);
     }
+#undef SGB_H_M0_OF
 }
 
 // fixed-order split reduction -- gemm_tc.cu
@@ -1056,21 +1108,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPThreads, 1) k_gemm
 // host side
 // ------------------------------------------------------------------------------------------
 struct HPlan {
-    int bn, n_tiles, k_chunks, stages, acc_stride;
+    int bn, n_tiles, k_chunks, stages, raw_stages, acc_stride;
     size_t smem_bytes, img_bytes;
     uint32_t tmem_cols;
+    bool pair;
 };
 
-static HPlan h_plan(int n, int k) {
+// CTA pairs: every n-tile must split into two halves of whole core-matrix rows (ncols % 16 == 0), and there must be enough
+// m-tiles to keep 74 pairs busy; SGB_F16_PAIR=0 / 1 overrides (experiments)
+static bool h_pair_wanted(int64_t m, int n) {
+    if (const char* e = getenv("SGB_F16_PAIR")) return atoi(e) != 0 && n % 16 == 0 && n >= 32;
+    return n % 32 == 0 && n >= 128 && m >= 32768;
+}
+
+static HPlan h_plan(int n, int k, bool pair = false) {
     HPlan p;
+    p.pair = pair;
     p.bn = n <= 256 ? n : 256;
     p.n_tiles = (n + p.bn - 1) / p.bn;
     p.k_chunks = (k + kHBK - 1) / kHBK;
-    int sb = h_stage_bytes(p.bn);
-    int st = (kHSmemBudget - 256 - kHEpiBytes - kHRawStages * kHRawBytes - 1024) / sb;
+    int sb = pair ? h_stage_bytes_pair(p.bn) : h_stage_bytes(p.bn);
+    p.raw_stages = 3;
+    if (const char* e = getenv("SGB_F16_RAW")) { int v = atoi(e); if (v >= 2 && v <= kHMaxRawStages) p.raw_stages = v; }
+    int st = (kHSmemBudget - kHBarBytes - kHEpiBytes - p.raw_stages * kHRawBytes - 1024) / sb;
     p.stages = st > kHMaxStages ? kHMaxStages : st;
     if (const char* e = getenv("SGB_F16_STAGES")) { int v = atoi(e); if (v >= 2 && v <= p.stages) p.stages = v; }
-    p.smem_bytes = (size_t)kHRawStages * kHRawBytes + (size_t)p.stages * sb + 256 + kHEpiBytes;
+    p.smem_bytes = (size_t)p.raw_stages * kHRawBytes + (size_t)p.stages * sb + kHBarBytes + kHEpiBytes;
     p.img_bytes = (size_t)p.n_tiles * p.k_chunks * 2 * h_b_tile_bytes(p.bn);
     p.acc_stride = (p.bn + 31) / 32 * 32;
     uint32_t cols = 32;
@@ -1083,7 +1146,7 @@ static HPlan h_plan(int n, int k) {
 size_t gemm_f16_workspace(int n, int k) { return h_plan(n, k).img_bytes + 512; }
 
 int gemm_f16_launch(const GemmArgs& g, const float* a_amax, void* ws, size_t ws_bytes, cudaStream_t stream) {
-    HPlan p = h_plan(g.n, g.k);
+    HPlan p = h_plan(g.n, g.k, h_pair_wanted(g.m, g.n));
     if (!ws || ws_bytes < p.img_bytes + 512) {
         set_error("sgb_gemm: fp16-split engine needs %zu bytes of workspace, got %zu", p.img_bytes + 512, ws_bytes);
         return SGB_ENOSPC;
@@ -1103,8 +1166,9 @@ int gemm_f16_launch(const GemmArgs& g, const float* a_amax, void* ws, size_t ws_
     k_prep_weights_f16<<<num_sms(), 256, 0, stream>>>(g.b, g.ldb, g.transb, g.n, g.k, p.bn, p.n_tiles, p.k_chunks, reinterpret_cast<__half*>(img), hdr);
     SGB_CHECK_LAUNCH("k_prep_weights_f16");
     {
-        static std::atomic<uint64_t> optin{0};
-        int rc = smem_optin(reinterpret_cast<const void*>(k_gemm_f16), kHSmemBudget, &optin);
+        static std::atomic<uint64_t> optin{0}, optin_pair{0};
+        int rc = p.pair ? smem_optin(reinterpret_cast<const void*>(k_gemm_f16<true>), kHSmemBudget, &optin_pair)
+                        : smem_optin(reinterpret_cast<const void*>(k_gemm_f16<false>), kHSmemBudget, &optin);
         if (rc != SGB_OK) return rc;
     }
     HArgs t{};
@@ -1113,7 +1177,7 @@ int gemm_f16_launch(const GemmArgs& g, const float* a_amax, void* ws, size_t ws_
         if (rc != SGB_OK) return rc;
     }
     t.a = g.a; t.lda = g.lda; t.wp = img; t.wscale = hdr; t.a_amax = a_amax; t.c = g.c; t.ldc = g.ldc; t.m = g.m; t.n = g.n; t.k = g.k;
-    t.bn = p.bn; t.n_tiles = p.n_tiles; t.k_chunks = p.k_chunks; t.stages = p.stages;
+    t.bn = p.bn; t.n_tiles = p.n_tiles; t.k_chunks = p.k_chunks; t.stages = p.stages; t.raw_stages = p.raw_stages;
     t.bias = g.bias; t.accumulate = g.accumulate; t.stat_partials = g.stat_partials; t.tmem_cols = p.tmem_cols; t.acc_stride = p.acc_stride;
     // grid = (m-tile groups) x n_tiles, a multiple of n_tiles: CTA b always works on n-tile b % n_tiles (its BatchNorm
     // moments then cover one fixed column range) and on the m-tiles b / n_tiles, + groups, ...
@@ -1121,6 +1185,11 @@ int gemm_f16_launch(const GemmArgs& g, const float* a_amax, void* ws, size_t ws_
     int groups = num_sms() / p.n_tiles;
     if (groups < 1) groups = 1;
     if (groups > m_tiles) groups = (int)m_tiles;
+    if (p.pair) groups = groups / 2 * 2;         // pairs: CTAs 2 u, 2 u + 1 form unit u; the CTA's moment-row group is 2 (u / n_tiles) + rank
+    if (p.pair && groups < 2) {
+        set_error("sgb_gemm: too few rows for CTA pairs");
+        return SGB_ENOTSUP;
+    }
     const int grid = groups * p.n_tiles;
     if (g.stat_partials) {
         SGB_CHECK_ARG((reinterpret_cast<uintptr_t>(g.stat_partials) & 15) == 0, "sgb_gemm: stat_partials must be 16-byte aligned");
@@ -1128,7 +1197,21 @@ int gemm_f16_launch(const GemmArgs& g, const float* a_amax, void* ws, size_t ws_
         if (rows > written)
             SGB_CUDA(cudaMemsetAsync(g.stat_partials + (size_t)written * 3 * g.n, 0, (size_t)(rows - written) * 3 * g.n * sizeof(float), stream));
     }
-    k_gemm_f16<<<grid, kHThreads, p.smem_bytes, stream>>>(t);
+    if (p.pair) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(kHThreads);
+        cfg.dynamicSmemBytes = p.smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        SGB_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_f16<true>, t));
+    } else {
+        k_gemm_f16<false><<<grid, kHThreads, p.smem_bytes, stream>>>(t);
+    }
     SGB_CHECK_LAUNCH("k_gemm_f16");
     return SGB_OK;
 }

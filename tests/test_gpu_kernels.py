@@ -482,3 +482,32 @@ def test_gemm_tn_pair_engine(m, n, k):
     assert torch.equal(got, ops.gemm_tn(g.to(DEV), a.to(DEV), engine=4)), "must be deterministic"
     acc = ops.gemm_tn(g.to(DEV), a.to(DEV), out=got.clone(), accumulate=True, engine=4)
     assert_close(acc, 2 * want, 1e-5, "accumulate")
+
+
+F16_PAIR_SHAPES = [(100000, 256, 256), (65537, 512, 256), (40001, 256, 512), (33000, 128, 64), (50000, 352, 96), (70001, 32, 16),
+                   (129, 256, 64), (300, 512, 32)]
+
+
+@pytest.mark.parametrize("m,n,k", F16_PAIR_SHAPES)
+@pytest.mark.parametrize("transb", [True, False])
+def test_gemm_f16_split_engine_on_cta_pairs(m, n, k, transb, monkeypatch):
+    """The fp16-split transform on CTA pairs (cta_group::2, UMMA M = 256): forced on with SGB_F16_PAIR=1 for every shape whose
+    n-tiles split into two halves of whole core-matrix rows, compared with fp64 and with the single-CTA kernel (SGB_F16_PAIR=0);
+    odd numbers of m-tiles (the second CTA of the last pair has no rows), partial n-tiles, one tile pair in all."""
+    ops = _ops()
+    torch.manual_seed(m + n + k)
+    a = torch.randn(m, k)
+    b = torch.randn(n, k) if transb else torch.randn(k, n)
+    bias = torch.randn(n)
+    want = a.double() @ (b.double().t() if transb else b.double()) + bias.double()
+    monkeypatch.setenv("SGB_F16_PAIR", "1")
+    got, partials = ops.gemm(a.to(DEV), b.to(DEV), transb=transb, bias=bias.to(DEV), want_stats=True, engine=3)
+    assert_close(got, want, 5e-6, "gemm on CTA pairs")
+    check_moments(partials, got.double().cpu())
+    c0 = torch.randn(m, n)
+    got2 = ops.gemm(a.to(DEV), b.to(DEV), transb=transb, out=c0.to(DEV).clone(), accumulate=True, engine=3)
+    assert_close(got2, want - bias.double() + c0.double(), 5e-6, "accumulate")
+    assert torch.equal(got, ops.gemm(a.to(DEV), b.to(DEV), transb=transb, bias=bias.to(DEV), engine=3)), "must be deterministic"
+    monkeypatch.setenv("SGB_F16_PAIR", "0")
+    single = ops.gemm(a.to(DEV), b.to(DEV), transb=transb, bias=bias.to(DEV), engine=3)
+    assert_close(got, single.double(), 1e-6, "pair vs single CTA")

@@ -13,8 +13,9 @@ def timeit(fn, reps=6, warm=2):
     for _ in range(reps): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
+import os
 out = []
-for (k, n) in ((256, 256), (256, 512), (512, 256), (128, 256), (256, 128), (64, 128)):
+for (k, n) in ((256, 256), (256, 512), (512, 256), (128, 256), (256, 128), (64, 128), (128, 64), (32, 64), (64, 32), (16, 32)):
     a = torch.randn(m, k, device=dev); w = torch.randn(n, k, device=dev); amx = a.abs().max().reshape(1)
     c = torch.empty(m, n, device=dev)
     ms = timeit(lambda: ops.gemm(a, w, engine=3, a_amax=amx, out=c))
