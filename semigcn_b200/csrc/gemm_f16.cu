@@ -38,6 +38,9 @@
 #define SGB_ABL_NO_CONV 8       // converters: only the hand-shakes
 #define SGB_ABL_NO_TMA 16       // A loader: no TMA
 #define SGB_ABL_NO_MMA 32       // MMA issuer: no tcgen05.mma
+#define SGB_ABL_T_NO_MMA 64     // weight-gradient kernels: no tcgen05.mma
+#define SGB_ABL_T_NO_CONV 128   // weight-gradient kernels: converters only do the hand-shakes
+#define SGB_ABL_T_NO_DRAIN 256  // weight-gradient kernels: drain warps only do the hand-shakes
 
 namespace sgb {
 
@@ -618,7 +621,9 @@ constexpr int kTGTile = (kTBM / 8) * kTSbo;      // per hi (or lo)
 constexpr int kTProducerWarps = 12;              // 384 threads: one (8 vertices x 4 columns) item each per stage
 constexpr int kTDrainWarps = 4;
 constexpr int kTThreads = (kTProducerWarps + 1 + kTDrainWarps + 1) * 32;   // converters, MMA, drain, TMA loader
-constexpr int kTRawStages = 2;
+constexpr int kTRawStages = 2;                  // CTA-pair kernel's default is set in its plan; this is the single-CTA minimum
+constexpr int kTMaxRawStages = 8;               // single-CTA kernel: raw (TMA) stages in flight, chosen per shape (TArgs::raw_stages)
+constexpr int kTBarBytes = 512;                 // single-CTA kernel: barrier block between the operand ring and the drain staging
 constexpr int kTSegChunks = 16;                  // 512 vertices per TMEM accumulation segment (tensor-core accumulation truncates)
 
 __host__ __device__ constexpr int t_a_tile_bytes(int bk) { return (bk / 8) * kTSbo; }
@@ -633,7 +638,7 @@ struct TArgs {
     float* partial;                   // [splits][n][k]
     int64_t m; int n; int k;
     int bk;                           // UMMA N: columns of D per CTA (multiple of 16, <= 256)
-    int k_tiles; int stages;
+    int k_tiles; int stages; int raw_stages;
     int64_t m_per_split;              // multiple of kTBV
     uint32_t tmem_cols; int acc_stride;
 };
@@ -643,18 +648,19 @@ __global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stage_bytes = t_stage_bytes(t.bk);
     const int a_tile_bytes = t_a_tile_bytes(t.bk);
-    // smem: [raw ring: kTRawStages x (G box | A box), fp32][operand ring: stages x stage_bytes][barriers]
+    // smem: [raw ring: raw_stages x (G box | A box), fp32][operand ring: stages x stage_bytes][barriers 512 B][drain staging]
     const int raw_g_bytes = kTBV * t.gbox * 4, raw_a_bytes = kTBV * t.abox * 4;
     const int raw_bytes = (raw_g_bytes + raw_a_bytes + 127) / 128 * 128;
     uint8_t* const raw_base = smem;
-    uint8_t* const op_base = smem + (size_t)kTRawStages * raw_bytes;
+    const uint32_t raw_stages = (uint32_t)t.raw_stages;
+    uint8_t* const op_base = smem + (size_t)raw_stages * raw_bytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(op_base + (size_t)t.stages * stage_bytes);
     uint64_t* empty = full + kHMaxStages;
     uint64_t* tfull = empty + kHMaxStages;      // [2]
     uint64_t* tempty = tfull + 2;               // [2]
-    uint64_t* rfull = tempty + 2;               // [kTRawStages]
-    uint64_t* rempty = rfull + kTRawStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + kTRawStages);
+    uint64_t* rfull = tempty + 2;               // [raw_stages]
+    uint64_t* rempty = rfull + kTMaxRawStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + kTMaxRawStages);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < t.stages; ++s) {
@@ -665,7 +671,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const __grid_const
             mbar_init(&tfull[b], 1);
             mbar_init(&tempty[b], kTDrainWarps);
         }
-        for (int s = 0; s < kTRawStages; ++s) {
+        for (uint32_t s = 0; s < raw_stages; ++s) {
             mbar_init(&rfull[s], 1);
             mbar_init(&rempty[s], kTProducerWarps * 32);
         }
@@ -710,7 +716,10 @@ __global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const __grid_const
             mbar_wait(&rfull[rs], rph);
             const uint8_t* raw = raw_base + (size_t)rs * raw_bytes + raw_off;
             uint4 h[4], l[4];
-            if (col_ok) {
+            if (SGB_ABL & SGB_ABL_T_NO_CONV) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { h[q] = make_uint4(0u, 0u, 0u, 0u); l[q] = make_uint4(0u, 0u, 0u, 0u); }
+            } else if (col_ok) {
                 float4 v[8];
 #pragma unroll
                 for (int r = 0; r < 8; ++r) v[r] = *reinterpret_cast<const float4*>(raw + (size_t)r * box * 4);
@@ -731,7 +740,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const __grid_const
             fence_proxy_async();
             mbar_arrive(&rempty[rs]);
             mbar_wait(&empty[s], ph ^ 1);
-            if (in_tile) {
+            if (in_tile && !(SGB_ABL & SGB_ABL_T_NO_CONV)) {
                 uint8_t* st = op_base + (size_t)s * stage_bytes + base_off;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -742,7 +751,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const __grid_const
             fence_proxy_async();
             mbar_arrive(&full[s]);
             if (++s == (uint32_t)t.stages) { s = 0; ph ^= 1; }
-            if (++rs == (uint32_t)kTRawStages) { rs = 0; rph ^= 1; }
+            if (++rs == raw_stages) { rs = 0; rph ^= 1; }
         }
     } else if (warp == kTProducerWarps + 1 + kTDrainWarps) {
         // ================= loader: one lane streams the raw G and A boxes of each 32-vertex stage (TMA 2-D, zero fill) =================
@@ -758,7 +767,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const __grid_const
                 const int row = (int)(ms + (int64_t)it * kTBV);
                 tma_load_2d_hint(dst, &t.g_map, n0, row, &rfull[rs], stream_policy);
                 tma_load_2d_hint(dst + raw_g_bytes, &t.a_map, k0, row, &rfull[rs], stream_policy);
-                if (++rs == (uint32_t)kTRawStages) { rs = 0; rph ^= 1; }
+                if (++rs == raw_stages) { rs = 0; rph ^= 1; }
             }
         }
     } else if (warp == kTProducerWarps) {
@@ -780,7 +789,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const __grid_const
                 const uint32_t a_hi = g_lo + kTGTile;
                 const uint32_t a_lo = a_hi + a_tile_bytes;
 #pragma unroll
-                for (int j = 0; j < kTBV / 16; ++j) {
+                for (int j = 0; j < ((SGB_ABL & SGB_ABL_T_NO_MMA) ? 0 : kTBV / 16); ++j) {
                     const uint64_t dgh = make_desc(g_hi + j * 2 * kTLbo, kTLbo, kTSbo);
                     const uint64_t dgl = make_desc(g_lo + j * 2 * kTLbo, kTLbo, kTSbo);
                     const uint64_t dah = make_desc(a_hi + j * 2 * kTLbo, kTLbo, kTSbo);
@@ -807,13 +816,13 @@ __global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const __grid_const
             if (gn < t.n)
                 for (int c = 0; c < kcols; ++c) out[(int64_t)gn * t.k + k0 + c] = 0.f;
         }
-        float* stg = reinterpret_cast<float*>(op_base + (size_t)t.stages * stage_bytes + 256) + quarter * 32 * kHEpiLd;
+        float* stg = reinterpret_cast<float*>(op_base + (size_t)t.stages * stage_bytes + kTBarBytes) + quarter * 32 * kHEpiLd;
         for (int seg = 0; seg < segments; ++seg) {
             const int acc = seg & 1;
             mbar_wait(&tfull[acc], (seg >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * t.acc_stride);
-            for (int c0 = 0; c0 < kcols; c0 += 32) {
+            for (int c0 = 0; c0 < ((SGB_ABL & SGB_ABL_T_NO_DRAIN) ? 0 : kcols); c0 += 32) {
                 float v[32];
                 tmem_ld_32x32(taddr + (uint32_t)c0, v);          // lane = row of D, registers = 32 consecutive columns
 #pragma unroll
@@ -967,7 +976,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPThreads, 1) k_gemm
             mbar_wait(&rfull[rs], rph);
             const uint8_t* raw = raw_base + (size_t)rs * raw_bytes + raw_off;
             uint4 h[4], l[4];
-            if (in_tile) {
+            if (SGB_ABL & SGB_ABL_T_NO_CONV) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { h[q] = make_uint4(0u, 0u, 0u, 0u); l[q] = make_uint4(0u, 0u, 0u, 0u); }
+            } else if (in_tile) {
                 float4 v[8];
 #pragma unroll
                 for (int r = 0; r < 8; ++r) v[r] = *reinterpret_cast<const float4*>(raw + (size_t)r * box * 4);
@@ -984,7 +996,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPThreads, 1) k_gemm
             fence_proxy_async();                 // the conversion consumed the loaded values: the raw slot may go back to the TMA engine
             mbar_arrive(&rempty[rs]);
             mbar_wait(&empty[s], ph ^ 1);        // multicast commit of the leader's MMAs that read this slot (in BOTH CTAs)
-            if (in_tile) {
+            if (in_tile && !(SGB_ABL & SGB_ABL_T_NO_CONV)) {
                 uint8_t* st = op_base + (size_t)s * stage_bytes + base_off;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -1033,7 +1045,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPThreads, 1) k_gemm
                 const uint32_t a_hi = g_lo + kTGTile;
                 const uint32_t a_lo = a_hi + a_tile_bytes;
 #pragma unroll
-                for (int j = 0; j < kTBV / 16; ++j) {
+                for (int j = 0; j < ((SGB_ABL & SGB_ABL_T_NO_MMA) ? 0 : kTBV / 16); ++j) {
                     const uint64_t dgh = make_desc(g_hi + j * 2 * kTLbo, kTLbo, kTSbo);
                     const uint64_t dgl = make_desc(g_lo + j * 2 * kTLbo, kTLbo, kTSbo);
                     const uint64_t dah = make_desc(a_hi + j * 2 * kTLbo, kTLbo, kTSbo);
@@ -1067,7 +1079,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPThreads, 1) k_gemm
             mbar_wait(&tfull[acc], (seg >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * t.acc_stride);
-            for (int c0 = 0; c0 < kcols; c0 += 32) {
+            for (int c0 = 0; c0 < ((SGB_ABL & SGB_ABL_T_NO_DRAIN) ? 0 : kcols); c0 += 32) {
                 float v[32];
                 tmem_ld_32x32(taddr + (uint32_t)c0, v);          // lane = row of D, registers = 32 consecutive columns
 #pragma unroll
@@ -1118,7 +1130,7 @@ struct HPlan {
 // m-tiles to keep 74 pairs busy; SGB_F16_PAIR=0 / 1 overrides (experiments)
 static bool h_pair_wanted(int64_t m, int n) {
     if (const char* e = getenv("SGB_F16_PAIR")) return atoi(e) != 0 && n % 16 == 0 && n >= 32;
-    return n % 32 == 0 && n >= 128 && m >= 32768;
+    return n % 32 == 0 && m >= 32768;
 }
 
 static HPlan h_plan(int n, int k, bool pair = false) {
@@ -1218,7 +1230,7 @@ int gemm_f16_launch(const GemmArgs& g, const float* a_amax, void* ws, size_t ws_
 
 // ---- weight gradient ----
 struct TPlan {
-    int bk, k_tiles, n_tiles, stages, splits, acc_stride, gbox, abox;
+    int bk, k_tiles, n_tiles, stages, raw_stages, splits, acc_stride, gbox, abox;
     int64_t m_per_split;
     size_t smem_bytes, ws_bytes;
     uint32_t tmem_cols;
@@ -1234,9 +1246,14 @@ static TPlan t_plan(int64_t m, int n, int k) {
     p.gbox = n < kTBM ? n : kTBM;
     p.abox = k < p.bk ? k : p.bk;
     int raw = (kTBV * (p.gbox + p.abox) * 4 + 127) / 128 * 128;
-    int st = (kHSmemBudget - 256 - kTEpiBytes - kTRawStages * raw) / sb;
+    int st = (kHSmemBudget - kTBarBytes - kTEpiBytes - kTRawStages * raw) / sb;
     p.stages = st > 4 ? 4 : st;
-    p.smem_bytes = (size_t)kTRawStages * raw + (size_t)p.stages * sb + 256 + kTEpiBytes;
+    // The raw ring is what hides the HBM latency: bytes in flight per SM = raw_stages x box bytes.  The narrow layers have 2.5 - 12 KB
+    // boxes (32 vertices x (n + k) floats), so two stages left them latency-bound (~0.17 ms whatever the shape): as deep as fits, <= 8.
+    int rs = (kHSmemBudget - kTBarBytes - kTEpiBytes - p.stages * sb) / raw;
+    p.raw_stages = rs > kTMaxRawStages ? kTMaxRawStages : (rs < kTRawStages ? kTRawStages : rs);
+    if (const char* e = getenv("SGB_TN_RAW")) { int v = atoi(e); if (v >= 2 && v <= p.raw_stages) p.raw_stages = v; }
+    p.smem_bytes = (size_t)p.raw_stages * raw + (size_t)p.stages * sb + kTBarBytes + kTEpiBytes;
     int tiles = p.k_tiles * p.n_tiles;
     int64_t want = num_sms() / tiles;
     if (want < 1) want = 1;
@@ -1290,7 +1307,7 @@ int gemm_tn_f16_launch(const float* g, int64_t ldg, const float* a, int64_t lda,
         t.gbox = p.gbox; t.abox = p.abox;
     }
     t.g = g; t.ldg = ldg; t.a = a; t.lda = lda; t.g_amax = g_amax; t.a_amax = a_amax; t.partial = partial; t.m = m; t.n = n; t.k = k;
-    t.bk = p.bk; t.k_tiles = p.k_tiles; t.stages = p.stages; t.m_per_split = p.m_per_split; t.tmem_cols = p.tmem_cols; t.acc_stride = p.acc_stride;
+    t.bk = p.bk; t.k_tiles = p.k_tiles; t.stages = p.stages; t.raw_stages = p.raw_stages; t.m_per_split = p.m_per_split; t.tmem_cols = p.tmem_cols; t.acc_stride = p.acc_stride;
     dim3 grid((unsigned)(p.n_tiles * p.k_tiles), (unsigned)p.splits);
     k_gemm_tn_f16<<<grid, kTThreads, p.smem_bytes, stream>>>(t);
     SGB_CHECK_LAUNCH("k_gemm_tn_f16");
