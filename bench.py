@@ -694,6 +694,23 @@ def partition_block(args, rank, world, local_rank):
 # ------------------------------------------------------------------------------------------
 # extra blocks of the default line: BASELINE.json configs[0], [1], [4]
 # ------------------------------------------------------------------------------------------
+def graph_step_block(args, dev, reps: int = 10):
+    """The headline step (same mesh, network, losses, optimizer) replayed as ONE CUDA graph (semigcn_b200/graphed.py): the narrow
+    encoder / decoder layers of the eager step are launch-bound (20-80 us kernels behind ~60 us of Python per launch); the replay
+    shows the step without those gaps.  Inputs (mask column) are copied into the graph's static buffers every step."""
+    from semigcn_b200.graphed import GraphedTrainStep
+    from semigcn_b200.networks import SingleScaleGCN
+    prob = make_problem(args.freq, dev, seed=314, order=args.mesh_order)
+    mesh = prob["mesh"]
+    torch.manual_seed(314)
+    net = SingleScaleGCN(dev, conv=args.conv).to(dev)
+    opt = torch.optim.Adam(net.parameters(), lr=0.01, capturable=True)
+    g = GraphedTrainStep(net, lambda o: step_losses(o, prob), opt, prob["z1"], prob["x_pos"], mesh.edge_index, prob["dms"][:, 0:1].contiguous())
+    ms, _ = _time_steps(lambda i: g(prob["dms"][:, i % 8:i % 8 + 1]), reps, 3, torch.cuda.synchronize)
+    return {"vertices": mesh.num_vertices, "directed_edges": mesh.nnz, "ms_per_step": ms / reps, "train_steps_per_s": 1e3 * reps / ms,
+            "edges_per_s": float(mesh.nnz) * N_LAYERS * reps / (ms / 1e3), "kernels_per_step": g.launches_per_replay}
+
+
 def small_mesh_block(args, dev, freq: int = 32, reps: int = 20):
     """configs[0] / configs[1] sizes (the reference's own meshes: 10-30 k vertices), one GPU: the SGCN step with the live
     conv of the reference (ChebConv, util/networks.py:13) and with GCNConv, and the MGCN step (util/meshnet.py mirror on a
@@ -974,6 +991,9 @@ def main():
             guarded("partition", lambda: partition_block(args, rank, world, local_rank))
         guarded("batch64", lambda: batch64_block(args, rank, world, local_rank))
         if world == 1:
+            guarded("cuda_graph_step", lambda: graph_step_block(args, torch.device(f"cuda:{local_rank}")))
+            ops.clear_graph_cache()
+            torch.cuda.empty_cache()
             guarded("small_meshes", lambda: small_mesh_block(args, torch.device(f"cuda:{local_rank}")))
             guarded("mesh_order_morton", lambda: mesh_order_block(args, torch.device(f"cuda:{local_rank}")))
         if line is not None:
