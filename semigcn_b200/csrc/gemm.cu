@@ -24,7 +24,9 @@ bool gemm_tn_pair_ok(int64_t m, int n, int k);
 size_t gemm_tn_pair_workspace(int64_t m, int n, int k);
 int gemm_tn_pair_launch(const float* g, int64_t ldg, const float* a, int64_t lda, const float* g_amax, const float* a_amax, float* d,
                         int64_t ldd, int64_t m, int n, int k, int accumulate, void* ws, size_t ws_bytes, cudaStream_t stream);
-static bool tn_tc_worthwhile(int64_t m, int n, int k) { return n >= 64 && k >= 32 && m >= 4096; }
+// (998 562 rows, two alternating converter groups for the narrow stages: 32x64 0.130 ms against 0.241 on the CUDA-core split-K kernel,
+// 32x16 0.122 / 0.159, 16x32 and below equal -- tools/bench_small_shapes.py)
+static bool tn_tc_worthwhile(int64_t m, int n, int k) { return n >= 32 && k >= 16 && m >= 4096; }
 
 // auto policy: the tensor pipe only where the transform is a real dense contraction
 // (measured on 998 562 rows: n32_k64 0.195 ms on the CUDA-core tiles, 0.085 ms on the fp16-split CTA pairs; n32_k16 0.087 / 0.071;

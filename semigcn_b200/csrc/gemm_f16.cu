@@ -639,6 +639,7 @@ struct TArgs {
     int64_t m; int n; int k;
     int bk;                           // UMMA N: columns of D per CTA (multiple of 16, <= 256)
     int k_tiles; int stages; int raw_stages;
+    int conv_groups;                  // 1: all 384 converter threads take every stage; 2: two groups of 192 alternate stages (narrow shapes)
     int64_t m_per_split;              // multiple of kTBV
     uint32_t tmem_cols; int acc_stride;
 };
@@ -664,7 +665,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const __grid_const
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < t.stages; ++s) {
-            mbar_init(&full[s], kTProducerWarps * 32);
+            mbar_init(&full[s], kTProducerWarps * 32 / t.conv_groups);
             mbar_init(&empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -673,7 +674,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const __grid_const
         }
         for (uint32_t s = 0; s < raw_stages; ++s) {
             mbar_init(&rfull[s], 1);
-            mbar_init(&rempty[s], kTProducerWarps * 32);
+            mbar_init(&rempty[s], kTProducerWarps * 32 / t.conv_groups);
         }
         fence_barrier_init();
     }
@@ -697,22 +698,43 @@ __global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const __grid_const
         // converter item: 8 consecutive vertices (core column mg) x 4 consecutive columns (float4 index c4) of G
         // (threads 0..127) or of A (threads 128..383), read from the raw fp32 stage; the 8 x 4 register block is four
         // 16-byte K-major rows after conversion (the transposition happens in registers)
+        // Narrow shapes (gbox + abox <= 192 columns): the stage is too small to keep 384 threads busy and the kernel sits on the
+        // length of ONE converter chain per stage (wait -> load -> convert -> fence -> wait -> store -> fence -> arrive, ~0.8 us
+        // whatever the shape); two groups of 192 threads alternate stages, so two chains are in flight.
         const int tid = threadIdx.x;
-        const bool is_g = tid < 128;
-        const int idx = is_g ? tid : tid - 128;
-        const int per_mg = is_g ? 32 : 64;
-        const int mg = idx / per_mg, c4 = idx % per_mg;
+        const int groups = t.conv_groups, gthreads = kTProducerWarps * 32 / groups;
+        const int grp = tid / gthreads, lt = tid - grp * gthreads;
+        bool is_g, active = true;
+        int mg, c4;
+        if (groups == 1) {
+            is_g = tid < 128;
+            const int idx = is_g ? tid : tid - 128;
+            const int per_mg = is_g ? 32 : 64;
+            mg = idx / per_mg; c4 = idx % per_mg;
+        } else {
+            const int qg = t.gbox >> 2, qa = t.abox >> 2;            // float4 items per 8-vertex core column
+            is_g = lt < 4 * qg;
+            const int la = is_g ? lt : lt - 4 * qg;
+            const int q = is_g ? qg : qa;
+            active = la < 4 * q;
+            mg = active ? la / q : 0; c4 = active ? la % q : 0;
+        }
         const int box = is_g ? t.gbox : t.abox;
-        const bool col_ok = c4 * 4 < box;                                 // inside the TMA box (zero-filled past n / k)
-        const bool in_tile = c4 * 4 < (is_g ? kTBM : t.bk);               // inside the operand tile the tensor core reads
+        const bool col_ok = active && c4 * 4 < box;                       // inside the TMA box (zero-filled past n / k)
+        const bool in_tile = active && c4 * 4 < (is_g ? kTBM : t.bk);     // inside the operand tile the tensor core reads
         const float sc = is_g ? sg : sa;
         const uint32_t raw_off = (is_g ? 0u : (uint32_t)raw_g_bytes) + (uint32_t)(mg * 8) * (uint32_t)box * 4u + (uint32_t)c4 * 16u;
         const uint32_t tile_off = is_g ? 0u : (uint32_t)(2 * kTGTile);
         const uint32_t lo_off = is_g ? (uint32_t)kTGTile : (uint32_t)a_tile_bytes;
         // rows 4*c4 .. 4*c4+3 of the operand tile, core column mg
         const uint32_t base_off = tile_off + (uint32_t)((c4 * 4) >> 3) * kTSbo + (uint32_t)mg * kTLbo + (uint32_t)((c4 * 4) & 7) * 16;
-        uint32_t s = 0, ph = 0, rs = 0, rph = 0;         // ring positions / phases carried incrementally (no division by a runtime stage count)
-        for (int it = 0; it < chunks; ++it) {
+        // ring positions / phases carried incrementally (no division by a runtime stage count in the loop)
+        const uint32_t ug = (uint32_t)groups, ustages = (uint32_t)t.stages;
+        uint32_t s = (uint32_t)grp % ustages, ph = ((uint32_t)grp / ustages) & 1u, rs = (uint32_t)grp % raw_stages, rph = ((uint32_t)grp / raw_stages) & 1u;
+        for (int it = grp; it < chunks; it += groups) {
+            // two groups: the slot's previous user may be the OTHER group and TMA completions are unordered -- wait for that use's
+            // release before testing rfull (parity aliasing, see k_gemm_f16)
+            if (groups == 2) mbar_wait(&rempty[rs], rph ^ 1);
             mbar_wait(&rfull[rs], rph);
             const uint8_t* raw = raw_base + (size_t)rs * raw_bytes + raw_off;
             uint4 h[4], l[4];
@@ -750,8 +772,10 @@ __global__ void __launch_bounds__(kTThreads, 1) k_gemm_tn_f16(const __grid_const
             }
             fence_proxy_async();
             mbar_arrive(&full[s]);
-            if (++s == (uint32_t)t.stages) { s = 0; ph ^= 1; }
-            if (++rs == raw_stages) { rs = 0; rph ^= 1; }
+            s += ug;
+            if (s >= ustages) { s -= ustages; ph ^= 1; }
+            rs += ug;
+            if (rs >= raw_stages) { rs -= raw_stages; rph ^= 1; }
         }
     } else if (warp == kTProducerWarps + 1 + kTDrainWarps) {
         // ================= loader: one lane streams the raw G and A boxes of each 32-vertex stage (TMA 2-D, zero fill) =================
@@ -1230,7 +1254,7 @@ int gemm_f16_launch(const GemmArgs& g, const float* a_amax, void* ws, size_t ws_
 
 // ---- weight gradient ----
 struct TPlan {
-    int bk, k_tiles, n_tiles, stages, raw_stages, splits, acc_stride, gbox, abox;
+    int bk, k_tiles, n_tiles, stages, raw_stages, conv_groups, splits, acc_stride, gbox, abox;
     int64_t m_per_split;
     size_t smem_bytes, ws_bytes;
     uint32_t tmem_cols;
@@ -1253,6 +1277,8 @@ static TPlan t_plan(int64_t m, int n, int k) {
     int rs = (kHSmemBudget - kTBarBytes - kTEpiBytes - p.stages * sb) / raw;
     p.raw_stages = rs > kTMaxRawStages ? kTMaxRawStages : (rs < kTRawStages ? kTRawStages : rs);
     if (const char* e = getenv("SGB_TN_RAW")) { int v = atoi(e); if (v >= 2 && v <= p.raw_stages) p.raw_stages = v; }
+    p.conv_groups = (p.gbox + p.abox <= kTProducerWarps * 32 / 2 && p.stages >= 2 && p.raw_stages >= 2) ? 2 : 1;
+    if (const char* e = getenv("SGB_TN_GROUPS")) { if (atoi(e) == 1) p.conv_groups = 1; }
     p.smem_bytes = (size_t)p.raw_stages * raw + (size_t)p.stages * sb + kTBarBytes + kTEpiBytes;
     int tiles = p.k_tiles * p.n_tiles;
     int64_t want = num_sms() / tiles;
@@ -1307,7 +1333,7 @@ int gemm_tn_f16_launch(const float* g, int64_t ldg, const float* a, int64_t lda,
         t.gbox = p.gbox; t.abox = p.abox;
     }
     t.g = g; t.ldg = ldg; t.a = a; t.lda = lda; t.g_amax = g_amax; t.a_amax = a_amax; t.partial = partial; t.m = m; t.n = n; t.k = k;
-    t.bk = p.bk; t.k_tiles = p.k_tiles; t.stages = p.stages; t.raw_stages = p.raw_stages; t.m_per_split = p.m_per_split; t.tmem_cols = p.tmem_cols; t.acc_stride = p.acc_stride;
+    t.bk = p.bk; t.k_tiles = p.k_tiles; t.stages = p.stages; t.raw_stages = p.raw_stages; t.conv_groups = p.conv_groups; t.m_per_split = p.m_per_split; t.tmem_cols = p.tmem_cols; t.acc_stride = p.acc_stride;
     dim3 grid((unsigned)(p.n_tiles * p.k_tiles), (unsigned)p.splits);
     k_gemm_tn_f16<<<grid, kTThreads, p.smem_bytes, stream>>>(t);
     SGB_CHECK_LAUNCH("k_gemm_tn_f16");

@@ -313,7 +313,7 @@ def colsum(gmat: Tensor, out: Optional[Tensor] = None, accumulate: bool = False,
 def tensor_core_likely(m: int, cin: int, cout: int) -> bool:
     """Mirror of the engine policy in csrc/gemm.cu (tc_worthwhile / tn_tc_worthwhile): will the dX GEMM [m, cout] x
     [cout, cin] or the dW GEMM of a layer go to the fp16-split tensor-core engine (which wants max|operand|)?"""
-    return m >= 2048 and ((cin >= 32 and cout >= 16) or (cout >= 64 and cin >= 32))
+    return m >= 2048 and ((cin >= 32 and cout >= 16) or (cout >= 32 and cin >= 16))
 
 
 def amax(x: Tensor) -> Optional[Tensor]:

@@ -346,7 +346,9 @@ def test_gemm_tensor_core_prologue_and_wide_dynamic_range():
 
 
 @pytest.mark.parametrize("m,n,k", [(5000, 128, 64), (4097, 64, 32), (30000, 256, 256), (2500, 132, 72), (100000, 512, 256),
-                                   (70000, 256, 512), (300, 16, 4), (9000, 64, 128)])
+                                   (70000, 256, 512), (300, 16, 4), (9000, 64, 128),
+                                   # narrow shapes, hundreds of stages per CTA: the two alternating converter groups
+                                   (400000, 32, 64), (300001, 64, 32), (250000, 16, 16), (199999, 48, 36), (350000, 64, 128)])
 @pytest.mark.parametrize("engine", [2, 3])
 def test_gemm_tn_tensor_core_engine(m, n, k, engine):
     """Weight gradient on tcgen05 (split over vertices, fixed-order reduce): 3xTF32 and 2xFP16-split engines."""
