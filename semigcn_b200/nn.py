@@ -172,24 +172,26 @@ class ConvBlockFn(torch.autograd.Function):
                 ctx.op_amax = [x_amax]
             ctx.agg_first = agg_first
         else:
-            ts = [x]
-            amx = [x_amax]
-            if len(weights) > 1:
-                ts.append(ops.spmm(graph, x, amax_out=am[0:1]))
-                amx.append(am[0:1])
-            for k in range(2, len(weights)):
-                slot = am[1:2] if k == 2 else ops.new_amax(x.device)
-                ts.append(ops.spmm(graph, ts[k - 1], alpha=2.0, addend=ts[k - 2], beta=-1.0, amax_out=slot))
-                amx.append(slot)
-            y = None
-            r = None
-            for k, w in enumerate(weights):
-                last = k == len(weights) - 1
-                r = ops.gemm(ts[k], w, transb=True, bias=bias if last else None, out=y, accumulate=k > 0,
-                             want_stats=want_stats and last, a_amax=amx[k])
-                y = r[0] if isinstance(r, tuple) else r
-            saved_ops = ts
-            ctx.op_amax = amx
+            # T1 .. T(K-1) live side by side in ONE [m, (K-1) cin] matrix: Y = x W0^T + [T1 | T2 | ..] [W1 | W2 | ..]^T is then two
+            # transforms instead of K accumulating ones (each of those re-reads and re-writes Y), and the backward pass reads dY
+            # twice instead of K times for the weight gradients and for dT.  The aggregation kernels write / read the column blocks
+            # in place (row stride (K-1) cin); max|.| of the whole block accumulates in one slot over the K - 1 launches.
+            nw = len(weights)
+            cin = x.shape[1]
+            tcat = None
+            if nw > 1:
+                tcat = torch.empty((x.shape[0], (nw - 1) * cin), dtype=torch.float32, device=x.device)
+                tk = [x] + [tcat[:, (k - 1) * cin:k * cin] for k in range(1, nw)]
+                ops.spmm(graph, x, out=tk[1], amax_out=am[0:1])
+                for k in range(2, nw):
+                    ops.spmm(graph, tk[k - 1], alpha=2.0, addend=tk[k - 2], beta=-1.0, out=tk[k], amax_out=am[0:1])
+            one = nw == 1
+            r = ops.gemm(x, weights[0], transb=True, bias=bias if one else None, want_stats=want_stats and one, a_amax=x_amax)
+            if not one:
+                wcat = weights[1] if nw == 2 else torch.cat(list(weights[1:]), dim=1)
+                r = ops.gemm(tcat, wcat, transb=True, bias=bias, out=r, accumulate=True, want_stats=want_stats, a_amax=am[0:1])
+            saved_ops = [x] if one else [x, tcat]
+            ctx.op_amax = [x_amax, am[0:1]]
         y, partials = r if want_stats else (r, None)
 
         ctx.graph, ctx.cfg, ctx.nw, ctx.has_bias = graph, cfg, len(weights), bias is not None
@@ -275,14 +277,24 @@ class ConvBlockFn(torch.autograd.Function):
                 if need_x:
                     dx = ops.gemm(dh, w, transb=False, a_amax=am[1:2])
         else:
-            ts = saved_ops
-            for k in range(nw):
-                dws[k] = ops.gemm_tn(dy, ts[k], g_amax=dy_amax, a_amax=ctx.op_amax[k])
+            x = saved_ops[0]
+            cin = x.shape[1]
+            dws[0] = ops.gemm_tn(dy, x, g_amax=dy_amax, a_amax=ctx.op_amax[0])
+            if nw > 1:
+                tcat = saved_ops[1]
+                dwcat = ops.gemm_tn(dy, tcat, g_amax=dy_amax, a_amax=ctx.op_amax[1])          # [cout, (K-1) cin]
+                for k in range(1, nw):
+                    dws[k] = dwcat[:, (k - 1) * cin:k * cin]
             if need_x:
-                # g_k = dY W_k + a_k S^T g_(k+1) - g_(k+2),  a_k = 2 for k >= 1, 1 for k = 0
+                # g_k = dY W_k + a_k S^T g_(k+1) - g_(k+2),  a_k = 2 for k >= 1, 1 for k = 0;  dY [W1 | W2 | ..] in one transform
+                ds: List[Optional[Tensor]] = [ops.gemm(dy, weights[0], transb=False, a_amax=dy_amax)]
+                if nw > 1:
+                    wcat = weights[1] if nw == 2 else torch.cat(list(weights[1:]), dim=1)
+                    dcat = ops.gemm(dy, wcat, transb=False, a_amax=dy_amax)
+                    ds += [dcat[:, (k - 1) * cin:k * cin] for k in range(1, nw)]
                 gs: List[Optional[Tensor]] = [None] * nw
                 for k in range(nw - 1, -1, -1):
-                    d = ops.gemm(dy, weights[k], transb=False, a_amax=dy_amax)
+                    d = ds[k]
                     if k + 2 <= nw - 1:
                         d = torch.sub(d, gs[k + 2], out=d)
                     if k + 1 <= nw - 1:
