@@ -161,7 +161,13 @@ SGB_API int sgb_gather_rows(const float* x, int64_t ldx, const int32_t* idx, int
  *    max |G|, e.g. from the amax_out of the kernel that produced the operand) save the engine its
  *    own reduction pass over that operand; NULL = computed internally.  Accuracy is norm-relative
  *    (elements > 2^23 below the tensor maximum lose relative precision).  engine 0 picks 3 for
- *    real contractions, 1 for thin ones.
+ *    real contractions (n >= 32, k >= 16), 1 for thin ones.  On large operands (m >= 32 768) engine 3
+ *    runs as clusters of two CTAs (tcgen05 cta_group::2, UMMA M = 256: each CTA stages its own 128
+ *    rows of the activation operand and half of the other operand; sgb_gemm when n % 32 == 0,
+ *    sgb_gemm_tn as `engine` 4 when n % 256 == 0, k % 32 == 0 and k <= 256 or k % 256 == 0 -- engine
+ *    4 may also be requested explicitly from m >= 4096, SGB_ENOTSUP otherwise).  The results of the
+ *    pair and single-CTA variants agree to fp32 rounding of the accumulation order, both are
+ *    deterministic run to run.
  * ------------------------------------------------------------------------------------ */
 SGB_API int sgb_gemm_stat_rows(int64_t m);
 SGB_API size_t sgb_gemm_workspace_bytes(int64_t m, int n, int k, int engine);
