@@ -621,9 +621,9 @@ constexpr int kTGTile = (kTBM / 8) * kTSbo;      // per hi (or lo)
 constexpr int kTProducerWarps = 12;              // 384 threads: one (8 vertices x 4 columns) item each per stage
 constexpr int kTDrainWarps = 4;
 constexpr int kTThreads = (kTProducerWarps + 1 + kTDrainWarps + 1) * 32;   // converters, MMA, drain, TMA loader
-constexpr int kTRawStages = 2;                  // CTA-pair kernel's default is set in its plan; this is the single-CTA minimum
-constexpr int kTMaxRawStages = 8;               // single-CTA kernel: raw (TMA) stages in flight, chosen per shape (TArgs::raw_stages)
-constexpr int kTBarBytes = 512;                 // single-CTA kernel: barrier block between the operand ring and the drain staging
+constexpr int kTRawStages = 2;                   // single-CTA kernel: fewest raw (TMA) stages (the wide shapes, where shared memory is short)
+constexpr int kTMaxRawStages = 8;                // single-CTA kernel: most raw stages in flight, chosen per shape (TArgs::raw_stages)
+constexpr int kTBarBytes = 512;                  // single-CTA kernel: barrier block between the operand ring and the drain staging
 constexpr int kTSegChunks = 16;                  // 512 vertices per TMEM accumulation segment (tensor-core accumulation truncates)
 
 __host__ __device__ constexpr int t_a_tile_bytes(int bk) { return (bk / 8) * kTSbo; }
