@@ -1153,6 +1153,7 @@ struct HPlan {
 // CTA pairs: every n-tile must split into two halves of whole core-matrix rows (ncols % 16 == 0), and there must be enough
 // m-tiles to keep 74 pairs busy; SGB_F16_PAIR=0 / 1 overrides (experiments)
 static bool h_pair_wanted(int64_t m, int n) {
+    if (m <= kHBM) return false;                 // a single m-tile: nothing to pair
     if (const char* e = getenv("SGB_F16_PAIR")) return atoi(e) != 0 && n % 16 == 0 && n >= 32;
     return n % 32 == 0 && m >= 32768;
 }
