@@ -2,14 +2,16 @@
 //
 // Replaces PyG's MessagePassing.propagate (x.index_select(0,row) -> norm.view(-1,1)*x_j ->
 // scatter_add at col), SURVEY.md §3.2 / A.1 step 3 / A.2 step 3, forward and -- on the
-// transpose CSR -- backward.  No [nnz, C] message tensor, no atomics, edge weights recomputed
-// from dis (never stored), neighbour indices staged in registers and broadcast by shuffles.
+// transpose CSR -- backward.  No [nnz, C] message tensor, no atomics.  The normalised edge weights are
+// computed once per edge_index by the graph builder (graph_build.cu, bit-identical to gcn_norm /
+// ChebConv.__norm__) and read as a packed (column, weight) stream in CSR order; the slice of a run of
+// vertices is staged into a warp-private shared-memory buffer with cp.async.
 //
 // Mapping: one sub-warp of LPV lanes per vertex, each lane owns VEC contiguous channels per
 // iteration (128-bit loads when C % 4 == 0), ITERS iterations cover up to LPV*VEC*ITERS
-// channels per pass; persistent grid (multiple of the SM count) with a grid-stride loop over
-// vertices so consecutive vertices are in flight together (their neighbourhoods overlap ->
-// L1/L2 hits; DRAM sees X once).  Up to 8 independent 128-bit gathers in flight per lane.
+// channels per pass; persistent grid, every warp owns runs of consecutive vertices and the co-resident
+// warps sweep one window of X together (their neighbourhoods overlap -> L1/L2 hits; DRAM sees X
+// once).  Up to NB (6 or 8) x ITERS independent 128-bit gathers in flight per lane.
 //
 // Arithmetic order is the reference's: per row, messages in CSR (= edge) order, each
 // msg = fl(w * x_j) with w = fl(dis_j * dis_i), acc = fl(acc + msg); then the self-loop

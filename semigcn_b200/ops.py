@@ -66,7 +66,8 @@ class MeshGraph:
 
     Holds what PyG recomputes in every conv call (gcn_norm / get_laplacian):
     ``rowptr/colidx`` grouped by target in stable edge order, the same grouped by source for
-    the backward pass, and ``dis = deg^-1/2`` (bit-exact).  Edge weights are never stored.
+    the backward pass, ``dis = deg^-1/2`` (bit-exact) and the normalised edge weights packed with the column ids
+    (``edges``: int32 [nnz, 2] = (column, float bits of the weight), the stream the aggregation kernel reads).
     """
 
     def __init__(self, edge_index: Tensor, num_nodes: int, mode: int, with_perm: bool = False):
